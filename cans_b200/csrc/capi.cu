@@ -1,0 +1,605 @@
+// C ABI of cans_b200 (include/cans_b200.h): context, plans, the solve.
+// Host-side orchestration only; all arithmetic lives in the kernels of
+// fft_kernels.cuh / thomas_kernels.cuh / aux_kernels.cuh.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cans_b200.h"
+#include "aux_kernels.cuh"
+#include "fft_kernels.cuh"
+#include "fft_plan.hpp"
+#include "thomas_kernels.cuh"
+
+using namespace cb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(CANSB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t b) {
+    if (b <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    if (cudaMalloc(&p, b) != cudaSuccess) return -1;
+    bytes = b;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+template <class T> struct FftTables {
+  HostFftPlan H;
+  C2<T>*tw = nullptr, *twp = nullptr, *mak = nullptr;
+  uint16_t* rev = nullptr;
+};
+template <class T> struct DirectTables {
+  int Q = 0;
+  C2<T>* cs = nullptr;
+};
+
+struct cansb200_ctx {
+  int ng[3], dims[2], ipencil_axis, rank, nranks, is_fp32;
+  int n[3], lo[3], n_z[3], lo_z[3];
+  size_t esz;
+  DevBuf scratch;   // haloless field buffer A (x pencil)
+  DevBuf staging;   // haloed p when the caller's p is host memory
+  DevBuf coef;      // a, b, c, lambdaxy staged from the host
+  std::map<int, FftTables<double>> tabs64;
+  std::map<int, FftTables<float>> tabs32;
+  std::map<long long, DirectTables<double>> dtabs64;
+  std::map<long long, DirectTables<float>> dtabs32;
+  unsigned long long launches = 0;
+  bool attr_set[16] = {false};
+};
+
+struct cansb200_plan {
+  cansb200_ctx* ctx;
+  char bc[6], cf[3];
+  int kind[2][2];   // [dir][fwd|bwd]
+  int nt[2];        // transform lengths (n - ix, n - iy)
+  int q, periodic_z;
+  cansb200_options opt;
+  // thomas
+  int th_n, th_nn, th_m, th_variant, th_mmax, nslots;
+  long long slot_z, slot_den;
+  DevBuf zcache, p2cache, dencache, state;
+  unsigned long long solves = 0;
+};
+
+template <class T> static std::map<int, FftTables<T>>& tabmap(cansb200_ctx* c);
+template <> std::map<int, FftTables<double>>& tabmap<double>(cansb200_ctx* c) { return c->tabs64; }
+template <> std::map<int, FftTables<float>>& tabmap<float>(cansb200_ctx* c) { return c->tabs32; }
+template <class T> static std::map<long long, DirectTables<T>>& dtabmap(cansb200_ctx* c);
+template <> std::map<long long, DirectTables<double>>& dtabmap<double>(cansb200_ctx* c) { return c->dtabs64; }
+template <> std::map<long long, DirectTables<float>>& dtabmap<float>(cansb200_ctx* c) { return c->dtabs32; }
+
+template <class T> static int get_tables(cansb200_ctx* ctx, int n, FftTables<T>** out) {
+  auto& mp = tabmap<T>(ctx);
+  auto it = mp.find(n);
+  if (it != mp.end()) { *out = &it->second; return 0; }
+  FftTables<T> t;
+  t.H = make_host_plan(n, K_R2HC);  // tables do not depend on the kind
+  if (t.H.fast) {
+    const int M = t.H.M;
+    std::vector<C2<T>> tw(M), twp(M / 2 + 1), mak(M + 1);
+    for (int i = 0; i < M; ++i) tw[i] = {(T)t.H.tw_re[i], (T)t.H.tw_im[i]};
+    for (int i = 0; i <= M / 2; ++i) twp[i] = {(T)t.H.twp_re[i], (T)t.H.twp_im[i]};
+    for (int i = 0; i <= M; ++i) mak[i] = {(T)t.H.mak_re[i], (T)t.H.mak_im[i]};
+    CK(cudaMalloc(&t.tw, sizeof(C2<T>) * (M > 0 ? M : 1)));
+    CK(cudaMalloc(&t.twp, sizeof(C2<T>) * (M / 2 + 1)));
+    CK(cudaMalloc(&t.mak, sizeof(C2<T>) * (M + 1)));
+    CK(cudaMalloc(&t.rev, sizeof(uint16_t) * (M > 0 ? M : 1)));
+    CK(cudaMemcpy(t.tw, tw.data(), sizeof(C2<T>) * M, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.twp, twp.data(), sizeof(C2<T>) * (M / 2 + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.mak, mak.data(), sizeof(C2<T>) * (M + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.rev, t.H.rev.data(), sizeof(uint16_t) * M, cudaMemcpyHostToDevice));
+  }
+  auto res = mp.emplace(n, t);
+  *out = &res.first->second;
+  return 0;
+}
+
+template <class T> static int get_direct_tables(cansb200_ctx* ctx, int n, int kind, DirectTables<T>** out) {
+  auto& mp = dtabmap<T>(ctx);
+  const int Q = slow_Q(n, kind);
+  auto it = mp.find(Q);
+  if (it != mp.end()) { *out = &it->second; return 0; }
+  DirectTables<T> t;
+  t.Q = Q;
+  std::vector<C2<T>> cs(2 * (size_t)Q);
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (long long m = 0; m < 2LL * Q; ++m) cs[m] = {(T)cosl(pi * m / Q), (T)sinl(pi * m / Q)};
+  CK(cudaMalloc(&t.cs, sizeof(C2<T>) * cs.size()));
+  CK(cudaMemcpy(t.cs, cs.data(), sizeof(C2<T>) * cs.size(), cudaMemcpyHostToDevice));
+  auto res = mp.emplace(Q, t);
+  *out = &res.first->second;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// one batched r2r launch.  ymode: lines are `lines_per_group` consecutive
+// elements (stride ls) and the transform runs with element stride es.
+struct R2RGeom {
+  long long in_es, out_es, in_ls, out_ls, in_gs, out_gs;
+  int lines_per_group, ngroups, line_len, ymode;
+};
+
+template <class T>
+static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, const R2RGeom& g, int tile_hint,
+                   cudaStream_t st) {
+  if (nt < 1 || g.lines_per_group < 1 || g.ngroups < 1) return 0;
+  FftTables<T>* tb;
+  int rc = get_tables<T>(ctx, nt, &tb);
+  if (rc) return rc;
+  if (tb->H.fast && kind_is_fast(kind)) {
+    FftArgs<T> A;
+    A.P.n = nt; A.P.M = tb->H.M; A.P.kind = kind; A.P.nstages = (int)tb->H.radix.size();
+    int rmax = 1;
+    for (int s = 0; s < A.P.nstages; ++s) { A.P.radix[s] = tb->H.radix[s]; if (tb->H.radix[s] > rmax) rmax = tb->H.radix[s]; }
+    A.P.tw = tb->tw; A.P.twp = tb->twp; A.P.mak = tb->mak; A.P.rev = tb->rev;
+    A.in = in; A.out = out;
+    A.in_es = g.in_es; A.out_es = g.out_es; A.in_ls = g.in_ls; A.out_ls = g.out_ls; A.in_gs = g.in_gs; A.out_gs = g.out_gs;
+    A.lines_per_group = g.lines_per_group; A.ngroups = g.ngroups; A.line_len = g.line_len; A.ymode = g.ymode;
+    const int nthr = 256;
+    const size_t cap = 64 * 1024;
+    if (g.ymode) {
+      int cx = tile_hint > 0 ? tile_hint : 16;
+      while (cx > 4 && (size_t)nt * cx * sizeof(T) > cap) cx /= 2;
+      A.tile_lines = cx;
+    } else {
+      const size_t line_b = (size_t)LayX::line_len(A.P.M) * sizeof(T);
+      long long nl = tile_hint > 0 ? tile_hint : ((long long)nthr * rmax + A.P.M - 1) / (A.P.M > 0 ? A.P.M : 1);
+      if (nl * (long long)line_b > (long long)cap) nl = cap / line_b;
+      if (nl > 1024) nl = 1024;
+      if (nl < 1) nl = 1;
+      A.tile_lines = (int)nl;
+    }
+    const size_t smem = tile_smem_elems(A) * sizeof(T);
+    if (smem > 200 * 1024) return fail(CANSB200_EUNSUPPORTED, "r2r: line too long for the shared-memory tile");
+    const long long ntiles = num_tiles(A);
+    const unsigned grid = (unsigned)(ntiles < 0x7fffffffLL ? ntiles : 0x7fffffffLL);
+    if (g.ymode) {
+      auto kfn = fft_tile_kernel<T, LayY>;
+      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      kfn<<<grid, nthr, smem, st>>>(A, ntiles);
+    } else {
+      auto kfn = fft_tile_kernel<T, LayX>;
+      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      kfn<<<grid, nthr, smem, st>>>(A, ntiles);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  // direct O(n^2) evaluation
+  DirectTables<T>* dt;
+  rc = get_direct_tables<T>(ctx, nt, kind, &dt);
+  if (rc) return rc;
+  DirectArgs<T> D;
+  D.n = nt; D.kind = kind; D.Q = dt->Q; D.cs = dt->cs; D.in = in; D.out = out;
+  D.in_es = g.in_es; D.out_es = g.out_es; D.in_ls = g.in_ls; D.out_ls = g.out_ls; D.in_gs = g.in_gs; D.out_gs = g.out_gs;
+  D.lines_per_group = g.lines_per_group; D.ngroups = g.ngroups; D.line_len = g.line_len;
+  const size_t smem = (size_t)g.line_len * sizeof(T);
+  if (smem > 200 * 1024) return fail(CANSB200_EUNSUPPORTED, "r2r(direct): line too long");
+  auto kfn = r2r_direct_kernel<T>;
+  CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const long long nlines = (long long)g.lines_per_group * g.ngroups;
+  kfn<<<(unsigned)nlines, 128, smem, st>>>(D);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// thomas
+template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int nx, int ny, long long sj, long long sk,
+                                                   int n_rows, int periodic, const T* lam, const T* a, const T* b, const T* c) {
+  ThomasDev<T> D;
+  D.nx = nx; D.ny = ny; D.n = n_rows; D.periodic = periodic; D.nn = periodic ? n_rows - 1 : n_rows;
+  D.sj = sj; D.sk = sk; D.a = a; D.b = b; D.c = c; D.lam = lam; D.lam_sj = nx;
+  D.m = pl->th_m; D.chunk_layout = pl->th_variant == 1;
+  return D;
+}
+
+template <class T, int MMAX>
+static int launch_warp(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, cudaStream_t st) {
+  constexpr int CX = 8;
+  auto kfn = thomas_warp_kernel<T, MMAX, CX>;
+  const size_t smem = ((size_t)CX * thomas_kp(D.m) + 2 * 32 * MMAX) * sizeof(T);
+  CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const long long tiles = (long long)((D.nx + CX - 1) / CX) * D.ny;
+  kfn<<<(unsigned)tiles, 32 * CX, smem, st>>>(D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
+                                             (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <class T>
+static int run_gaussel(cansb200_plan* pl, T* p, int nx, int ny, long long sj, long long sk, int n_rows, int periodic, T norm,
+                       const T* lam, const T* a, const T* b, const T* c, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  if (n_rows != pl->th_n || periodic != pl->periodic_z)
+    return fail(CANSB200_EINVAL, "gaussel: n_rows / periodicity differ from the plan's");
+  if (pl->th_nn < 1) return fail(CANSB200_EINVAL, "gaussel: empty system");
+  ThomasDev<T> D = make_thomas<T>(pl, nx, ny, sj, sk, n_rows, periodic, lam, a, b, c);
+  CacheState* cs = (CacheState*)pl->state.p;
+  const long long ncol = (long long)nx * ny;
+  {
+    const long long total = 3LL * D.n + ncol;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    thomas_hash_kernel<T><<<blocks, 256, 0, st>>>(D, cs);
+    thomas_select_kernel<<<1, 32, 0, st>>>(cs);
+    thomas_factor_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(D, cs, (T*)pl->zcache.p, (T*)pl->p2cache.p,
+                                                                          (T*)pl->dencache.p, pl->slot_z, pl->slot_den);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+  }
+  if (pl->th_variant == 1) {
+    switch (pl->th_mmax) {
+      case 4: return launch_warp<T, 4>(ctx, D, pl, p, norm, st);
+      case 8: return launch_warp<T, 8>(ctx, D, pl, p, norm, st);
+      case 16: return launch_warp<T, 16>(ctx, D, pl, p, norm, st);
+      case 24: return launch_warp<T, 24>(ctx, D, pl, p, norm, st);
+      default: return launch_warp<T, 32>(ctx, D, pl, p, norm, st);
+    }
+  }
+  thomas_seq_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(D, cs, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
+                                                                     (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+static void find_fft(char b0, char b1, char cf, int& kf, int& kb, double& n1, double& n2) {
+  // src/fft.f90:260-313
+  const std::string key{b0, b1};
+  n1 = 2.0; n2 = 0.0;
+  if (key == "PP") { kf = K_R2HC; kb = K_HC2R; n1 = 1.0; return; }
+  if (cf == 'c') {
+    if (key == "NN") { kf = K_REDFT10; kb = K_REDFT01; }
+    else if (key == "DD") { kf = K_RODFT10; kb = K_RODFT01; }
+    else if (key == "ND") { kf = K_REDFT11; kb = K_REDFT11; }
+    else { kf = K_RODFT11; kb = K_RODFT11; }
+  } else {
+    if (key == "NN") { kf = K_REDFT00; kb = K_REDFT00; n2 = -1.0; }
+    else if (key == "DD") { kf = K_RODFT00; kb = K_RODFT00; n2 = 1.0; }
+    else if (key == "ND") { kf = K_REDFT10; kb = K_REDFT01; }
+    else { kf = K_RODFT01; kb = K_RODFT10; }
+  }
+}
+
+extern "C" {
+
+const char* cansb200_last_error(void) { return g_err.c_str(); }
+int cansb200_version(void) { return 100; }
+
+int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ipencil_axis, int rank, int nranks,
+                  const void* nccl_id, int is_fp32) {
+  (void)nccl_id;
+  if (!out || !ng || !dims) return fail(CANSB200_EINVAL, "init: null argument");
+  if (ng[0] < 1 || ng[1] < 1 || ng[2] < 1) return fail(CANSB200_EINVAL, "init: ng must be positive");
+  if (ipencil_axis != 1) return fail(CANSB200_EUNSUPPORTED, "init: only ipencil_axis = 1 (x pencils) is implemented");
+  if (nranks != 1 || dims[0] != 1 || dims[1] != 1)
+    return fail(CANSB200_EUNSUPPORTED, "init: multi-rank contexts are created with cansb200_init_dist");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return fail(CANSB200_ECUDA, "init: no CUDA device");
+  auto* c = new cansb200_ctx();
+  for (int d = 0; d < 3; ++d) { c->ng[d] = ng[d]; c->n[d] = ng[d]; c->lo[d] = 1; c->n_z[d] = ng[d]; c->lo_z[d] = 1; }
+  c->dims[0] = dims[0]; c->dims[1] = dims[1]; c->ipencil_axis = ipencil_axis; c->rank = rank; c->nranks = nranks;
+  c->is_fp32 = is_fp32 ? 1 : 0;
+  c->esz = is_fp32 ? 4 : 8;
+  const size_t nel = (size_t)c->n[0] * c->n[1] * c->n[2];
+  if (c->scratch.ensure(nel * c->esz)) { delete c; return fail(CANSB200_ENOMEM, "init: scratch allocation failed"); }
+  *out = c;
+  return 0;
+}
+
+int cansb200_finalize(cansb200_ctx* c) {
+  if (!c) return 0;
+  c->scratch.release(); c->staging.release(); c->coef.release();
+  for (auto& kv : c->tabs64) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
+  for (auto& kv : c->tabs32) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
+  for (auto& kv : c->dtabs64) cudaFree(kv.second.cs);
+  for (auto& kv : c->dtabs32) cudaFree(kv.second.cs);
+  delete c;
+  return 0;
+}
+
+int cansb200_get_extents(const cansb200_ctx* c, int n[3], int lo[3], int n_z[3], int lo_z[3]) {
+  if (!c) return fail(CANSB200_EINVAL, "null ctx");
+  for (int d = 0; d < 3; ++d) {
+    if (n) n[d] = c->n[d];
+    if (lo) lo[d] = c->lo[d];
+    if (n_z) n_z[d] = c->n_z[d];
+    if (lo_z) lo_z[d] = c->lo_z[d];
+  }
+  return 0;
+}
+
+int cansb200_get_work(cansb200_ctx* c, int which, void** ptr, size_t* nelem) {
+  if (!c || !ptr) return fail(CANSB200_EINVAL, "null argument");
+  if (which != 0) return fail(CANSB200_EINVAL, "get_work: only buffer 0 exists");
+  *ptr = c->scratch.p;
+  if (nelem) *nelem = c->scratch.bytes / c->esz;
+  return 0;
+}
+
+int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6], const char cf[3],
+                         const cansb200_options* opt, double* normfft_out) {
+  if (!ctx || !out || !bc || !cf) return fail(CANSB200_EINVAL, "plan_create: null argument");
+  for (int i = 0; i < 6; ++i)
+    if (bc[i] != 'P' && bc[i] != 'D' && bc[i] != 'N') return fail(CANSB200_EINVAL, "plan_create: bc must be P, D or N");
+  for (int d = 0; d < 3; ++d) {
+    if (cf[d] != 'c' && cf[d] != 'f') return fail(CANSB200_EINVAL, "plan_create: c_or_f must be c or f");
+    if ((bc[2 * d] == 'P') != (bc[2 * d + 1] == 'P')) return fail(CANSB200_EINVAL, "plan_create: periodic BCs must come in pairs");
+  }
+  auto pl = std::unique_ptr<cansb200_plan>(new cansb200_plan());
+  pl->ctx = ctx;
+  memcpy(pl->bc, bc, 6);
+  memcpy(pl->cf, cf, 3);
+  cansb200_options o;
+  for (int* q = (int*)&o; q < (int*)(&o + 1); ++q) *q = -1;
+  if (opt) o = *opt;
+  pl->opt = o;
+  // fftini, src/fft.f90:76-208
+  double normfft = 1.0;
+  for (int d = 0; d < 2; ++d) {
+    double n1, n2;
+    find_fft(bc[2 * d], bc[2 * d + 1], cf[d], pl->kind[d][0], pl->kind[d][1], n1, n2);
+    const int ii = (bc[2 * d] == 'D' && bc[2 * d + 1] == 'D' && cf[d] == 'f') ? 1 : 0;
+    pl->nt[d] = ctx->ng[d] - ii;
+    if (pl->nt[d] < 1) return fail(CANSB200_EINVAL, "plan_create: transform length < 1");
+    normfft *= n1 * (ctx->ng[d] + n2 - ii);
+  }
+  normfft = 1.0 / normfft;
+  if (normfft_out) *normfft_out = ctx->is_fp32 ? (double)(1.0f / (float)(1.0 / normfft)) : normfft;
+  // z solve geometry, src/solver.f90:77-82
+  pl->q = (cf[2] == 'f' && bc[5] == 'D') ? 1 : 0;
+  pl->periodic_z = (bc[4] == 'P' && bc[5] == 'P') ? 1 : 0;
+  pl->th_n = ctx->ng[2] - pl->q;
+  pl->th_nn = pl->periodic_z ? pl->th_n - 1 : pl->th_n;
+  if (pl->th_nn < 1) return fail(CANSB200_EINVAL, "plan_create: z system is empty");
+  pl->th_m = (pl->th_nn + 31) / 32;
+  int variant = o.thomas_variant >= 0 ? o.thomas_variant : 1;
+  if (pl->th_m > 32) variant = 0;
+  pl->th_variant = variant;
+  pl->th_mmax = pl->th_m <= 4 ? 4 : pl->th_m <= 8 ? 8 : pl->th_m <= 16 ? 16 : pl->th_m <= 24 ? 24 : 32;
+  pl->nslots = o.cache_slots >= 1 ? (o.cache_slots > CB_MAX_SLOTS ? CB_MAX_SLOTS : o.cache_slots) : 1;
+  const long long ncol = (long long)ctx->n_z[0] * ctx->n_z[1];
+  pl->slot_z = variant == 1 ? ncol * pl->th_m * 32 : ncol * pl->th_nn;
+  pl->slot_den = ncol;
+  if (pl->zcache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: pivot cache");
+  if (pl->periodic_z) {
+    if (pl->p2cache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: p2 cache");
+    if (pl->dencache.ensure((size_t)pl->slot_den * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: den cache");
+  }
+  if (pl->state.ensure(sizeof(CacheState))) return fail(CANSB200_ENOMEM, "plan_create: cache state");
+  CacheState cs;
+  memset(&cs, 0, sizeof(cs));
+  cs.nslots = pl->nslots;
+  CK(cudaMemcpy(pl->state.p, &cs, sizeof(cs), cudaMemcpyHostToDevice));
+  // build the transform tables now so that the first solve does not allocate
+  for (int d = 0; d < 2; ++d) {
+    int rc;
+    if (ctx->is_fp32) { FftTables<float>* t; rc = get_tables<float>(ctx, pl->nt[d], &t); }
+    else { FftTables<double>* t; rc = get_tables<double>(ctx, pl->nt[d], &t); }
+    if (rc) return rc;
+  }
+  *out = pl.release();
+  return 0;
+}
+
+int cansb200_plan_destroy(cansb200_plan* pl) {
+  if (!pl) return 0;
+  pl->zcache.release(); pl->p2cache.release(); pl->dencache.release(); pl->state.release();
+  delete pl;
+  return 0;
+}
+
+int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
+  if (!pl || !stats) return fail(CANSB200_EINVAL, "null argument");
+  CacheState cs;
+  CK(cudaMemcpy(&cs, pl->state.p, sizeof(cs), cudaMemcpyDeviceToHost));
+  stats[0] = pl->solves; stats[1] = cs.nfactor; stats[2] = pl->ctx->launches; stats[3] = (unsigned long long)pl->th_variant;
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+template <class T>
+static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double normfft, const void* lam_any, const void* a_any,
+                      const void* b_any, const void* c_any, int mem_kind, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  const int nx = n[0], ny = n[1], nz = n[2];
+  const long long px = nx + 2, py = ny + 2;          // haloed pitches
+  const size_t nh = (size_t)px * py * (nz + 2);
+  T* p = (T*)p_any;
+  const T *lam = (const T*)lam_any, *a = (const T*)a_any, *b = (const T*)b_any, *c = (const T*)c_any;
+  if (mem_kind == CANSB200_MEM_HOST) {
+    if (ctx->staging.ensure(nh * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: staging");
+    const size_t ncoef = 3 * (size_t)nz + (size_t)nx * ny;
+    if (ctx->coef.ensure(ncoef * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: coefficient staging");
+    T* cf = (T*)ctx->coef.p;
+    CK(cudaMemcpyAsync(ctx->staging.p, p_any, nh * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf, a_any, nz * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf + nz, b_any, nz * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf + 2 * nz, c_any, nz * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf + 3 * nz, lam_any, (size_t)nx * ny * sizeof(T), cudaMemcpyHostToDevice, st));
+    p = (T*)ctx->staging.p;
+    a = cf; b = cf + nz; c = cf + 2 * nz; lam = cf + 3 * nz;
+  }
+  T* A = (T*)ctx->scratch.p;
+  T* pin = p + (px * py + px + 1);  // p(1,1,1)
+  int rc;
+  // forward x: p (haloed) -> A
+  R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nz, nx, 0};
+  rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
+  if (rc) return rc;
+  // forward y, in place in A
+  R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nz, ny, 1};
+  rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
+  if (rc) return rc;
+  // tridiagonal solve in z
+  rc = run_gaussel<T>(pl, A, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, (T)normfft, lam, a, b, c, st);
+  if (rc) return rc;
+  // backward y, backward x
+  rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
+  if (rc) return rc;
+  R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nz, nx, 0};
+  rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
+  if (rc) return rc;
+  if (mem_kind == CANSB200_MEM_HOST) {
+    CK(cudaMemcpyAsync(p_any, ctx->staging.p, nh * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  pl->solves++;
+  return 0;
+}
+
+extern "C" {
+
+int cansb200_solve(cansb200_plan* pl, void* p, const int n[3], int nhalo, double normfft, const void* lambdaxy,
+                   const void* a, const void* b, const void* c, int mem_kind, void* stream) {
+  if (!pl || !p || !n || !lambdaxy || !a || !b || !c) return fail(CANSB200_EINVAL, "solve: null argument");
+  if (nhalo != 1) return fail(CANSB200_EINVAL, "solve: nhalo must be 1");
+  cansb200_ctx* ctx = pl->ctx;
+  for (int d = 0; d < 3; ++d)
+    if (n[d] != ctx->n[d]) return fail(CANSB200_EINVAL, "solve: n differs from the context's local extents");
+  if (mem_kind != CANSB200_MEM_HOST && mem_kind != CANSB200_MEM_DEVICE) return fail(CANSB200_EINVAL, "solve: bad mem_kind");
+  cudaStream_t st = (cudaStream_t)stream;
+  return ctx->is_fp32 ? solve_impl<float>(pl, p, n, normfft, lambdaxy, a, b, c, mem_kind, st)
+                      : solve_impl<double>(pl, p, n, normfft, lambdaxy, a, b, c, mem_kind, st);
+}
+
+int cansb200_r2r(cansb200_ctx* ctx, int kind, int nt, int axis, void* arr, const int d3[3], void* stream) {
+  if (!ctx || !arr || !d3) return fail(CANSB200_EINVAL, "r2r: null argument");
+  if (axis != 0 && axis != 1) return fail(CANSB200_EINVAL, "r2r: axis must be 0 (x) or 1 (y)");
+  const int nx = d3[0], ny = d3[1], nz = d3[2];
+  if (nt < 1 || nt > (axis == 0 ? nx : ny)) return fail(CANSB200_EINVAL, "r2r: bad transform length");
+  const bool known = kind == K_R2HC || kind == K_HC2R || (kind >= K_REDFT00 && kind <= K_RODFT11);
+  if (!known) return fail(CANSB200_EINVAL, "r2r: unknown transform kind");
+  R2RGeom g = axis == 0 ? R2RGeom{1, 1, nx, nx, (long long)nx * ny, (long long)nx * ny, ny, nz, nx, 0}
+                        : R2RGeom{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nz, ny, 1};
+  cudaStream_t st = (cudaStream_t)stream;
+  return ctx->is_fp32 ? run_r2r<float>(ctx, kind, nt, (const float*)arr, (float*)arr, g, 0, st)
+                      : run_r2r<double>(ctx, kind, nt, (const double*)arr, (double*)arr, g, 0, st);
+}
+
+int cansb200_gaussel(cansb200_plan* pl, void* pz, const int d3[3], int n_rows, int is_periodic, double norm,
+                     const void* lam, const void* a, const void* b, const void* c, void* stream) {
+  if (!pl || !pz || !d3 || !lam || !a || !b || !c) return fail(CANSB200_EINVAL, "gaussel: null argument");
+  const int nx = d3[0], ny = d3[1];
+  if (nx != pl->ctx->n_z[0] || ny != pl->ctx->n_z[1]) return fail(CANSB200_EINVAL, "gaussel: extents differ from the plan's");
+  cudaStream_t st = (cudaStream_t)stream;
+  return pl->ctx->is_fp32
+             ? run_gaussel<float>(pl, (float*)pz, nx, ny, nx, (long long)nx * ny, n_rows, is_periodic, (float)norm,
+                                  (const float*)lam, (const float*)a, (const float*)b, (const float*)c, st)
+             : run_gaussel<double>(pl, (double*)pz, nx, ny, nx, (long long)nx * ny, n_rows, is_periodic, norm,
+                                   (const double*)lam, (const double*)a, (const double*)b, (const double*)c, st);
+}
+
+int cansb200_fill_hash(cansb200_ctx* ctx, void* p, const int n[3], const int lo[3], int nhalo, unsigned long long seed,
+                       void* stream) {
+  if (!ctx || !p || !n || !lo) return fail(CANSB200_EINVAL, "fill_hash: null argument");
+  if (nhalo != 0 && nhalo != 1) return fail(CANSB200_EINVAL, "fill_hash: nhalo must be 0 or 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tot = (long long)(n[0] + 2 * nhalo) * (n[1] + 2 * nhalo) * (n[2] + 2 * nhalo);
+  const unsigned blocks = (unsigned)((tot + 255) / 256 < 65535LL * 16 ? (tot + 255) / 256 : 65535LL * 16);
+  if (ctx->is_fp32)
+    fill_hash_kernel<float><<<blocks, 256, 0, st>>>((float*)p, n[0], n[1], n[2], lo[0] - 1, lo[1] - 1, lo[2] - 1, ctx->ng[0], ctx->ng[1], nhalo, seed);
+  else
+    fill_hash_kernel<double><<<blocks, 256, 0, st>>>((double*)p, n[0], n[1], n[2], lo[0] - 1, lo[1] - 1, lo[2] - 1, ctx->ng[0], ctx->ng[1], nhalo, seed);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int cansb200_fillps(cansb200_ctx* ctx, const int n[3], const double dli[3], const void* dzfi, double dti, const void* u,
+                    const void* v, const void* w, void* p, void* stream) {
+  if (!ctx || !n || !dli || !dzfi || !u || !v || !w || !p) return fail(CANSB200_EINVAL, "fillps: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tot = (long long)n[0] * n[1] * n[2];
+  const unsigned blocks = (unsigned)((tot + 255) / 256);
+  if (ctx->is_fp32)
+    fillps_kernel<float><<<blocks, 256, 0, st>>>(n[0], n[1], n[2], (float)dli[0], (float)dli[1], (const float*)dzfi, (float)dti,
+                                                 (const float*)u, (const float*)v, (const float*)w, (float*)p);
+  else
+    fillps_kernel<double><<<blocks, 256, 0, st>>>(n[0], n[1], n[2], dli[0], dli[1], (const double*)dzfi, dti, (const double*)u,
+                                                  (const double*)v, (const double*)w, (double*)p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int cansb200_correc(cansb200_ctx* ctx, const int n[3], const double dli[3], const void* dzci, double dt, const void* p, void* u,
+                    void* v, void* w, void* stream) {
+  if (!ctx || !n || !dli || !dzci || !u || !v || !w || !p) return fail(CANSB200_EINVAL, "correc: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tot = (long long)(n[0] + 2) * (n[1] + 2) * (n[2] + 2);
+  const unsigned blocks = (unsigned)((tot + 255) / 256);
+  if (ctx->is_fp32)
+    correc_kernel<float><<<blocks, 256, 0, st>>>(n[0], n[1], n[2], (float)dli[0], (float)dli[1], (const float*)dzci, (float)dt,
+                                                 (const float*)p, (float*)u, (float*)v, (float*)w);
+  else
+    correc_kernel<double><<<blocks, 256, 0, st>>>(n[0], n[1], n[2], dli[0], dli[1], (const double*)dzci, dt, (const double*)p,
+                                                  (double*)u, (double*)v, (double*)w);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int cansb200_chkdiv(cansb200_ctx* ctx, const int n[3], const double dli[3], const void* dzfi, const void* u, const void* v,
+                    const void* w, double* divtot_sum, double* divmax, void* stream) {
+  if (!ctx || !n || !dli || !dzfi || !u || !v || !w || !divtot_sum || !divmax) return fail(CANSB200_EINVAL, "chkdiv: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* res = nullptr;
+  CK(cudaMalloc(&res, 2 * sizeof(double)));
+  CK(cudaMemsetAsync(res, 0, 2 * sizeof(double), st));
+  const long long tot = (long long)n[0] * n[1] * n[2];
+  unsigned blocks = (unsigned)((tot + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (ctx->is_fp32)
+    chkdiv_kernel<float><<<blocks, 256, 0, st>>>(n[0], n[1], n[2], (float)dli[0], (float)dli[1], (const float*)dzfi, (const float*)u,
+                                                 (const float*)v, (const float*)w, res);
+  else
+    chkdiv_kernel<double><<<blocks, 256, 0, st>>>(n[0], n[1], n[2], dli[0], dli[1], (const double*)dzfi, (const double*)u,
+                                                  (const double*)v, (const double*)w, res);
+  ctx->launches++;
+  double h[2];
+  cudaError_t e = cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(res);
+  if (e != cudaSuccess) return fail(CANSB200_ECUDA, std::string("chkdiv: ") + cudaGetErrorString(e));
+  *divtot_sum = h[0];
+  *divmax = h[1];
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+"""Host-side mirror of the reference's solver interface.
+
+Same names, argument order and meaning as the Fortran the C ABI replaces:
+
+    initsolver(...)       /root/reference/src/initsolver.f90:15-83
+    fftini / fftend       src/fft.f90:25-245
+    solver(...)           src/solver.f90:17-112 == src/solver_gpu.f90:34-276
+    solve_helmholtz(...)  src/solve_helmholtz.f90:28-75
+    updt_rhs_b            src/bound.f90:514-598
+
+Array convention: a Fortran field p(0:n1+1,0:n2+1,0:n3+1) is a C-ordered array
+indexed [k, j, i] of shape (n3+2, n2+2, n1+2) -- a CUDA torch tensor (device
+mode, zero copies) or a numpy array (host mode: the library does H2D/D2H).
+`cbc[idir][ibound]` with idir 0..2 = x, y, z (the transpose of cbc(0:1,3)).
+
+The arithmetic of `initsolver` (eigenvalues, tridiagonal coefficients) stays
+host code exactly as in the reference, where it is Fortran run once at start-up.
+Everything per-solve runs in the CUDA library; nothing here falls back to a
+CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MEM_DEVICE, MEM_HOST, Options, check, d3, i3, lib
+
+try:  # torch is plumbing only: device memory + streams
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _ptr(x) -> int:
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return x.ctypes.data
+    raise TypeError(f"unsupported array type {type(x)}")
+
+
+def _stream_ptr(stream=None) -> int:
+    if stream is not None:
+        return int(stream.cuda_stream) if hasattr(stream, "cuda_stream") else int(stream)
+    if torch is not None and torch.cuda.is_available():
+        return int(torch.cuda.current_stream().cuda_stream)
+    return 0
+
+
+class Context:
+    """cansb200_ctx: replaces initmpi's decomposition setup + workspaces (single rank: dims = [1,1])."""
+
+    def __init__(self, ng: Sequence[int], is_fp32: bool = False, dims=(1, 1), ipencil_axis: int = 1, rank: int = 0,
+                 nranks: int = 1, nccl_id: Optional[bytes] = None):
+        self.ng = [int(v) for v in ng]
+        self.is_fp32 = bool(is_fp32)
+        self.dtype = np.float32 if is_fp32 else np.float64
+        self._h = C.c_void_p()
+        idp = C.cast(C.c_char_p(nccl_id), C.c_void_p) if nccl_id else None
+        check(lib.cansb200_init(C.byref(self._h), i3(self.ng), i3(dims), ipencil_axis, rank, nranks, idp, int(is_fp32)),
+              "cansb200_init")
+        n, lo, nz, loz = i3([0] * 3), i3([0] * 3), i3([0] * 3), i3([0] * 3)
+        check(lib.cansb200_get_extents(self._h, n, lo, nz, loz), "get_extents")
+        self.n, self.lo, self.n_z, self.lo_z = list(n), list(lo), list(nz), list(loz)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib.cansb200_finalize(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Plan:
+    """What `arrplan(2,2)` is in the reference: the four r2r plans of one solved variable
+    (the handle a Fortran host would keep in arrplan(1,1) as type(C_PTR))."""
+
+    def __init__(self, ctx: Context, cbc, c_or_f, **options):
+        self.ctx = ctx
+        self.cbc = [list(b) for b in cbc]
+        self.c_or_f = list(c_or_f)
+        bc6 = "".join(self.cbc[d][i] for d in range(3) for i in range(2)).encode()
+        cf3 = "".join(self.c_or_f).encode()
+        self._h = C.c_void_p()
+        nf = C.c_double()
+        opt = Options(**options)
+        check(lib.cansb200_plan_create(ctx.handle, C.byref(self._h), bc6, cf3, C.byref(opt), C.byref(nf)), "plan_create")
+        self.normfft = ctx.dtype(nf.value)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def stats(self):
+        s = (C.c_ulonglong * 4)()
+        check(lib.cansb200_plan_stats(self._h, s), "plan_stats")
+        return {"solves": s[0], "factorisations": s[1], "launches": s[2], "thomas_variant": s[3]}
+
+    def destroy(self):
+        if self._h:
+            lib.cansb200_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
+# initsolver and its pieces (host arithmetic, as in the reference)
+# ---------------------------------------------------------------------------
+def eigenvalues(n, bc, c_or_f, dtype=np.float64):
+    """src/initsolver.f90:85-144, CPU-build (halfcomplex) ordering for 'PP'."""
+    pi = np.arccos(dtype(-1.0))
+    l = np.arange(1, n + 1)
+    key = bc[0] + bc[1]
+    two, one = dtype(2.0), dtype(1.0)
+    if key == "PP":
+        th = (2 * (l - 1)).astype(dtype) * pi / dtype(n)
+    elif key == "NN":
+        th = (l - 1).astype(dtype) * pi / dtype(n)
+    elif key == "DD":
+        th = l.astype(dtype) * pi / dtype(n)
+    else:
+        th = (2 * l - 1).astype(dtype) * pi / dtype(2.0 * n)
+    lam = (-two * (one - np.cos(th))).astype(dtype)
+    if key == "DD" and c_or_f == "f":
+        lam[n - 1] = 0.0
+    return lam
+
+
+def tridmatrix(bc, n, dzci, dzfi, c_or_f, dtype=np.float64):
+    """src/initsolver.f90:146-187; dzci / dzfi indexed 0..n+1."""
+    k = np.arange(1, n + 1)
+    if c_or_f == "c":
+        a = (dzfi[k] * dzci[k - 1]).astype(dtype)
+        c = (dzfi[k] * dzci[k]).astype(dtype)
+    else:
+        a = (dzfi[k] * dzci[k]).astype(dtype)
+        c = (dzfi[k + 1] * dzci[k]).astype(dtype)
+    b = -(a + c)
+    f = [{"P": 0.0, "D": -1.0, "N": 1.0}[bc[i]] for i in (0, 1)]
+    if c_or_f == "c" or bc[0] == "N":
+        b[0] = b[0] + dtype(f[0]) * a[0]
+    if c_or_f == "c" or bc[1] == "N":
+        b[n - 1] = b[n - 1] + dtype(f[1]) * c[n - 1]
+    return a, b, c
+
+
+def bc_rhs(cbc, bc, dlc, dlf, c_or_f):
+    """src/initsolver.f90:189-232 -> [lower, upper] plane values."""
+    out = []
+    for ib in (0, 1):
+        sgn = 1.0 if ib == 0 else -1.0
+        if cbc[ib] == "P":
+            fac = 0.0
+        elif cbc[ib] == "D":
+            fac = -2.0 * bc[ib] if c_or_f == "c" else -bc[ib]
+        else:
+            fac = sgn * (dlc[ib] if c_or_f == "c" else dlf[ib]) * bc[ib]
+        out.append(fac / dlc[ib] / dlf[ib])
+    return out
+
+
+def find_fft(bc, c_or_f):
+    """src/fft.f90:260-313 -> (kind_fwd, kind_bwd, (norm1, norm2)) with FFTW kind numbers."""
+    key = bc[0] + bc[1]
+    if key == "PP":
+        return 0, 1, (1.0, 0.0)
+    if c_or_f == "c":
+        return {"NN": (5, 4, (2.0, 0.0)), "DD": (9, 8, (2.0, 0.0)), "ND": (6, 6, (2.0, 0.0)), "DN": (10, 10, (2.0, 0.0))}[key]
+    return {"NN": (3, 3, (2.0, -1.0)), "DD": (7, 7, (2.0, 1.0)), "ND": (5, 4, (2.0, 0.0)), "DN": (8, 9, (2.0, 0.0))}[key]
+
+
+def fftini(ctx: Context, cbc, c_or_f, **options):
+    """src/fft.f90:25-209 -> (arrplan, normfft).  `cbc` needs all three directions because the
+    plan also fixes the z-solve variant (periodic closure, face-centred Dirichlet exclusion)."""
+    plan = Plan(ctx, cbc, c_or_f, **options)
+    return plan, plan.normfft
+
+
+def fftend(arrplan: Plan):
+    """src/fft.f90:211-245."""
+    arrplan.destroy()
+
+
+@dataclass
+class SolverData:
+    lambdaxy: Any
+    a: Any
+    b: Any
+    c: Any
+    arrplan: Plan
+    normfft: Any
+    rhsbx: List[float]
+    rhsby: List[float]
+    rhsbz: List[float]
+    host: dict = field(default_factory=dict)
+
+
+def initsolver(ctx: Context, ng, dli, dzci_g, dzfi_g, cbc, bc, c_or_f, device=None, **options) -> SolverData:
+    """src/initsolver.f90:15-83.  Returns lambdaxy[j,i], a, b, c (on `device` if given, else numpy),
+    arrplan, normfft and the boundary RHS values."""
+    dt = ctx.dtype
+    dli = [dt(v) for v in dli]
+    dzci_g = np.asarray(dzci_g, dtype=dt)
+    dzfi_g = np.asarray(dzfi_g, dtype=dt)
+    lx = eigenvalues(ng[0], cbc[0], c_or_f[0], dt) * dli[0] ** 2
+    ly = eigenvalues(ng[1], cbc[1], c_or_f[1], dt) * dli[1] ** 2
+    lambdaxy = np.ascontiguousarray((lx[None, :] + ly[:, None]).astype(dt))
+    a, b, c = tridmatrix(cbc[2], ng[2], dzci_g, dzfi_g, c_or_f[2], dt)
+    dl = [dt(1.0) / v for v in dli]
+    dzc_g, dzf_g = dt(1.0) / dzci_g, dt(1.0) / dzfi_g
+    n3 = ng[2]
+    rhsbx = bc_rhs(cbc[0], bc[0], [dl[0]] * 2, [dl[0]] * 2, c_or_f[0])
+    rhsby = bc_rhs(cbc[1], bc[1], [dl[1]] * 2, [dl[1]] * 2, c_or_f[1])
+    if c_or_f[2] == "c":
+        rhsbz = bc_rhs(cbc[2], bc[2], [dzc_g[0], dzc_g[n3]], [dzf_g[1], dzf_g[n3]], "c")
+    else:
+        rhsbz = bc_rhs(cbc[2], bc[2], [dzc_g[1], dzc_g[n3 - 1]], [dzf_g[1], dzf_g[n3]], "f")
+    arrplan, normfft = fftini(ctx, cbc, c_or_f, **options)
+    host = dict(lambdaxy=lambdaxy, a=a, b=b, c=c)
+    if device is not None:
+        lam_d = torch.from_numpy(lambdaxy).to(device)
+        a_d, b_d, c_d = (torch.from_numpy(v).to(device) for v in (a, b, c))
+        return SolverData(lam_d, a_d, b_d, c_d, arrplan, normfft, rhsbx, rhsby, rhsbz, host)
+    return SolverData(lambdaxy, a, b, c, arrplan, normfft, rhsbx, rhsby, rhsbz, host)
+
+
+# ---------------------------------------------------------------------------
+# solver / solve_helmholtz
+# ---------------------------------------------------------------------------
+def solver(n, ng, arrplan: Plan, normfft, lambdaxy, a, b, c, bc, c_or_f, p, stream=None):
+    """src/solver.f90:17-112.  Solves in place on the interior of the haloed `p`.
+    `bc` / `c_or_f` are accepted for signature parity; the plan already fixed them."""
+    if list(c_or_f) != arrplan.c_or_f or [list(x) for x in bc] != arrplan.cbc:
+        raise ValueError("solver: bc / c_or_f differ from the ones the plan (arrplan) was created with")
+    dev = _is_torch(p) and p.is_cuda
+    for name, arr in (("lambdaxy", lambdaxy), ("a", a), ("b", b), ("c", c)):
+        if (_is_torch(arr) and arr.is_cuda) != dev:
+            raise ValueError(f"solver: {name} must live where p lives (all device or all host)")
+    want = (n[2] + 2, n[1] + 2, n[0] + 2)
+    if tuple(p.shape) != want:
+        raise ValueError(f"solver: p has shape {tuple(p.shape)}, expected {want}")
+    check(lib.cansb200_solve(arrplan.handle, _ptr(p), i3(n), 1, float(normfft), _ptr(lambdaxy), _ptr(a), _ptr(b), _ptr(c),
+                             MEM_DEVICE if dev else MEM_HOST, _stream_ptr(stream)), "cansb200_solve")
+    return p
+
+
+def updt_rhs_b(c_or_f, cbc, n, rhsbx, rhsby, rhsbz, p, alpha=None):
+    """src/bound.f90:514-598 on one rank: adds the wall contributions to the first / last planes."""
+    norm = 1.0 if alpha is None else alpha
+    q = [1 if (c_or_f[d] == "f" and cbc[d][1] == "D") else 0 for d in range(3)]
+    n1, n2, n3 = n
+    K, J, I = slice(1, n3 + 1), slice(1, n2 + 1), slice(1, n1 + 1)
+    if rhsbx is not None:
+        p[K, J, 1] += rhsbx[0] * norm
+        p[K, J, n1 - q[0]] += rhsbx[1] * norm
+    if rhsby is not None:
+        p[K, 1, I] += rhsby[0] * norm
+        p[K, n2 - q[1], I] += rhsby[1] * norm
+    if rhsbz is not None:
+        p[1, J, I] += rhsbz[0] * norm
+        p[n3 - q[2], J, I] += rhsbz[1] * norm
+
+
+def solve_helmholtz(n, ng, arrplan, normfft, alpha, lambdaxy, a, b, c, rhsbx, rhsby, rhsbz, cbc, c_or_f, p, stream=None):
+    """src/solve_helmholtz.f90:28-75: p/alpha + lap(p) = rhs."""
+    updt_rhs_b(c_or_f, cbc, n, rhsbx, rhsby, rhsbz, p, alpha)
+    ty = p.dtype.type if isinstance(p, np.ndarray) else (np.float32 if p.dtype == torch.float32 else np.float64)
+    alphai = ty(1.0) / ty(alpha)
+    bb = b + alphai if not _is_torch(b) else b + float(alphai)
+    return solver(n, ng, arrplan, ty(normfft) * alphai, lambdaxy, a, bb, c, cbc, c_or_f, p, stream)
+
+
+# ---------------------------------------------------------------------------
+# stage-level calls + the steps either side of the path (device tensors)
+# ---------------------------------------------------------------------------
+def r2r(ctx: Context, kind: int, n_transform: int, axis: int, arr, stream=None):
+    """One `call fft(plan, arr)` (src/fft.f90:247-258) on a haloless device array [k,j,i]."""
+    nz, ny, nx = arr.shape
+    check(lib.cansb200_r2r(ctx.handle, kind, n_transform, axis, _ptr(arr), i3([nx, ny, nz]), _stream_ptr(stream)), "cansb200_r2r")
+    return arr
+
+
+def gaussel(arrplan: Plan, n_rows, a, b, c, is_periodic, norm, pz, lambdaxy, stream=None):
+    """`call gaussel(nx,ny,n,0,a,b,c,is_periodic,norm,p,lambdaxy)` (src/solver.f90:114-307)."""
+    nz, ny, nx = pz.shape
+    check(lib.cansb200_gaussel(arrplan.handle, _ptr(pz), i3([nx, ny, nz]), int(n_rows), int(is_periodic), float(norm),
+                               _ptr(lambdaxy), _ptr(a), _ptr(b), _ptr(c), _stream_ptr(stream)), "cansb200_gaussel")
+    return pz
+
+
+def fillps(ctx, n, dli, dzfi, dti, u, v, w, p, stream=None):
+    """src/fillps.f90:13-51."""
+    check(lib.cansb200_fillps(ctx.handle, i3(n), d3(dli), _ptr(dzfi), float(dti), _ptr(u), _ptr(v), _ptr(w), _ptr(p),
+                              _stream_ptr(stream)), "cansb200_fillps")
+
+
+def correc(ctx, n, dli, dzci, dt, p, u, v, w, stream=None):
+    """src/correc.f90:13-60."""
+    check(lib.cansb200_correc(ctx.handle, i3(n), d3(dli), _ptr(dzci), float(dt), _ptr(p), _ptr(u), _ptr(v), _ptr(w),
+                              _stream_ptr(stream)), "cansb200_correc")
+
+
+def chkdiv(ctx, n, l, dli, dzfi, u, v, w, stream=None):
+    """src/chkdiv.f90:15-54 -> (divtot, divmax)."""
+    tot, mx = C.c_double(), C.c_double()
+    check(lib.cansb200_chkdiv(ctx.handle, i3(n), d3(dli), _ptr(dzfi), _ptr(u), _ptr(v), _ptr(w), C.byref(tot), C.byref(mx),
+                              _stream_ptr(stream)), "cansb200_chkdiv")
+    return tot.value / float(l[0] * l[1] * l[2]), mx.value
+
+
+def fill_hash(ctx, p, n, lo, nhalo, seed, stream=None):
+    """Counter-based synthetic field written on the device."""
+    check(lib.cansb200_fill_hash(ctx.handle, _ptr(p), i3(n), i3(lo), int(nhalo), int(seed), _stream_ptr(stream)),
+          "cansb200_fill_hash")
+    return p

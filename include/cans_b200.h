@@ -1,0 +1,117 @@
+/* cans_b200 -- C ABI of the B200-native FFT-based Poisson/Helmholtz solver.
+ *
+ * Drop-in boundary for the ONE hot path of CaNS: `solver` / `solver_gpu`
+ * (reference /root/reference/src/solver.f90:17-112, src/solver_gpu.f90:34-276),
+ * reused by `solve_helmholtz` (src/solve_helmholtz.f90:28-75).  A <=150-line
+ * Fortran module (`fortran/solver_b200.f90`) named
+ * `mod_solver_gpu` binds these symbols through ISO_C_BINDING so that
+ * main.f90 / rk.f90 / mom.f90 / initsolver.f90 stay unchanged.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative CANSB200_E* code otherwise,
+ *    and never aborts (the reference `error stop`s: src/fft.f90:525,696 -- the
+ *    Fortran shim turns a non-zero status into `error stop`);
+ *  - fields are Fortran arrays p(0:n1+1,0:n2+1,0:n3+1), x fastest, one ghost
+ *    cell per side (src/main.f90:164-168); only the interior is written;
+ *  - `mem_kind` says where p / lambdaxy / a / b / c live (host or device);
+ *  - all work is stream-ordered on the caller's CUDA stream (the reference
+ *    enqueues everything on OpenACC queue 1: src/workspaces.f90:101-106);
+ *    no host synchronisation happens inside cansb200_solve in device mode;
+ *  - precision is fixed per context: FP64, or FP32 when CaNS is built with
+ *    -D_SINGLE_PRECISION (src/types.f90:12-18).
+ */
+#ifndef CANS_B200_H
+#define CANS_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cansb200_ctx cansb200_ctx;
+typedef struct cansb200_plan cansb200_plan;
+
+enum {
+  CANSB200_OK = 0,
+  CANSB200_EINVAL = -1,   /* bad argument */
+  CANSB200_ECUDA = -2,    /* CUDA runtime error, see cansb200_last_error() */
+  CANSB200_ENOMEM = -3,
+  CANSB200_EUNSUPPORTED = -4,
+  CANSB200_ECOMM = -5     /* NCCL / peer-memory error */
+};
+enum { CANSB200_MEM_HOST = 0, CANSB200_MEM_DEVICE = 1 };
+
+/* Tunables; negative = library default.  Read once by cansb200_plan_create. */
+typedef struct cansb200_options {
+  int thomas_variant;   /* 0 = sequential two-sweep (any nz), 1 = warp-per-column on-chip (nz <= 1024) */
+  int cache_slots;      /* factorisation cache entries per plan (1..8); Helmholtz plans want 3 */
+  int fft_x_lines;      /* lines per tile of the contiguous transforms (0 = auto) */
+  int fft_y_lines;      /* 8 or 16: x-width of the strided-transform tile (0 = auto) */
+  int exchange;         /* multi-GPU: 0 = NCCL all-to-all, 1 = fused peer stores */
+  int reserved[11];
+} cansb200_options;
+
+/* -- context: replaces initmpi's cuDecomp setup (src/initmpi.f90:84-146), common_cudecomp.f90
+ *    and workspaces.f90's init_wspace_arrays.  ng = global grid, dims = processor grid
+ *    (only dims = [1, nranks], z slabs / x pencils, is implemented), nccl_id = 128-byte
+ *    ncclUniqueId broadcast by the host (cuDecomp does the same: cudecomp.cc:65-69) or
+ *    NULL when nranks == 1. */
+int cansb200_init(cansb200_ctx** ctx, const int ng[3], const int dims[2], int ipencil_axis,
+                  int rank, int nranks, const void* nccl_id, int is_fp32);
+int cansb200_finalize(cansb200_ctx* ctx);
+
+/* local extents of this rank: n = x-pencil (nx, ny, nz/P) as main.f90 sees it, lo_z / n_z =
+ * z-pencil (nx, ny/P, nz) that lambdaxy is indexed by (src/initsolver.f90:54-58). 1-based lo. */
+int cansb200_get_extents(const cansb200_ctx* ctx, int n[3], int lo[3], int n_z[3], int lo_z[3]);
+
+/* -- plan: replaces fftini / fftend (src/fft.f90:25-245).  bc = {x0,x1,y0,y1,z0,z1} in
+ *    {'P','D','N'}, c_or_f = {'c'|'f'} per direction.  normfft_out receives fftini's normfft. */
+int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** plan, const char bc[6],
+                         const char c_or_f[3], const cansb200_options* opt, double* normfft_out);
+int cansb200_plan_destroy(cansb200_plan* plan);
+
+/* -- the solve: replaces solver / solver_gpu.  Same argument meaning as the reference:
+ *    n = local interior extents, nhalo = 1, normfft (normfft/alpha for Helmholtz),
+ *    lambdaxy(n_z(1),n_z(2)), a/b/c(n_z(3)) -- b already shifted by 1/alpha by the caller
+ *    (src/solve_helmholtz.f90:63-71).  p is solved in place. */
+int cansb200_solve(cansb200_plan* plan, void* p, const int n[3], int nhalo, double normfft,
+                   const void* lambdaxy, const void* a, const void* b, const void* c,
+                   int mem_kind, void* stream);
+
+/* -- stage-level entry points (device pointers only), so that tests can compare every stage
+ *    with the oracle the way the reference composes them:
+ *    cansb200_r2r     == one `call fft(arrplan(idir_fb), arr)`            (src/fft.f90:247-258)
+ *    cansb200_gaussel == `call gaussel(nx,ny,n,0,a,b,c,is_periodic,norm,p,lambdaxy)` (src/solver.f90:114) */
+int cansb200_r2r(cansb200_ctx* ctx, int kind, int n_transform, int axis /*0=x,1=y*/,
+                 void* arr, const int dims3[3] /*nx,ny,nz of the haloless array*/, void* stream);
+int cansb200_gaussel(cansb200_plan* plan, void* pz, const int dims3[3], int n_rows, int is_periodic,
+                     double norm, const void* lambdaxy, const void* a, const void* b, const void* c,
+                     void* stream);
+
+/* -- the steps either side of the path (device pointers, haloed arrays):
+ *    fillps (src/fillps.f90:13-51), correc (src/correc.f90:13-60), chkdiv (src/chkdiv.f90:15-54) */
+int cansb200_fillps(cansb200_ctx* ctx, const int n[3], const double dli[3], const void* dzfi, double dti,
+                    const void* u, const void* v, const void* w, void* p, void* stream);
+int cansb200_correc(cansb200_ctx* ctx, const int n[3], const double dli[3], const void* dzci, double dt,
+                    const void* p, void* u, void* v, void* w, void* stream);
+int cansb200_chkdiv(cansb200_ctx* ctx, const int n[3], const double dli[3], const void* dzfi,
+                    const void* u, const void* v, const void* w, double* divtot_sum, double* divmax,
+                    void* stream);
+
+/* -- synthetic input: counter-based uniform(-1,1) field indexed by the GLOBAL (i,j,k)
+ *    (SURVEY.md 8d); fills the interior of a haloed device array, halo set to 0. */
+int cansb200_fill_hash(cansb200_ctx* ctx, void* p, const int n[3], const int lo[3], int nhalo,
+                       unsigned long long seed, void* stream);
+
+/* -- diagnostics */
+const char* cansb200_last_error(void);
+int cansb200_version(void);
+/* counters since plan creation: [0] solves, [1] factorisations run, [2] kernels launched */
+int cansb200_plan_stats(cansb200_plan* plan, unsigned long long stats[4]);
+/* workspace the OpenACC host may alias as `work` / `solver_buf_0` (src/rk.f90:26-30) */
+int cansb200_get_work(cansb200_ctx* ctx, int which, void** ptr, size_t* nelem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANS_B200_H */

@@ -1,0 +1,72 @@
+"""Shared case table for the parity tests (CPU and GPU)."""
+import numpy as np
+
+from oracle import cans_oracle as O
+
+P, N, D = ["P", "P"], ["N", "N"], ["D", "D"]
+ND, DN = ["N", "D"], ["D", "N"]
+C3 = ["c", "c", "c"]
+
+# name -> (ng, l, cbc, c_or_f, gr, dtype)
+CASES = {
+    # BASELINE.json configs[0]: tests/lid_driven_cavity/input.nml as shipped
+    "C1_ldc_2x64x64": ([2, 64, 64], [0.03125, 1.0, 1.0], [P, N, N], C3, 0.0, np.float64),
+    # scaled-down twins of configs[1..3]
+    "C2s_triperiodic": ([32, 16, 24], [6.2832, 6.2832, 6.2832], [P, P, P], C3, 0.0, np.float64),
+    "C3s_channel": ([32, 16, 40], [12.0, 6.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    "C4s_duct": ([16, 24, 48], [12.0, 2.0, 2.0], [P, N, N], C3, 1.5, np.float64),
+    # edge cases: odd / prime sizes (direct transform path), tiny z, Dirichlet pressure
+    "odd_sizes": ([9, 14, 11], [1.0, 1.0, 1.0], [P, N, N], C3, 1.0, np.float64),
+    "prime_17x34": ([34, 17, 6], [1.0, 1.0, 1.0], [N, P, N], C3, 0.0, np.float64),
+    "dirichlet_xyz": ([16, 12, 20], [1.0, 1.0, 1.0], [D, D, D], C3, 1.0, np.float64),
+    "mixed_nd_dn": ([12, 10, 16], [1.0, 1.0, 1.0], [ND, DN, D], C3, 0.5, np.float64),
+    "periodic_z_odd": ([8, 6, 37], [1.0, 1.0, 1.0], [N, P, P], C3, 0.0, np.float64),
+    "tiny_z": ([8, 8, 2], [1.0, 1.0, 1.0], [P, P, N], C3, 0.0, np.float64),
+    "nz_gt_512": ([8, 8, 600], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    # implicit-diffusion (Helmholtz) operators: face-centred in one direction, Dirichlet walls
+    "helm_u_face_x": ([16, 12, 20], [1.0, 1.0, 1.0], [D, D, D], ["f", "c", "c"], 1.0, np.float64),
+    "helm_v_face_y": ([16, 12, 20], [1.0, 1.0, 1.0], [P, D, D], ["c", "f", "c"], 1.0, np.float64),
+    "helm_w_face_z": ([16, 12, 20], [1.0, 1.0, 1.0], [P, P, D], ["c", "c", "f"], 1.0, np.float64),
+    "helm_w_face_z_nn": ([16, 12, 20], [1.0, 1.0, 1.0], [N, N, N], ["f", "f", "f"], 1.0, np.float64),
+    # single precision build (-D_SINGLE_PRECISION)
+    "fp32_channel": ([32, 16, 40], [12.0, 6.0, 2.0], [P, P, N], C3, 2.0, np.float32),
+    "fp32_ldc": ([2, 64, 64], [0.03125, 1.0, 1.0], [P, N, N], C3, 0.0, np.float32),
+}
+HELMHOLTZ = {"helm_u_face_x", "helm_v_face_y", "helm_w_face_z", "helm_w_face_z_nn"}
+ALPHA = -0.0123  # alpha = -0.5 * visc * dt_rk < 0 (src/main.f90:456)
+
+
+def build_case(name):
+    ng, l, cbc, cf, gr, dt = CASES[name]
+    cs = O.make_case(ng, l, cbc, c_or_f=cf, gr=gr, dtype=dt)
+    return cs
+
+
+def make_rhs(cs, seed=123):
+    """Seeded RHS on the haloed grid; made compatible when the operator is singular."""
+    ng, dt = cs["ng"], cs["dtype"]
+    rhs = O.hash_field(ng, seed, np.float64)
+    singular = all(b[0] in "PN" and b[1] in "PN" for b in cs["cbc"])
+    if singular:
+        w = cs["dzf"][1:-1].astype(np.float64)[:, None, None]
+        rhs = rhs - (rhs * w).sum() / (w.sum() * ng[0] * ng[1])
+    p = np.zeros((ng[2] + 2, ng[1] + 2, ng[0] + 2), dtype=dt)
+    p[1:-1, 1:-1, 1:-1] = rhs.astype(dt)
+    return p
+
+
+def oracle_solve(name, cs, p, helmholtz=False):
+    ng = cs["ng"]
+    ref = p.copy()
+    if helmholtz:
+        O.solve_helmholtz(ng, ng, cs["arrplan"], cs["normfft"], ALPHA, cs["lambdaxy"], cs["a"], cs["b"], cs["c"],
+                          None, None, None, cs["cbc"], cs["c_or_f"], ref)
+    else:
+        O.solver(ng, ng, cs["arrplan"], cs["normfft"], cs["lambdaxy"], cs["a"], cs["b"], cs["c"], cs["cbc"], cs["c_or_f"], ref)
+    return ref
+
+
+def rel_l2(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300))
