@@ -48,6 +48,8 @@ SYMBOLS = {
     "cansb200_last_error": (C.c_char_p, []),
     "cansb200_version": (C.c_int, []),
     "cansb200_plan_stats": (C.c_int, [_VP, C.POINTER(C.c_ulonglong)]),
+    "cansb200_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "cansb200_get_profile": (C.c_int, [_VP, _D3, C.POINTER(C.c_ulonglong)]),
     "cansb200_get_work": (C.c_int, [_VP, C.c_int, C.POINTER(_VP), C.POINTER(C.c_size_t)]),
 }
 

@@ -71,8 +71,20 @@ struct cansb200_ctx {
   std::map<long long, DirectTables<double>> dtabs64;
   std::map<long long, DirectTables<float>> dtabs32;
   unsigned long long launches = 0;
-  bool attr_set[16] = {false};
+  // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;   // 7 events per profiled solve
+  double prof_ms[8] = {0};
+  unsigned long long prof_n = 0;
 };
+
+static void prof_mark(cansb200_ctx* c, cudaStream_t st) {
+  if (!c->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  c->prof_events.push_back(e);
+}
 
 struct cansb200_plan {
   cansb200_ctx* ctx;
@@ -258,6 +270,7 @@ static int run_gaussel(cansb200_plan* pl, T* p, int nx, int ny, long long sj, lo
     ctx->launches += 3;
     CK(cudaGetLastError());
   }
+  prof_mark(ctx, st);
   if (pl->th_variant == 1) {
     switch (pl->th_mmax) {
       case 4: return launch_warp<T, 4>(ctx, D, pl, p, norm, st);
@@ -422,6 +435,35 @@ int cansb200_plan_destroy(cansb200_plan* pl) {
   return 0;
 }
 
+int cansb200_set_profiling(cansb200_ctx* c, int on) {
+  if (!c) return fail(CANSB200_EINVAL, "null ctx");
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  c->prof_events.clear();
+  for (double& v : c->prof_ms) v = 0.0;
+  c->prof_n = 0;
+  c->profiling = on != 0;
+  return 0;
+}
+
+int cansb200_get_profile(cansb200_ctx* c, double ms[8], unsigned long long* nsolves) {
+  if (!c || !ms) return fail(CANSB200_EINVAL, "null argument");
+  const size_t per = 7;
+  CK(cudaDeviceSynchronize());
+  const size_t ns = c->prof_events.size() / per;
+  for (size_t s = 0; s < ns; ++s)
+    for (size_t k = 0; k + 1 < per; ++k) {
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, c->prof_events[s * per + k], c->prof_events[s * per + k + 1]));
+      c->prof_ms[k] += t;
+    }
+  c->prof_n += ns;
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  c->prof_events.clear();
+  for (int k = 0; k < 8; ++k) ms[k] = c->prof_ms[k];
+  if (nsolves) *nsolves = c->prof_n;
+  return 0;
+}
+
 int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
   if (!pl || !stats) return fail(CANSB200_EINVAL, "null argument");
   CacheState cs;
@@ -458,23 +500,29 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   T* A = (T*)ctx->scratch.p;
   T* pin = p + (px * py + px + 1);  // p(1,1,1)
   int rc;
+  prof_mark(ctx, st);
   // forward x: p (haloed) -> A
   R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nz, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
   if (rc) return rc;
+  prof_mark(ctx, st);
   // forward y, in place in A
   R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nz, ny, 1};
   rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
   if (rc) return rc;
+  prof_mark(ctx, st);
   // tridiagonal solve in z
   rc = run_gaussel<T>(pl, A, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, (T)normfft, lam, a, b, c, st);
   if (rc) return rc;
+  prof_mark(ctx, st);
   // backward y, backward x
   rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
   if (rc) return rc;
+  prof_mark(ctx, st);
   R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nz, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
   if (rc) return rc;
+  prof_mark(ctx, st);
   if (mem_kind == CANSB200_MEM_HOST) {
     CK(cudaMemcpyAsync(p_any, ctx->staging.p, nh * sizeof(T), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

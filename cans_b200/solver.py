@@ -79,6 +79,17 @@ class Context:
     def handle(self):
         return self._h
 
+    def set_profiling(self, on: bool):
+        check(lib.cansb200_set_profiling(self._h, int(on)), "set_profiling")
+
+    def get_profile(self):
+        """-> (dict stage -> total ms, number of profiled solves)"""
+        ms = (C.c_double * 8)()
+        ns = C.c_ulonglong()
+        check(lib.cansb200_get_profile(self._h, ms, C.byref(ns)), "get_profile")
+        names = ["fft_x_fwd", "fft_y_fwd", "pivot_cache", "thomas", "fft_y_bwd", "fft_x_bwd"]
+        return {k: ms[i] for i, k in enumerate(names)}, int(ns.value)
+
     def close(self):
         if self._h:
             lib.cansb200_finalize(self._h)

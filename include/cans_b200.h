@@ -108,6 +108,12 @@ const char* cansb200_last_error(void);
 int cansb200_version(void);
 /* counters since plan creation: [0] solves, [1] factorisations run, [2] kernels launched */
 int cansb200_plan_stats(cansb200_plan* plan, unsigned long long stats[4]);
+/* per-stage device timing with CUDA events on the solve's stream (the role of the reference's
+ * unused timer_tic/toc CUDA-event pool, src/timer.f90:113-216).  Stages of one solve:
+ * [0] fft x fwd, [1] fft y fwd, [2] pivot-cache check (+ factorisation on a miss),
+ * [3] tridiagonal substitution, [4] fft y bwd, [5] fft x bwd.  ms[] are sums over nsolves. */
+int cansb200_set_profiling(cansb200_ctx* ctx, int on);
+int cansb200_get_profile(cansb200_ctx* ctx, double ms[8], unsigned long long* nsolves);
 /* workspace the OpenACC host may alias as `work` / `solver_buf_0` (src/rk.f90:26-30) */
 int cansb200_get_work(cansb200_ctx* ctx, int which, void** ptr, size_t* nelem);
 

@@ -563,3 +563,57 @@ def make_case(ng, l, cbc, c_or_f=('c', 'c', 'c'), gr=0.0, gtype=1, bc=None, dtyp
     s.update(ng=list(ng), l=list(l), cbc=cbc, c_or_f=list(c_or_f), dli=dli, dzc=dzc, dzf=dzf,
              dzci=dzci, dzfi=dzfi, dtype=dtype, bc=bc)
     return s
+
+
+# --------------------------------------------------------------------------
+# C restatement of gaussel (oracle/gaussel_c.c) -- used by the CPU baseline
+# --------------------------------------------------------------------------
+_GAUSSEL_C = None
+
+
+def _load_gaussel_c():
+    global _GAUSSEL_C
+    if _GAUSSEL_C is None:
+        import ctypes as C
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libgaussel_c.so")
+        if not os.path.exists(path):
+            _GAUSSEL_C = False
+        else:
+            lib = C.CDLL(path)
+            dp = C.POINTER(C.c_double)
+            lib.gaussel_c.restype = C.c_int
+            lib.gaussel_c.argtypes = [C.c_long, C.c_long, C.c_long, dp, dp, dp, C.c_int, C.c_double, dp, dp]
+            _GAUSSEL_C = lib
+    return _GAUSSEL_C
+
+
+def gaussel_c(n, a, b, c, is_periodic, norm, p, lambdaxy):
+    """FP64 only; p[k,j,i] C-contiguous.  Bit-identical to `gaussel` (tests/test_oracle.py)."""
+    import ctypes as C
+    lib = _load_gaussel_c()
+    if not lib:
+        raise RuntimeError("oracle/_build/libgaussel_c.so missing: run __graft_entry__.build()")
+    assert p.dtype == np.float64 and p.flags["C_CONTIGUOUS"]
+    dp = C.POINTER(C.c_double)
+    f = lambda x: np.ascontiguousarray(x, dtype=np.float64).ctypes.data_as(dp)
+    rc = lib.gaussel_c(p.shape[2], p.shape[1], n, f(a), f(b), f(c), int(is_periodic), float(norm), p.ctypes.data_as(dp),
+                       f(lambdaxy))
+    if rc:
+        raise RuntimeError(f"gaussel_c failed: {rc}")
+    return p
+
+
+def solver_fast(n, ng, arrplan, normfft, lambdaxy, a, b, c, bc, c_or_f, p, workers=-1):
+    """`solver` with threaded pocketfft and the OpenMP C gaussel: the CPU baseline
+    ("kind": "port").  FP64.  Same stages, same order as `solver`."""
+    n1, n2, n3 = n
+    px = np.ascontiguousarray(p[1:n3 + 1, 1:n2 + 1, 1:n1 + 1])
+    fft(arrplan[0][0], px, workers)
+    fft(arrplan[1][0], px, workers)
+    q = 1 if (c_or_f[2] == 'f' and bc[2][1] == 'D') else 0
+    gaussel_c(n3 - q, a, b, c, bc[2][0] + bc[2][1] == 'PP', normfft, px, lambdaxy)
+    fft(arrplan[1][1], px, workers)
+    fft(arrplan[0][1], px, workers)
+    p[1:n3 + 1, 1:n2 + 1, 1:n1 + 1] = px
+    return p

@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle.
+
+Bars (BASELINE.json north_star): pressure within 1e-12 relative L2 in FP64,
+1e-5 in FP32, on identical inputs; post-correction divergence below `small`.
+Every stage is also checked alone, the way the reference composes them
+(fft x, fft y, gaussel, fft y, fft x), so a failure names its kernel."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import cans_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+@pytest.fixture(scope="module")
+def cb():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; the product path has no CPU fallback")
+    return importlib.import_module("cans_b200")
+
+
+@pytest.fixture(scope="module")
+def S():
+    return importlib.import_module("cans_b200.solver")
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _gpu_solve(cb, cs, p, helmholtz=False, **options):
+    ng = cs["ng"]
+    ctx = cb.Context(ng, is_fp32=cs["dtype"] == np.float32)
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cs["cbc"], cs["bc"], cs["c_or_f"], device=_dev(), **options)
+    assert float(sd.normfft) == pytest.approx(float(cs["normfft"]), rel=1e-15 if cs["dtype"] == np.float64 else 1e-6)
+    pd = torch.from_numpy(p.copy()).to(_dev())
+    if helmholtz:
+        cb.solve_helmholtz(ng, ng, sd.arrplan, sd.normfft, cases.ALPHA, sd.lambdaxy, sd.a, sd.b, sd.c, None, None, None,
+                           cs["cbc"], cs["c_or_f"], pd)
+    else:
+        cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cs["cbc"], cs["c_or_f"], pd)
+    torch.cuda.synchronize()
+    return pd.cpu().numpy(), sd, ctx
+
+
+# ------------------------------------------------------------------ stages ---
+R2R_KINDS = {"R2HC": 0, "HC2R": 1, "REDFT00": 3, "REDFT01": 4, "REDFT10": 5, "REDFT11": 6,
+             "RODFT00": 7, "RODFT01": 8, "RODFT10": 9, "RODFT11": 10}
+
+
+@pytest.mark.parametrize("kname", sorted(R2R_KINDS))
+@pytest.mark.parametrize("n", [2, 3, 8, 9, 30, 34, 64, 96, 250])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_r2r_stage(cb, S, kname, n, axis):
+    """cansb200_r2r == `call fft(plan, arr)` (src/fft.f90:247-258), every FFTW kind the reference can plan."""
+    kind = R2R_KINDS[kname]
+    if kname == "REDFT00" and n < 2:
+        pytest.skip("REDFT00 needs n >= 2")
+    other = 5 if axis == 0 else 19
+    shape = (3, n, other) if axis == 1 else (3, other, n)
+    rng = np.random.default_rng(n * 31 + kind)
+    x = rng.uniform(-1, 1, shape)
+    ref = O.r2r_1d(x, kind, axis=2 - axis)
+    ctx = cb.Context([shape[2], shape[1], shape[0]])
+    xd = torch.from_numpy(x.copy()).to(_dev())
+    S.r2r(ctx, kind, n, axis, xd)
+    torch.cuda.synchronize()
+    got = xd.cpu().numpy()
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-14 * max(1.0, np.log2(n))
+
+
+@pytest.mark.parametrize("n,axis", [(512, 0), (1024, 0), (2048, 0), (512, 1), (768, 1), (1024, 1)])
+@pytest.mark.parametrize("kname", ["R2HC", "HC2R", "REDFT10", "REDFT01", "RODFT10", "RODFT01"])
+def test_r2r_stage_bench_sizes(cb, S, kname, n, axis):
+    """The line lengths of BASELINE.json's configs (512, 768, 1024, 2048) on ragged batches."""
+    kind = R2R_KINDS[kname]
+    shape = (2, 21, n) if axis == 0 else (2, n, 37)
+    rng = np.random.default_rng(n + kind)
+    x = rng.uniform(-1, 1, shape)
+    ref = O.r2r_1d(x, kind, axis=2 - axis)
+    ctx = cb.Context([shape[2], shape[1], shape[0]])
+    xd = torch.from_numpy(x.copy()).to(_dev())
+    S.r2r(ctx, kind, n, axis, xd)
+    got = xd.cpu().numpy()
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 5e-14
+
+
+def test_r2r_partial_length_leaves_tail(cb, S):
+    """Face-centred Dirichlet lines transform n-1 points and leave the last one alone (src/fft.f90:82,87)."""
+    rng = np.random.default_rng(5)
+    for axis, shape in ((0, (3, 7, 16)), (1, (3, 16, 7))):
+        x = rng.uniform(-1, 1, shape)
+        ref = x.copy()
+        sl = [slice(None)] * 3
+        sl[2 - axis] = slice(0, 15)
+        ref[tuple(sl)] = O.r2r_1d(np.ascontiguousarray(x[tuple(sl)]), O.FFTW_RODFT00, axis=2 - axis)
+        ctx = cb.Context([shape[2], shape[1], shape[0]])
+        xd = torch.from_numpy(x.copy()).to(_dev())
+        S.r2r(ctx, O.FFTW_RODFT00, 15, axis, xd)
+        assert np.abs(xd.cpu().numpy() - ref).max() < 1e-13
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", ["C1_ldc_2x64x64", "C2s_triperiodic", "C3s_channel", "periodic_z_odd", "tiny_z",
+                                  "nz_gt_512", "helm_w_face_z", "dirichlet_xyz"])
+def test_gaussel_stage(cb, S, name, variant):
+    """cansb200_gaussel == gaussel (src/solver.f90:114-307): pivot pin, periodic closure, q = 1."""
+    cs = cases.build_case(name)
+    ng = cs["ng"]
+    rng = np.random.default_rng(11)
+    pz = rng.uniform(-1, 1, (ng[2], ng[1], ng[0]))
+    q = 1 if (cs["c_or_f"][2] == "f" and cs["cbc"][2][1] == "D") else 0
+    per = cs["cbc"][2] == cases.P
+    ref = pz.copy()
+    O.gaussel(ng[2] - q, cs["a"], cs["b"], cs["c"], per, cs["normfft"], ref, cs["lambdaxy"])
+    ctx = cb.Context(ng)
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cs["cbc"], cs["bc"], cs["c_or_f"], device=_dev(),
+                       thomas_variant=variant)
+    pd = torch.from_numpy(pz.copy()).to(_dev())
+    S.gaussel(sd.arrplan, ng[2] - q, sd.a, sd.b, sd.c, per, sd.normfft, pd, sd.lambdaxy)
+    got = pd.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = cases.rel_l2(got, ref)
+    if variant == 0:
+        assert np.array_equal(got, ref), f"sequential variant must be bit-identical to the reference order (rel {err:.2e})"
+    assert err < 1e-13, err
+
+
+# ------------------------------------------------------------- full solves ---
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_solver_matches_oracle(cb, name):
+    cs = cases.build_case(name)
+    p = cases.make_rhs(cs)
+    helm = name in cases.HELMHOLTZ
+    ref = cases.oracle_solve(name, cs, p, helmholtz=helm)
+    got, sd, ctx = _gpu_solve(cb, cs, p, helmholtz=helm)
+    I = (slice(1, -1),) * 3
+    err = cases.rel_l2(got[I], ref[I])
+    assert err < TOL[cs["dtype"]], f"{name}: rel L2 {err:.3e}"
+    # halo cells must be left untouched (boundp refills them, src/main.f90:468)
+    halo = np.ones(got.shape, bool)
+    halo[I] = False
+    assert np.array_equal(got[halo], p[halo])
+
+
+@pytest.mark.parametrize("name", [f[:-4] for f in sorted(os.listdir(os.path.join(os.path.dirname(__file__), "golden")))
+                                  if f.endswith(".npz")])
+def test_solver_matches_golden(cb, name):
+    cs = cases.build_case(name)
+    p = cases.make_rhs(cs)
+    got, _, _ = _gpu_solve(cb, cs, p, helmholtz=name in cases.HELMHOLTZ)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))["p"]
+    assert cases.rel_l2(got[1:-1, 1:-1, 1:-1], gold) < TOL[cs["dtype"]]
+
+
+@pytest.mark.parametrize("name", ["C1_ldc_2x64x64", "C3s_channel", "C2s_triperiodic"])
+def test_sequential_thomas_variant(cb, name):
+    cs = cases.build_case(name)
+    p = cases.make_rhs(cs)
+    ref = cases.oracle_solve(name, cs, p)
+    got, _, _ = _gpu_solve(cb, cs, p, thomas_variant=0)
+    assert cases.rel_l2(got[1:-1, 1:-1, 1:-1], ref[1:-1, 1:-1, 1:-1]) < 1e-12
+
+
+def test_host_memory_mode(cb):
+    """CPU-built CaNS passes host arrays; the library stages them (mode A)."""
+    name = "C3s_channel"
+    cs = cases.build_case(name)
+    p = cases.make_rhs(cs)
+    ref = cases.oracle_solve(name, cs, p)
+    ctx = cb.Context(cs["ng"])
+    sd = cb.initsolver(ctx, cs["ng"], cs["dli"], cs["dzci"], cs["dzfi"], cs["cbc"], cs["bc"], cs["c_or_f"])
+    ph = p.copy()
+    cb.solver(cs["ng"], cs["ng"], sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cs["cbc"], cs["c_or_f"], ph)
+    assert cases.rel_l2(ph, ref) < 1e-12
+
+
+def test_factorisation_cache(cb):
+    """b and normfft change per Helmholtz call (src/solve_helmholtz.f90:63-71): the pivot cache must
+    notice, refactor, and hit again when an earlier operator returns."""
+    name = "helm_w_face_z"
+    cs = cases.build_case(name)
+    ng = cs["ng"]
+    ctx = cb.Context(ng)
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cs["cbc"], cs["bc"], cs["c_or_f"], device=_dev(),
+                       cache_slots=2)
+    p0 = cases.make_rhs(cs)
+    alphas = [-0.01, -0.02, -0.01, -0.02, -0.03, -0.01]
+    for al in alphas:
+        ref = p0.copy()
+        O.solve_helmholtz(ng, ng, cs["arrplan"], cs["normfft"], al, cs["lambdaxy"], cs["a"], cs["b"], cs["c"], None, None,
+                          None, cs["cbc"], cs["c_or_f"], ref)
+        pd = torch.from_numpy(p0.copy()).to(_dev())
+        cb.solve_helmholtz(ng, ng, sd.arrplan, sd.normfft, al, sd.lambdaxy, sd.a, sd.b, sd.c, None, None, None,
+                           cs["cbc"], cs["c_or_f"], pd)
+        assert cases.rel_l2(pd.cpu().numpy(), ref) < 1e-12
+    st = sd.arrplan.stats()
+    assert st["solves"] == len(alphas)
+    assert st["factorisations"] == 4  # -0.01, -0.02, (hit, hit), -0.03 evicts LRU (-0.01), -0.01 again
+
+
+def test_argument_errors(cb):
+    ctx = cb.Context([8, 8, 8])
+    with pytest.raises(Exception):
+        cb.Plan(ctx, [["P", "N"], ["P", "P"], ["N", "N"]], ["c"] * 3)  # periodic on one side only
+    plan = cb.Plan(ctx, [["P", "P"]] * 2 + [["N", "N"]], ["c"] * 3)
+    bad = torch.zeros((10, 10, 9), dtype=torch.float64, device=_dev())
+    lam = torch.zeros((8, 8), dtype=torch.float64, device=_dev())
+    v = torch.zeros(8, dtype=torch.float64, device=_dev())
+    with pytest.raises(ValueError):
+        cb.solver([8, 8, 8], [8, 8, 8], plan, 1.0, lam, v, v, v, [["P", "P"]] * 2 + [["N", "N"]], ["c"] * 3, bad)
+
+
+# ------------------------------------------- the steps either side + sanity ---
+def test_sanity_solver_on_gpu(cb, S):
+    """The reference's in-binary self-test (src/sanity.f90:262-283) with every step on the device:
+    noise -> fillps -> solver -> boundp (host-free: periodic/Neumann halos via torch) -> correc -> chkdiv."""
+    ng, l = [64, 48, 40], [6.0, 3.0, 2.0]
+    cbc = [cases.P, cases.P, cases.N]
+    cs = O.make_case(ng, l, cbc, gr=1.5)
+    ctx = cb.Context(ng)
+    dev = _dev()
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], ["c"] * 3, device=dev)
+    shp = (ng[2] + 2, ng[1] + 2, ng[0] + 2)
+    u, v, w, p = (torch.zeros(shp, dtype=torch.float64, device=dev) for _ in range(4))
+    for t, seed in ((u, 123), (v, 456), (w, 789)):
+        S.fill_hash(ctx, t, ng, [1, 1, 1], 1, seed)
+        t.mul_(0.5)
+    uh = np.zeros(shp)
+    uh[1:-1, 1:-1, 1:-1] = 0.5 * O.hash_field(ng, 123)
+    assert np.array_equal(u.cpu().numpy(), uh), "device hash field must equal the oracle's"
+
+    def bounduvw():
+        for t in (u, v, w):  # periodic x, y
+            t[:, :, 0] = t[:, :, -2]; t[:, :, -1] = t[:, :, 1]
+            t[:, 0, :] = t[:, -2, :]; t[:, -1, :] = t[:, 1, :]
+        for t in (u, v):     # no-slip walls in z (cell centred: antisymmetric ghost)
+            t[0] = -t[1]; t[-1] = -t[-2]
+        w[0] = 0.0; w[-2] = 0.0; w[-1] = w[-3]
+
+    bounduvw()
+    dzfi = torch.from_numpy(cs["dzfi"]).to(dev)
+    dzci = torch.from_numpy(cs["dzci"]).to(dev)
+    dt = float(np.arccos(-1.0))
+    S.fillps(ctx, ng, cs["dli"], dzfi, 1.0 / dt, u, v, w, p)
+    cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, ["c"] * 3, p)
+    p[:, :, 0] = p[:, :, -2]; p[:, :, -1] = p[:, :, 1]
+    p[:, 0, :] = p[:, -2, :]; p[:, -1, :] = p[:, 1, :]
+    p[0] = p[1]; p[-1] = p[-2]
+    S.correc(ctx, ng, cs["dli"], dzci, dt, p, u, v, w)
+    divtot, divmax = S.chkdiv(ctx, ng, l, cs["dli"], dzfi, u, v, w)
+    assert divmax < O.small(np.float64), divmax
+
+
+@pytest.mark.parametrize("ng,cbc,gr", [
+    ([512, 512, 512], [cases.P, cases.P, cases.P], 0.0),    # C2 triperiodic TGV grid
+    ([1024, 512, 512], [cases.P, cases.P, cases.N], 2.0),   # C3 channel
+    ([1024, 768, 768], [cases.P, cases.N, cases.N], 1.5),   # C4 duct (radix-3 stage, DCT in y)
+])
+def test_full_size_residual(cb, S, ng, cbc, gr):
+    """At BASELINE.json's full sizes the oracle is too slow; check size-independent properties:
+    the discrete Poisson residual (chk_poisson, src/debug.f90:91-132) and linearity."""
+    l = [6.2832, 6.2832, 6.2832] if gr == 0.0 else [12.0, 6.0, 2.0]
+    per_z = cbc[2] == cases.P
+    dzc, dzf, _, _ = O.initgrid(1, ng[2], gr, l[2], per_z)
+    dli = [ng[0] / l[0], ng[1] / l[1], ng[2] / l[2]]
+    ctx = cb.Context(ng)
+    dev = _dev()
+    sd = cb.initsolver(ctx, ng, dli, 1.0 / dzc, 1.0 / dzf, cbc, [[0.0, 0.0]] * 3, ["c"] * 3, device=dev)
+    shp = (ng[2] + 2, ng[1] + 2, ng[0] + 2)
+    p = torch.empty(shp, dtype=torch.float64, device=dev)
+    S.fill_hash(ctx, p, ng, [1, 1, 1], 1, 123)
+    I = (slice(1, -1),) * 3
+    wz = torch.from_numpy(dzf[1:-1]).to(dev)[:, None, None]
+    p[I] -= (p[I] * wz).sum() / (wz.sum() * ng[0] * ng[1])  # compatibility (singular operator)
+    rhs = p[I].clone()
+    cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, ["c"] * 3, p)
+    assert torch.isfinite(p).all()
+    # halos: periodic wrap or Neumann mirror
+    for ax, b in ((2, cbc[0]), (1, cbc[1]), (0, cbc[2])):
+        lo, hi = [slice(None)] * 3, [slice(None)] * 3
+        src_lo, src_hi = [slice(None)] * 3, [slice(None)] * 3
+        lo[ax], hi[ax] = 0, -1
+        src_lo[ax], src_hi[ax] = (-2, 1) if b == cases.P else (1, -2)
+        p[tuple(lo)] = p[tuple(src_lo)]
+        p[tuple(hi)] = p[tuple(src_hi)]
+    dzci = torch.from_numpy(1.0 / dzc).to(dev)
+    dzfi = torch.from_numpy(1.0 / dzf).to(dev)
+    c0 = p[I]
+    lap = (p[1:-1, 1:-1, 2:] - 2 * c0 + p[1:-1, 1:-1, :-2]) * dli[0] ** 2
+    lap += (p[1:-1, 2:, 1:-1] - 2 * c0 + p[1:-1, :-2, 1:-1]) * dli[1] ** 2
+    lap += ((p[2:, 1:-1, 1:-1] - c0) * dzci[1:-1, None, None] - (c0 - p[:-2, 1:-1, 1:-1]) * dzci[:-2, None, None]) * dzfi[1:-1, None, None]
+    resmax = float((lap - rhs).abs().max())
+    del lap
+    assert resmax < O.small(np.float64), resmax
+    st = sd.arrplan.stats()
+    assert st["factorisations"] == 1
