@@ -50,6 +50,7 @@ SYMBOLS = {
     "cansb200_plan_stats": (C.c_int, [_VP, C.POINTER(C.c_ulonglong)]),
     "cansb200_set_profiling": (C.c_int, [_VP, C.c_int]),
     "cansb200_get_profile": (C.c_int, [_VP, _D3, C.POINTER(C.c_ulonglong)]),
+    "cansb200_ctx_set": (C.c_int, [_VP, C.c_int, C.c_int]),
     "cansb200_get_work": (C.c_int, [_VP, C.c_int, C.POINTER(_VP), C.POINTER(C.c_size_t)]),
 }
 

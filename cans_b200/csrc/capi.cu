@@ -13,9 +13,22 @@
 #include "aux_kernels.cuh"
 #include "fft_kernels.cuh"
 #include "fft_plan.hpp"
+#include "r2r2.cuh"
 #include "thomas_kernels.cuh"
 
 using namespace cb;
+
+namespace cb {
+// explicit instantiations live in r2r2_{x,y}{64,32}.cu
+template <class T, bool YMODE> int r2r2_run(const R2Args<T>& A, int n, int var, bool fwd, cudaStream_t st);
+template <bool YMODE> int r2r2_query(int n, int var, int radix[4]);
+extern template int r2r2_run<double, false>(const R2Args<double>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<double, true>(const R2Args<double>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<float, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<float, true>(const R2Args<float>&, int, int, bool, cudaStream_t);
+extern template int r2r2_query<false>(int, int, int[4]);
+extern template int r2r2_query<true>(int, int, int[4]);
+}  // namespace cb
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -59,6 +72,12 @@ template <class T> struct DirectTables {
   C2<T>* cs = nullptr;
 };
 
+// tables of the two-for-one fast path (r2r2.cuh), one set per (length, mode)
+template <class T> struct R2Tables {
+  Cx<T>* tw[4] = {nullptr, nullptr, nullptr, nullptr};
+  Cx<T>* mak = nullptr;
+};
+
 struct cansb200_ctx {
   int ng[3], dims[2], ipencil_axis, rank, nranks, is_fp32;
   int n[3], lo[3], n_z[3], lo_z[3];
@@ -70,6 +89,10 @@ struct cansb200_ctx {
   std::map<int, FftTables<float>> tabs32;
   std::map<long long, DirectTables<double>> dtabs64;
   std::map<long long, DirectTables<float>> dtabs32;
+  std::map<int, R2Tables<double>> r2tabs64;   // key = (n * 4 + variant) * 2 + ymode
+  std::map<int, R2Tables<float>> r2tabs32;
+  int force_generic = 0;                       // tests: route every transform through the generic engine
+  int r2_variant[2] = {0, 0};                  // tuning variant of the fast path, [x, y]
   unsigned long long launches = 0;
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
   bool profiling = false;
@@ -106,6 +129,52 @@ template <> std::map<int, FftTables<float>>& tabmap<float>(cansb200_ctx* c) { re
 template <class T> static std::map<long long, DirectTables<T>>& dtabmap(cansb200_ctx* c);
 template <> std::map<long long, DirectTables<double>>& dtabmap<double>(cansb200_ctx* c) { return c->dtabs64; }
 template <> std::map<long long, DirectTables<float>>& dtabmap<float>(cansb200_ctx* c) { return c->dtabs32; }
+
+template <class T> static std::map<int, R2Tables<T>>& r2tabmap(cansb200_ctx* c);
+template <> std::map<int, R2Tables<double>>& r2tabmap<double>(cansb200_ctx* c) { return c->r2tabs64; }
+template <> std::map<int, R2Tables<float>>& r2tabmap<float>(cansb200_ctx* c) { return c->r2tabs32; }
+
+// twiddles of the fast path: stage s holds w_{Ns}^{o r} at [(r-1) L + o]; mak[k] = (cos, sin)(pi k / 2n)
+template <class T> static int get_r2_tables(cansb200_ctx* ctx, int n, int ymode, int& var, R2Tables<T>** out) {
+  auto& mp = r2tabmap<T>(ctx);
+  int radix[4];
+  int ns = ymode ? r2r2_query<true>(n, var, radix) : r2r2_query<false>(n, var, radix);
+  if (ns < 1 && var != 0) {
+    var = 0;
+    ns = ymode ? r2r2_query<true>(n, var, radix) : r2r2_query<false>(n, var, radix);
+  }
+  const int key = (n * 4 + var) * 2 + (ymode ? 1 : 0);
+  auto it = mp.find(key);
+  if (it != mp.end()) { *out = &it->second; return 0; }
+  if (ns < 1) { *out = nullptr; return 0; }
+  R2Tables<T> t;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  int Ns = n;
+  for (int s = 0; s < ns; ++s) {
+    const int Rs = radix[s], L = Ns / Rs;
+    if (L > 1) {
+      std::vector<Cx<T>> h((size_t)(Rs - 1) * L);
+      for (int r = 1; r < Rs; ++r)
+        for (int o = 0; o < L; ++o) {
+          const long double a = -2.0L * pi * (long double)((long long)o * r) / Ns;
+          h[(size_t)(r - 1) * L + o] = Cx<T>{(T)cosl(a), (T)sinl(a)};
+        }
+      CK(cudaMalloc(&t.tw[s], sizeof(Cx<T>) * h.size()));
+      CK(cudaMemcpy(t.tw[s], h.data(), sizeof(Cx<T>) * h.size(), cudaMemcpyHostToDevice));
+    }
+    Ns = L;
+  }
+  std::vector<Cx<T>> mk((size_t)n / 2 + 1);
+  for (int k = 0; k <= n / 2; ++k) {
+    const long double a = pi * k / (2.0L * n);
+    mk[k] = Cx<T>{(T)cosl(a), (T)sinl(a)};
+  }
+  CK(cudaMalloc(&t.mak, sizeof(Cx<T>) * mk.size()));
+  CK(cudaMemcpy(t.mak, mk.data(), sizeof(Cx<T>) * mk.size(), cudaMemcpyHostToDevice));
+  auto res = mp.emplace(key, t);
+  *out = &res.first->second;
+  return 0;
+}
 
 template <class T> static int get_tables(cansb200_ctx* ctx, int n, FftTables<T>** out) {
   auto& mp = tabmap<T>(ctx);
@@ -162,6 +231,40 @@ template <class T>
 static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, const R2RGeom& g, int tile_hint,
                    cudaStream_t st) {
   if (nt < 1 || g.lines_per_group < 1 || g.ngroups < 1) return 0;
+  // fast path: two-for-one register transforms (r2r2.cuh) for the instantiated lengths
+  if (!ctx->force_generic && kind_is_fast(kind)) {
+    bool ok = true;
+    if (g.ymode) {
+      // column pairs are moved as 16-byte (2 x T) vectors
+      const size_t al = 2 * sizeof(T);
+      ok = g.in_ls == 1 && g.out_ls == 1 && (g.in_es % 2) == 0 && (g.out_es % 2) == 0 && (g.in_gs % 2) == 0 &&
+           (g.out_gs % 2) == 0 && ((uintptr_t)in % al) == 0 && ((uintptr_t)out % al) == 0;
+    } else {
+      ok = g.in_es == 1 && g.out_es == 1;
+    }
+    R2Tables<T>* rt = nullptr;
+    int var = ctx->r2_variant[g.ymode ? 1 : 0];
+    if (ok) {
+      int rc = get_r2_tables<T>(ctx, nt, g.ymode, var, &rt);
+      if (rc) return rc;
+    }
+    if (ok && rt) {
+      R2Args<T> A;
+      A.in = in; A.out = out;
+      A.in_es = g.in_es; A.out_es = g.out_es; A.in_ls = g.in_ls; A.out_ls = g.out_ls; A.in_gs = g.in_gs; A.out_gs = g.out_gs;
+      A.lines_per_group = g.lines_per_group; A.ngroups = g.ngroups; A.line_len = g.line_len; A.kind = kind;
+      for (int s = 0; s < 4; ++s) A.tw[s] = rt->tw[s];
+      A.mak = rt->mak;
+      const int rc = g.ymode ? r2r2_run<T, true>(A, nt, var, kind_is_forward(kind), st)
+                             : r2r2_run<T, false>(A, nt, var, kind_is_forward(kind), st);
+      if (rc < 0) return fail(CANSB200_ECUDA, "r2r: fast-path launch failed");
+      if (rc == 0) {
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
+      }
+    }
+  }
   FftTables<T>* tb;
   int rc = get_tables<T>(ctx, nt, &tb);
   if (rc) return rc;
@@ -231,19 +334,24 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   ThomasDev<T> D;
   D.nx = nx; D.ny = ny; D.n = n_rows; D.periodic = periodic; D.nn = periodic ? n_rows - 1 : n_rows;
   D.sj = sj; D.sk = sk; D.a = a; D.b = b; D.c = c; D.lam = lam; D.lam_sj = nx;
-  D.m = pl->th_m; D.chunk_layout = pl->th_variant == 1;
+  D.m = pl->th_m; D.chunk_layout = 0;
   return D;
 }
 
 template <class T, int MMAX>
-static int launch_warp(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, cudaStream_t st) {
-  constexpr int CX = 8;
-  auto kfn = thomas_warp_kernel<T, MMAX, CX>;
-  const size_t smem = ((size_t)CX * thomas_kp(D.m) + 2 * 32 * MMAX) * sizeof(T);
-  CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  const long long tiles = (long long)((D.nx + CX - 1) / CX) * D.ny;
-  kfn<<<(unsigned)tiles, 32 * CX, smem, st>>>(D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
-                                             (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm);
+static int launch_reg(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, cudaStream_t st) {
+  auto kfn = thomas_reg_kernel<T, MMAX>;
+  const size_t smem = thomas_reg_smem<T, MMAX>();
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const long long ncol = (long long)D.nx * D.ny;
+  const long long tiles = (ncol + CB_TH_COLS - 1) / CB_TH_COLS;
+  kfn<<<(unsigned)tiles, CB_TH_COLS * CB_TH_CHUNKS, smem, st>>>(D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p,
+                                                              (const T*)pl->p2cache.p, (const T*)pl->dencache.p, pl->slot_z,
+                                                              pl->slot_den, p, norm);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -273,11 +381,10 @@ static int run_gaussel(cansb200_plan* pl, T* p, int nx, int ny, long long sj, lo
   prof_mark(ctx, st);
   if (pl->th_variant == 1) {
     switch (pl->th_mmax) {
-      case 4: return launch_warp<T, 4>(ctx, D, pl, p, norm, st);
-      case 8: return launch_warp<T, 8>(ctx, D, pl, p, norm, st);
-      case 16: return launch_warp<T, 16>(ctx, D, pl, p, norm, st);
-      case 24: return launch_warp<T, 24>(ctx, D, pl, p, norm, st);
-      default: return launch_warp<T, 32>(ctx, D, pl, p, norm, st);
+      case 4: return launch_reg<T, 4>(ctx, D, pl, p, norm, st);
+      case 8: return launch_reg<T, 8>(ctx, D, pl, p, norm, st);
+      case 16: return launch_reg<T, 16>(ctx, D, pl, p, norm, st);
+      default: return launch_reg<T, 32>(ctx, D, pl, p, norm, st);
     }
   }
   thomas_seq_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(D, cs, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
@@ -338,6 +445,8 @@ int cansb200_finalize(cansb200_ctx* c) {
   c->scratch.release(); c->staging.release(); c->coef.release();
   for (auto& kv : c->tabs64) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (auto& kv : c->tabs32) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
+  for (auto& kv : c->r2tabs64) { for (int q = 0; q < 4; ++q) cudaFree(kv.second.tw[q]); cudaFree(kv.second.mak); }
+  for (auto& kv : c->r2tabs32) { for (int q = 0; q < 4; ++q) cudaFree(kv.second.tw[q]); cudaFree(kv.second.mak); }
   for (auto& kv : c->dtabs64) cudaFree(kv.second.cs);
   for (auto& kv : c->dtabs32) cudaFree(kv.second.cs);
   delete c;
@@ -353,6 +462,17 @@ int cansb200_get_extents(const cansb200_ctx* c, int n[3], int lo[3], int n_z[3],
     if (lo_z) lo_z[d] = c->lo_z[d];
   }
   return 0;
+}
+
+int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
+  if (!c) return fail(CANSB200_EINVAL, "null ctx");
+  if (what == CANSB200_CTX_FORCE_GENERIC) { c->force_generic = value ? 1 : 0; return 0; }
+  if (what == CANSB200_CTX_X_VARIANT || what == CANSB200_CTX_Y_VARIANT) {
+    if (value < 0 || value > 3) return fail(CANSB200_EINVAL, "ctx_set: variant must be 0..3");
+    c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
+    return 0;
+  }
+  return fail(CANSB200_EINVAL, "ctx_set: unknown switch");
 }
 
 int cansb200_get_work(cansb200_ctx* c, int which, void** ptr, size_t* nelem) {
@@ -402,10 +522,10 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   int variant = o.thomas_variant >= 0 ? o.thomas_variant : 1;
   if (pl->th_m > 32) variant = 0;
   pl->th_variant = variant;
-  pl->th_mmax = pl->th_m <= 4 ? 4 : pl->th_m <= 8 ? 8 : pl->th_m <= 16 ? 16 : pl->th_m <= 24 ? 24 : 32;
+  pl->th_mmax = pl->th_m <= 4 ? 4 : pl->th_m <= 8 ? 8 : pl->th_m <= 16 ? 16 : 32;
   pl->nslots = o.cache_slots >= 1 ? (o.cache_slots > CB_MAX_SLOTS ? CB_MAX_SLOTS : o.cache_slots) : 1;
   const long long ncol = (long long)ctx->n_z[0] * ctx->n_z[1];
-  pl->slot_z = variant == 1 ? ncol * pl->th_m * 32 : ncol * pl->th_nn;
+  pl->slot_z = ncol * pl->th_nn;
   pl->slot_den = ncol;
   if (pl->zcache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: pivot cache");
   if (pl->periodic_z) {

@@ -1,0 +1,514 @@
+// Two-for-one register-resident batched r2r transforms (sm_100a fast path).
+//
+// Replaces one `call fft(arrplan(idir,fb), arr)` of the reference CPU path
+// (/root/reference/src/fft.f90:247-258; FFTW guru r2r plans :83-97,:148-162)
+// and the cuFFT + OpenACC Makhoul passes of the reference GPU path
+// (src/fft.f90:369-401, :452-767) with ONE kernel per transform that touches
+// HBM once (read the field, write the field).
+//
+// Algorithm.  Two real lines a, b are transformed by one complex FFT of the
+// full length N on z = a + i b ("two-for-one"); the spectra are separated with
+//     A_k = (Z_k + conj Z_{N-k}) / 2,   B_k = (Z_k - conj Z_{N-k}) / (2i)
+// which needs no twiddle factors.  In x (contiguous lines) the pair is two
+// consecutive lines; in y (strided lines) it is two adjacent x columns, so one
+// 16-byte element of a 128-byte row is one complex sample.  The cosine / sine
+// kinds use Makhoul's permutation v_j = x_{2j} | x_{2(N-1-j)+1} at load time
+// and the quarter-wave rotation in the separation pass.
+//
+// Forward kinds run decimation-in-frequency: natural-order samples go straight
+// from global memory into registers (coalesced), each thread owns E = N / TPL
+// samples, stages exchange through shared memory in place, the spectrum ends
+// digit-reversed in shared memory and the separation pass gathers (k, N-k).
+// Backward kinds run the transposed network (decimation-in-time): the
+// pre-pass scatters Z_k to its digit-reversed slot (re/im swapped, which turns
+// the forward butterflies into the inverse transform), and the last stage
+// leaves natural-order samples in registers that are stored coalesced.
+//
+// Shared memory: x mode keeps one region of N complex per transform with an
+// XOR swizzle of the low 3 (FP64) / 4 (FP32) index bits, which makes the
+// strided butterfly accesses of every stage conflict free; y mode keeps
+// [position][column pair], whose rows are exactly 128 bytes, so any set of
+// rows is conflict free.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fft_engine.cuh"  // Kind constants
+
+namespace cb {
+
+template <class T> struct __align__(sizeof(T) * 2) Cx { T x, y; };
+
+template <class T> __device__ __forceinline__ Cx<T> cx_add(Cx<T> a, Cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <class T> __device__ __forceinline__ Cx<T> cx_sub(Cx<T> a, Cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <class T> __device__ __forceinline__ Cx<T> cx_mul(Cx<T> a, Cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+template <class T> __device__ __forceinline__ Cx<T> cx_mi(Cx<T> a) { return {a.y, -a.x}; }  // * (-i)
+__device__ __forceinline__ Cx<double> cx_ldg(const Cx<double>* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return {v.x, v.y};
+}
+__device__ __forceinline__ Cx<float> cx_ldg(const Cx<float>* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return {v.x, v.y};
+}
+
+// ---- register butterflies: forward sign, natural in, natural out --------------------------------
+template <class T> __device__ __forceinline__ void bf2(Cx<T>* a) {
+  const Cx<T> t = a[0];
+  a[0] = cx_add(t, a[1]);
+  a[1] = cx_sub(t, a[1]);
+}
+template <class T> __device__ __forceinline__ void bf3(Cx<T>* a) {
+  const T c = T(0.86602540378443864676372317075294);
+  const Cx<T> s = cx_add(a[1], a[2]), d = cx_sub(a[1], a[2]);
+  const Cx<T> m = {a[0].x - T(0.5) * s.x, a[0].y - T(0.5) * s.y};
+  a[0] = cx_add(a[0], s);
+  a[1] = {m.x + c * d.y, m.y - c * d.x};
+  a[2] = {m.x - c * d.y, m.y + c * d.x};
+}
+template <class T> __device__ __forceinline__ void bf4(Cx<T>& a0, Cx<T>& a1, Cx<T>& a2, Cx<T>& a3) {
+  const Cx<T> t0 = cx_add(a0, a2), t1 = cx_sub(a0, a2), t2 = cx_add(a1, a3), t3 = cx_sub(a1, a3);
+  a0 = cx_add(t0, t2);
+  a2 = cx_sub(t0, t2);
+  a1 = {t1.x + t3.y, t1.y - t3.x};
+  a3 = {t1.x - t3.y, t1.y + t3.x};
+}
+template <class T> __device__ __forceinline__ void bf5(Cx<T>* a) {
+  const T c1 = T(0.30901699437494742410229341718282), c2 = T(-0.80901699437494742410229341718282);
+  const T s1 = T(0.95105651629515357211643933337938), s2 = T(0.58778525229247312916870595463907);
+  const Cx<T> p1 = cx_add(a[1], a[4]), m1 = cx_sub(a[1], a[4]);
+  const Cx<T> p2 = cx_add(a[2], a[3]), m2 = cx_sub(a[2], a[3]);
+  const Cx<T> a0 = a[0];
+  a[0] = {a0.x + p1.x + p2.x, a0.y + p1.y + p2.y};
+  const Cx<T> u1 = {a0.x + c1 * p1.x + c2 * p2.x, a0.y + c1 * p1.y + c2 * p2.y};
+  const Cx<T> u2 = {a0.x + c2 * p1.x + c1 * p2.x, a0.y + c2 * p1.y + c1 * p2.y};
+  const Cx<T> v1 = {s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y};
+  const Cx<T> v2 = {s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y};
+  a[1] = {u1.x + v1.y, u1.y - v1.x};
+  a[4] = {u1.x - v1.y, u1.y + v1.x};
+  a[2] = {u2.x + v2.y, u2.y - v2.x};
+  a[3] = {u2.x - v2.y, u2.y + v2.x};
+}
+template <class T> __device__ __forceinline__ void bf8(Cx<T>* a) {
+  const T h = T(0.70710678118654752440084436210485);
+  bf4(a[0], a[2], a[4], a[6]);
+  bf4(a[1], a[3], a[5], a[7]);
+  const Cx<T> o1 = {h * (a[3].x + a[3].y), h * (a[3].y - a[3].x)};
+  const Cx<T> o2 = cx_mi(a[5]);
+  const Cx<T> o3 = {h * (a[7].y - a[7].x), -h * (a[7].x + a[7].y)};
+  const Cx<T> e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1];
+  a[0] = cx_add(e0, o0); a[4] = cx_sub(e0, o0);
+  a[1] = cx_add(e1, o1); a[5] = cx_sub(e1, o1);
+  a[2] = cx_add(e2, o2); a[6] = cx_sub(e2, o2);
+  a[3] = cx_add(e3, o3); a[7] = cx_sub(e3, o3);
+}
+// 12 = 4 x 3: n = 3 n1 + n2, k = k1 + 4 k2
+template <class T> __device__ __forceinline__ void bf12(Cx<T>* a) {
+  const T c = T(0.86602540378443864676372317075294);
+#pragma unroll
+  for (int n2 = 0; n2 < 3; ++n2) bf4(a[n2], a[n2 + 3], a[n2 + 6], a[n2 + 9]);
+  // a[n2 + 3 k1] = B[n2][k1]; twiddle w12^(n2 k1)
+  const Cx<T> w1 = {c, T(-0.5)}, w2 = {T(0.5), -c}, w4 = {T(-0.5), -c};
+  a[1 + 3] = cx_mul(a[1 + 3], w1); a[1 + 6] = cx_mul(a[1 + 6], w2); a[1 + 9] = cx_mi(a[1 + 9]);
+  a[2 + 3] = cx_mul(a[2 + 3], w2); a[2 + 6] = cx_mul(a[2 + 6], w4); a[2 + 9] = {-a[2 + 9].x, -a[2 + 9].y};
+  Cx<T> o[12];
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    Cx<T> b[3] = {a[3 * k1], a[3 * k1 + 1], a[3 * k1 + 2]};
+    bf3(b);
+    o[k1] = b[0]; o[k1 + 4] = b[1]; o[k1 + 8] = b[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) a[k] = o[k];
+}
+// 6 = 2 x 3: n = 3 n1 + n2, k = k1 + 2 k2
+template <class T> __device__ __forceinline__ void bf6(Cx<T>* a) {
+  const T c = T(0.86602540378443864676372317075294);
+#pragma unroll
+  for (int n2 = 0; n2 < 3; ++n2) {
+    const Cx<T> t = a[n2];
+    a[n2] = cx_add(t, a[n2 + 3]);
+    a[n2 + 3] = cx_sub(t, a[n2 + 3]);
+  }
+  const Cx<T> w1 = {T(0.5), -c}, w2 = {T(-0.5), -c};
+  a[1 + 3] = cx_mul(a[1 + 3], w1);
+  a[2 + 3] = cx_mul(a[2 + 3], w2);
+  Cx<T> o[6];
+#pragma unroll
+  for (int k1 = 0; k1 < 2; ++k1) {
+    Cx<T> b[3] = {a[3 * k1], a[3 * k1 + 1], a[3 * k1 + 2]};
+    bf3(b);
+    o[k1] = b[0]; o[k1 + 2] = b[1]; o[k1 + 4] = b[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) a[k] = o[k];
+}
+template <class T> __device__ __forceinline__ void bf16(Cx<T>* a) {
+  const T c1 = T(0.92387953251128675612818318939679), s1 = T(0.38268343236508977172845998403040);
+  const T h = T(0.70710678118654752440084436210485);
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) bf4(a[n2], a[n2 + 4], a[n2 + 8], a[n2 + 12]);
+  const Cx<T> w1 = {c1, -s1}, w2 = {h, -h}, w3 = {s1, -c1}, w6 = {-h, -h}, w9 = {-c1, s1};
+  a[5] = cx_mul(a[5], w1);   a[9] = cx_mul(a[9], w2);   a[13] = cx_mul(a[13], w3);
+  a[6] = cx_mul(a[6], w2);   a[10] = cx_mi(a[10]);      a[14] = cx_mul(a[14], w6);
+  a[7] = cx_mul(a[7], w3);   a[11] = cx_mul(a[11], w6); a[15] = cx_mul(a[15], w9);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) bf4(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+    for (int k2 = k1 + 1; k2 < 4; ++k2) {
+      const Cx<T> t = a[4 * k1 + k2];
+      a[4 * k1 + k2] = a[4 * k2 + k1];
+      a[4 * k2 + k1] = t;
+    }
+}
+template <class T, int R> __device__ __forceinline__ void bfR(Cx<T>* a) {
+  static_assert(R == 1 || R == 2 || R == 3 || R == 4 || R == 5 || R == 6 || R == 8 || R == 12 || R == 16, "radix");
+  if (R == 2) bf2(a);
+  else if (R == 3) bf3(a);
+  else if (R == 4) bf4(a[0], a[1], a[2], a[3]);
+  else if (R == 5) bf5(a);
+  else if (R == 6) bf6(a);
+  else if (R == 8) bf8(a);
+  else if (R == 12) bf12(a);
+  else if (R == 16) bf16(a);
+}
+
+// ---- compile-time plan --------------------------------------------------------------------------
+// N = R0 R1 R2 R3 complex length, TPL threads per transform (E = N / TPL samples per thread, every
+// radix divides E), G = transforms per CTA (x mode) / column pairs per CTA (y mode), MINB = CTAs per
+// SM the register allocation must allow (__launch_bounds__).
+template <int N_, int TPL_, int G_, int MINB_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1> struct R2Cfg {
+  static constexpr int N = N_, TPL = TPL_, G = G_, E = N_ / TPL_, MINB = MINB_;
+  static constexpr int NS = R3_ > 1 ? 4 : (R2_ > 1 ? 3 : (R1_ > 1 ? 2 : 1));
+  __host__ __device__ static constexpr int R(int s) { return s == 0 ? R0_ : (s == 1 ? R1_ : (s == 2 ? R2_ : R3_)); }
+  __host__ __device__ static constexpr int Ns(int s) { return s == 0 ? N_ : (s == 1 ? N_ / R0_ : (s == 2 ? N_ / (R0_ * R1_) : N_ / (R0_ * R1_ * R2_))); }
+  static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
+  static_assert(N_ % TPL_ == 0 && E % R0_ == 0 && E % R1_ == 0 && E % R2_ == 0 && E % R3_ == 0, "every radix must divide E");
+  // slot of frequency k after the DIF stages (digit reversal)
+  __host__ __device__ static constexpr int rev(int k) {
+    int pos = 0;
+    pos += (k % R0_) * (N_ / R0_); k /= R0_;
+    pos += (k % R1_) * (N_ / (R0_ * R1_)); k /= R1_;
+    pos += (k % R2_) * (N_ / (R0_ * R1_ * R2_)); k /= R2_;
+    pos += k;
+    return pos;
+  }
+};
+
+template <class T> struct R2Args {
+  const T* in;
+  T* out;
+  long long in_es, out_es;   // element stride along the transform (1 in x mode, the row pitch in y mode)
+  long long in_ls, out_ls;   // stride between consecutive lines of a group
+  long long in_gs, out_gs;   // stride between groups (z planes)
+  int lines_per_group, ngroups, line_len;  // line_len >= N: the tail is copied, not transformed
+  int kind;
+  const Cx<T>* tw[4];        // per stage s: (R_s - 1) * L_s entries, w_{Ns}^{o r} at [(r-1) L + o]
+  const Cx<T>* mak;          // (cos, sin)(pi k / (2N)), k = 0..N/2
+};
+
+template <class T, class Cfg, bool YMODE> struct R2Lay {
+  static constexpr int SW = sizeof(T) == 8 ? 3 : 4;
+  static constexpr int NP = (Cfg::N + (1 << SW) - 1) & ~((1 << SW) - 1);
+  static constexpr size_t smem_bytes() { return (YMODE ? (size_t)Cfg::N * Cfg::G : (size_t)NP * Cfg::G) * sizeof(Cx<T>); }
+  __device__ static __forceinline__ int at(int c, int pos) {
+    if (YMODE) return pos * Cfg::G + c;
+    return c * NP + (pos ^ (((pos >> SW) ^ (pos >> (2 * SW))) & ((1 << SW) - 1)));
+  }
+};
+
+template <int ID, int CNT> __device__ __forceinline__ void r2_named_bar() {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(CNT) : "memory");
+}
+// barrier among the TPL threads of one transform.  Barrier ids are compile-time constants so that
+// ptxas reserves G + 1 hardware barriers per CTA, not all 16 (which would cap the CTAs per SM at 4).
+template <class Cfg, bool YMODE> __device__ __forceinline__ void r2_group_sync(int c) {
+  if (YMODE || Cfg::G == 1) __syncthreads();
+  else if (Cfg::TPL <= 32 && (32 % Cfg::TPL) == 0) __syncwarp();
+  else if ((Cfg::TPL % 32) == 0 && Cfg::G <= 8) {
+    switch (c) {
+      case 0: r2_named_bar<1, Cfg::TPL>(); break;
+      case 1: r2_named_bar<2, Cfg::TPL>(); break;
+      case 2: r2_named_bar<3, Cfg::TPL>(); break;
+      case 3: r2_named_bar<4, Cfg::TPL>(); break;
+      case 4: r2_named_bar<5, Cfg::TPL>(); break;
+      case 5: r2_named_bar<6, Cfg::TPL>(); break;
+      case 6: r2_named_bar<7, Cfg::TPL>(); break;
+      default: r2_named_bar<8, Cfg::TPL>(); break;
+    }
+  } else __syncthreads();
+}
+
+// where my transform lives in global memory
+template <class T> struct R2Loc {
+  long long ia, ib, oa, ob;  // offsets of sequences a and b (x mode: two lines; y mode: ib = ia + 1)
+  bool has_a, has_b;
+};
+
+template <class T, class Cfg, bool YMODE>
+__device__ __forceinline__ R2Loc<T> r2_locate(const R2Args<T>& A, int c) {
+  R2Loc<T> L;
+  if (YMODE) {
+    const int tiles = (A.lines_per_group + 2 * Cfg::G - 1) / (2 * Cfg::G);
+    const int g = blockIdx.x / tiles;
+    const int x = (blockIdx.x - g * tiles) * 2 * Cfg::G + 2 * c;
+    L.ia = (long long)g * A.in_gs + (long long)x * A.in_ls;
+    L.oa = (long long)g * A.out_gs + (long long)x * A.out_ls;
+    L.ib = L.ia + A.in_ls;
+    L.ob = L.oa + A.out_ls;
+    L.has_a = x < A.lines_per_group;
+    L.has_b = x + 1 < A.lines_per_group;
+  } else {
+    const long long nl = (long long)A.lines_per_group * A.ngroups;
+    const long long la = ((long long)blockIdx.x * Cfg::G + c) * 2, lb = la + 1;
+    const long long ga = la / A.lines_per_group, gb = lb / A.lines_per_group;
+    const long long ja = la - ga * A.lines_per_group, jb = lb - gb * A.lines_per_group;
+    L.ia = ga * A.in_gs + ja * A.in_ls;
+    L.oa = ga * A.out_gs + ja * A.out_ls;
+    L.ib = gb * A.in_gs + jb * A.in_ls;
+    L.ob = gb * A.out_gs + jb * A.out_ls;
+    L.has_a = la < nl;
+    L.has_b = lb < nl;
+  }
+  return L;
+}
+
+template <class T, bool YMODE>
+__device__ __forceinline__ Cx<T> r2_load(const T* __restrict__ p, const R2Loc<T>& L, long long es, int i) {
+  Cx<T> v;
+  if (YMODE) {
+    if (L.has_b) return *reinterpret_cast<const Cx<T>*>(p + L.ia + (long long)i * es);
+    v.x = L.has_a ? p[L.ia + (long long)i * es] : T(0);
+    v.y = T(0);
+  } else {
+    v.x = L.has_a ? p[L.ia + i] : T(0);
+    v.y = L.has_b ? p[L.ib + i] : T(0);
+  }
+  return v;
+}
+template <class T, bool YMODE>
+__device__ __forceinline__ void r2_store(T* __restrict__ p, const R2Loc<T>& L, long long es, int i, T a, T b) {
+  if (YMODE) {
+    if (L.has_b) { *reinterpret_cast<Cx<T>*>(p + L.oa + (long long)i * es) = Cx<T>{a, b}; return; }
+    if (L.has_a) p[L.oa + (long long)i * es] = a;
+  } else {
+    if (L.has_a) p[L.oa + i] = a;
+    if (L.has_b) p[L.ob + i] = b;
+  }
+}
+
+// Makhoul permutation: position j of v holds input sample vperm(j)
+__device__ __forceinline__ int r2_vperm(bool trig, int n, int j) {
+  if (!trig) return j;
+  const int h = (n + 1) >> 1;
+  return j < h ? 2 * j : 2 * (n - 1 - j) + 1;
+}
+
+// one DIF stage on the shared tile (S > 0) or on registers already loaded (S == 0)
+template <class T, class Cfg, bool YMODE, int S>
+__device__ __forceinline__ void r2_dif_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T>& A, int c, int t) {
+  using Lay = R2Lay<T, Cfg, YMODE>;
+  constexpr int Rs = Cfg::R(S), Ns = Cfg::Ns(S), L = Ns / Rs, NB = Cfg::E / Rs, TPL = Cfg::TPL;
+#pragma unroll
+  for (int m = 0; m < NB; ++m) {
+    const int u = t + TPL * m;
+    const int blk = u / L, o = u - blk * L;
+    const int base = blk * Ns + o;
+    Cx<T>* a = (S == 0) ? v + m * Rs : v;
+    if (S > 0) {
+#pragma unroll
+      for (int q = 0; q < Rs; ++q) a[q] = sm[Lay::at(c, base + q * L)];
+    }
+    bfR<T, Rs>(a);
+    if (L > 1) {
+#pragma unroll
+      for (int r = 1; r < Rs; ++r) a[r] = cx_mul(a[r], cx_ldg(A.tw[S] + (r - 1) * L + o));
+    }
+#pragma unroll
+    for (int r = 0; r < Rs; ++r) sm[Lay::at(c, base + r * L)] = a[r];
+  }
+}
+
+// one DIT stage: twiddle before the butterfly; S == 0 leaves the results in v[]
+template <class T, class Cfg, bool YMODE, int S>
+__device__ __forceinline__ void r2_dit_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T>& A, int c, int t) {
+  using Lay = R2Lay<T, Cfg, YMODE>;
+  constexpr int Rs = Cfg::R(S), Ns = Cfg::Ns(S), L = Ns / Rs, NB = Cfg::E / Rs, TPL = Cfg::TPL;
+#pragma unroll
+  for (int m = 0; m < NB; ++m) {
+    const int u = t + TPL * m;
+    const int blk = u / L, o = u - blk * L;
+    const int base = blk * Ns + o;
+    Cx<T>* a = (S == 0) ? v + m * Rs : v;
+#pragma unroll
+    for (int q = 0; q < Rs; ++q) a[q] = sm[Lay::at(c, base + q * L)];
+    if (L > 1) {
+#pragma unroll
+      for (int q = 1; q < Rs; ++q) a[q] = cx_mul(a[q], cx_ldg(A.tw[S] + (q - 1) * L + o));
+    }
+    bfR<T, Rs>(a);
+    if (S > 0) {
+#pragma unroll
+      for (int r = 0; r < Rs; ++r) sm[Lay::at(c, base + r * L)] = a[r];
+    }
+  }
+}
+
+// ---- forward kinds: R2HC, REDFT10, RODFT10 ---------------------------------------------------------
+template <class T, class Cfg, bool YMODE>
+__global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(const R2Args<T> A) {
+  using C = Cx<T>;
+  using Lay = R2Lay<T, Cfg, YMODE>;
+  extern __shared__ __align__(16) unsigned char cb_smem_raw[];
+  C* sm = reinterpret_cast<C*>(cb_smem_raw);
+  constexpr int N = Cfg::N, TPL = Cfg::TPL, E = Cfg::E, G = Cfg::G, NS = Cfg::NS;
+  const int tid = threadIdx.x;
+  const int c = YMODE ? tid % G : tid / TPL;
+  const int t = YMODE ? tid / G : tid % TPL;
+  const R2Loc<T> loc = r2_locate<T, Cfg, YMODE>(A, c);
+  const int kind = A.kind;
+  const bool trig = kind != K_R2HC;
+  const bool neg_odd = kind == K_RODFT10;
+
+  C v[E];
+  {
+    constexpr int R0 = Cfg::R(0), L0 = N / R0;
+#pragma unroll
+    for (int m = 0; m < E / R0; ++m)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int j = q * L0 + t + TPL * m;
+        const int i = r2_vperm(trig, N, j);
+        C x = r2_load<T, YMODE>(A.in, loc, A.in_es, i);
+        if (neg_odd && (i & 1)) x = {-x.x, -x.y};
+        v[m * R0 + q] = x;
+      }
+  }
+  // copy the untransformed tail when the result goes to another array
+  if (A.line_len > N && A.in != A.out) {
+    for (int i = N + t; i < A.line_len; i += TPL) {
+      const C x = r2_load<T, YMODE>(A.in, loc, A.in_es, i);
+      r2_store<T, YMODE>(A.out, loc, A.out_es, i, x.x, x.y);
+    }
+  }
+  r2_dif_stage<T, Cfg, YMODE, 0>(v, sm, A, c, t);
+  r2_group_sync<Cfg, YMODE>(c);
+  if (NS > 1) { r2_dif_stage<T, Cfg, YMODE, (NS > 1 ? 1 : 0)>(v, sm, A, c, t); r2_group_sync<Cfg, YMODE>(c); }
+  if (NS > 2) { r2_dif_stage<T, Cfg, YMODE, (NS > 2 ? 2 : 0)>(v, sm, A, c, t); r2_group_sync<Cfg, YMODE>(c); }
+  if (NS > 3) { r2_dif_stage<T, Cfg, YMODE, (NS > 3 ? 3 : 0)>(v, sm, A, c, t); r2_group_sync<Cfg, YMODE>(c); }
+
+  // separation pass over pairs (k, N - k): k = t + m TPL covers 0 .. N/2 - 1, thread 0 adds k = N/2
+  const bool rev_out = kind == K_RODFT10;
+  auto separate = [&](int k) {
+    const int km = k ? N - k : 0;
+    const C zk = sm[Lay::at(c, Cfg::rev(k))];
+    const C zm = sm[Lay::at(c, Cfg::rev(km))];
+    const T sx = zk.x + zm.x, dx = zk.x - zm.x, sy = zk.y + zm.y, dy = zk.y - zm.y;
+    if (!trig) {
+      // A_k = (sx, dy) / 2, B_k = (sy, -dx) / 2 ; halfcomplex: re at k, im at N - k
+      r2_store<T, YMODE>(A.out, loc, A.out_es, k, T(0.5) * sx, T(0.5) * sy);
+      if (k > 0 && 2 * k != N) r2_store<T, YMODE>(A.out, loc, A.out_es, N - k, T(0.5) * dy, T(-0.5) * dx);
+    } else {
+      const C cs = cx_ldg(A.mak + k);
+      const T xa = cs.x * sx + cs.y * dy, xb = cs.x * sy - cs.y * dx;
+      r2_store<T, YMODE>(A.out, loc, A.out_es, rev_out ? N - 1 - k : k, xa, xb);
+      if (k > 0) {
+        const T ya = cs.y * sx - cs.x * dy, yb = cs.y * sy + cs.x * dx;
+        r2_store<T, YMODE>(A.out, loc, A.out_es, rev_out ? k - 1 : N - k, ya, yb);
+      }
+    }
+  };
+  static_assert(N % 2 == 0 && (N / 2) % TPL == 0, "pair pass needs TPL | N/2");
+#pragma unroll
+  for (int m = 0; m < (N / 2) / TPL; ++m) separate(t + m * TPL);
+  if (t == 0) separate(N / 2);
+}
+
+// ---- backward kinds: HC2R, REDFT01, RODFT01 --------------------------------------------------------
+template <class T, class Cfg, bool YMODE>
+__global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(const R2Args<T> A) {
+  using C = Cx<T>;
+  using Lay = R2Lay<T, Cfg, YMODE>;
+  extern __shared__ __align__(16) unsigned char cb_smem_raw[];
+  C* sm = reinterpret_cast<C*>(cb_smem_raw);
+  constexpr int N = Cfg::N, TPL = Cfg::TPL, E = Cfg::E, G = Cfg::G, NS = Cfg::NS;
+  const int tid = threadIdx.x;
+  const int c = YMODE ? tid % G : tid / TPL;
+  const int t = YMODE ? tid / G : tid % TPL;
+  const R2Loc<T> loc = r2_locate<T, Cfg, YMODE>(A, c);
+  const int kind = A.kind;
+  const bool trig = kind != K_HC2R;
+  const bool rv = kind == K_RODFT01;
+
+  // pre-pass: Z_k = W^a_k + i W^b_k and Z_{N-k} = conj W^a_k + i conj W^b_k, stored re/im swapped.
+  // Two steps so that all global loads of a thread are in flight together.
+  static_assert(N % 2 == 0 && (N / 2) % TPL == 0, "pair pass needs TPL | N/2");
+  constexpr int NK = (N / 2) / TPL;
+  auto fetch = [&](int k, C& xk, C& xm) {
+    const int km = N - k;
+    xm = C{T(0), T(0)};
+    if (!trig) {
+      xk = r2_load<T, YMODE>(A.in, loc, A.in_es, k);
+      if (k > 0 && 2 * k != N) xm = r2_load<T, YMODE>(A.in, loc, A.in_es, km);
+    } else {
+      xk = r2_load<T, YMODE>(A.in, loc, A.in_es, rv ? N - 1 - k : k);
+      if (k > 0) xm = r2_load<T, YMODE>(A.in, loc, A.in_es, rv ? k - 1 : km);  // X_N := 0
+    }
+  };
+  auto scatter = [&](int k, const C& xk, const C& xm) {
+    const int km = N - k;
+    C wa, wb;  // spectra of the two real sequences at k
+    if (!trig) {
+      wa = C{xk.x, xm.x};
+      wb = C{xk.y, xm.y};
+    } else {
+      const C cs = cx_ldg(A.mak + k);
+      wa = C{cs.x * xk.x + cs.y * xm.x, cs.y * xk.x - cs.x * xm.x};
+      wb = C{cs.x * xk.y + cs.y * xm.y, cs.y * xk.y - cs.x * xm.y};
+    }
+    // Z_k = (wa.x - wb.y, wa.y + wb.x); swapped store
+    sm[Lay::at(c, Cfg::rev(k))] = C{wa.y + wb.x, wa.x - wb.y};
+    if (k > 0 && km != k) sm[Lay::at(c, Cfg::rev(km))] = C{wb.x - wa.y, wa.x + wb.y};
+  };
+  {
+    C xk[NK], xm[NK];
+#pragma unroll
+    for (int m = 0; m < NK; ++m) fetch(t + m * TPL, xk[m], xm[m]);
+#pragma unroll
+    for (int m = 0; m < NK; ++m) scatter(t + m * TPL, xk[m], xm[m]);
+    if (t == 0) {
+      C a0, a1;
+      fetch(N / 2, a0, a1);
+      scatter(N / 2, a0, a1);
+    }
+  }
+  if (A.line_len > N && A.in != A.out) {
+    for (int i = N + t; i < A.line_len; i += TPL) {
+      const C x = r2_load<T, YMODE>(A.in, loc, A.in_es, i);
+      r2_store<T, YMODE>(A.out, loc, A.out_es, i, x.x, x.y);
+    }
+  }
+  r2_group_sync<Cfg, YMODE>(c);
+  C v[E];
+  if (NS > 3) { r2_dit_stage<T, Cfg, YMODE, (NS > 3 ? 3 : 0)>(v, sm, A, c, t); r2_group_sync<Cfg, YMODE>(c); }
+  if (NS > 2) { r2_dit_stage<T, Cfg, YMODE, (NS > 2 ? 2 : 0)>(v, sm, A, c, t); r2_group_sync<Cfg, YMODE>(c); }
+  if (NS > 1) { r2_dit_stage<T, Cfg, YMODE, (NS > 1 ? 1 : 0)>(v, sm, A, c, t); r2_group_sync<Cfg, YMODE>(c); }
+  r2_dit_stage<T, Cfg, YMODE, 0>(v, sm, A, c, t);
+  // natural-order samples (swapped back: a = im, b = re) straight to global memory
+  {
+    constexpr int R0 = Cfg::R(0), L0 = N / R0;
+#pragma unroll
+    for (int m = 0; m < E / R0; ++m)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int j = q * L0 + t + TPL * m;
+        const int i = r2_vperm(trig, N, j);
+        C x = v[m * R0 + q];
+        if (rv && (i & 1)) x = {-x.x, -x.y};
+        r2_store<T, YMODE>(A.out, loc, A.out_es, i, x.y, x.x);
+      }
+  }
+}
+
+}  // namespace cb

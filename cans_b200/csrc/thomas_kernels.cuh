@@ -223,150 +223,172 @@ __global__ void __launch_bounds__(128) thomas_seq_kernel(const ThomasDev<T> D, c
   for (int k = 0; k < nn; ++k) pc[(long long)k * D.sk] = add_rn(pc[(long long)k * D.sk], mul_rn(p2[zidx(D, i, j, k)], pcl));
 }
 
-// ---- warp-per-column chunked substitution ------------------------------------
-// shared tile: column c occupies KP elements; row k = l*m + r sits at l*CS + r,
-// CS = m | 1 (odd -> the 32 lanes of a column hit distinct banks), KP = 2 mod 16
-// (-> the cooperative 8-wide row copies are conflict free as well).
-__host__ __device__ inline int thomas_cs(int m) { return m | 1; }
-__host__ __device__ inline int thomas_kp(int m) {
-  int kp = 32 * thomas_cs(m) + 1;  // +1: room for the periodic closure row (k = nn <= 32 m)
-  while ((kp & 15) != 2) ++kp;
-  return kp;
+// ---- register-resident chunked substitution -----------------------------------
+// CTA = 16 consecutive columns (one 128-byte row segment of the z pencil) x 32
+// chunks of m consecutive rows.  Thread (c, g) owns rows g*m .. g*m+m-1 of
+// column c: its m right-hand-side values are loaded straight into registers
+// (the 16 lanes of a half warp read one full 128-byte line), its m pivots are
+// fetched with cp.async into a private shared-memory strip (so that registers
+// stay below 64 and two CTAs share an SM: one computes while the other's loads
+// are in flight).  Both first-order recurrences are evaluated chunk-parallel:
+// local sweep -> (value, product) of every chunk to shared memory -> each thread
+// folds the chunks before (after) its own -> fix-up.  Nothing but the final
+// result is written; traffic = read p + read z + write p = 24 B/point.
+#define CB_TH_COLS 16
+#define CB_TH_CHUNKS 32
+
+__device__ __forceinline__ void cp_async_elem(double* dst_smem, const double* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(float* dst_smem, const float* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <class T, int MMAX> constexpr size_t thomas_reg_smem() {
+  return ((size_t)MMAX * CB_TH_COLS * CB_TH_CHUNKS + 2 * CB_TH_CHUNKS * (MMAX + 1) + 2 * CB_TH_COLS * CB_TH_CHUNKS) * sizeof(T);
 }
 
-template <class T, int MMAX, int CX>
-__global__ void __launch_bounds__(32 * CX, (MMAX <= 16 ? 2 : 1))
-thomas_warp_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, const T* p2base, const T* denbase,
-                   long long slot_z, long long slot_den, T* p, T norm) {
+template <class T, int MMAX>
+__global__ void __launch_bounds__(CB_TH_COLS* CB_TH_CHUNKS, (MMAX <= 16 ? 2 : 1))
+thomas_reg_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, const T* p2base, const T* denbase,
+                  long long slot_z, long long slot_den, T* p, T norm) {
+  constexpr int NT = CB_TH_COLS * CB_TH_CHUNKS;
   extern __shared__ __align__(16) unsigned char cb_smem_raw[];
-  T* s = reinterpret_cast<T*>(cb_smem_raw);
-  const int m = D.m, nn = D.nn, n = D.n;
-  const int CS = thomas_cs(m), KP = thomas_kp(m);
-  T* sa = s + CX * KP;       // -a_k in [r][lane] order
-  T* sc = sa + 32 * MMAX;    //  c_k in [r][lane] order
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int tiles_x = (D.nx + CX - 1) / CX;
-  const int j = blockIdx.x / tiles_x;
-  const int i0 = (blockIdx.x - j * tiles_x) * CX;
+  T* zs = reinterpret_cast<T*>(cb_smem_raw);   // [r][tid]
+  T* sa = zs + (size_t)MMAX * NT;              // a_k at [g][r], chunk stride m|1: the two chunks of a warp hit different banks
+  T* sc = sa + CB_TH_CHUNKS * (MMAX + 1);      // c_k
+  T* sY = sc + CB_TH_CHUNKS * (MMAX + 1);      // [g][c] chunk value
+  T* sP = sY + NT;                             // [g][c] chunk product
+  const int tid = threadIdx.x, c = tid & (CB_TH_COLS - 1), g = tid / CB_TH_COLS;
+  const int m = D.m, nn = D.nn;
+  const long long ncol = (long long)D.nx * D.ny;
+  const long long col = (long long)blockIdx.x * CB_TH_COLS + c;
+  const bool live = col < ncol;
   const int sel = st->sel;
-  const bool live = (i0 + w) < D.nx;
-  const long long col = (long long)j * D.nx + i0 + w;
+  const int k0 = g * m;
+  const int cs0 = g * (m | 1);
 
-  // pivots of my chunk straight into registers (coalesced: lane fastest)
-  T z[MMAX];
+  // pivots: asynchronous copies into my strip
   {
-    const T* zc = zbase + (long long)sel * slot_z + col * m * 32 + lane;
-#pragma unroll
-    for (int r = 0; r < MMAX; ++r) z[r] = (live && r < m) ? zc[(long long)r * 32] : T(0);
-  }
-  for (int e = tid; e < 32 * m; e += 32 * CX) {
-    const int r = e >> 5, l = e & 31, k = l * m + r;
-    sa[e] = (k < nn) ? -D.a[k] : T(0);
-    sc[e] = (k < nn) ? D.c[k] : T(0);
-  }
-  // cooperative tile load, rows 0..n-1
-  T* pg = p + (long long)j * D.sj + i0;
-  for (int e = tid; e < n * CX; e += 32 * CX) {
-    const int k = e / CX, c = e - k * CX;
-    const int l = k / m, r = k - l * m;
-    if (i0 + c < D.nx) s[c * KP + l * CS + r] = pg[(long long)k * D.sk + c];
-  }
-  __syncthreads();
-
-  T y[MMAX];
-  if (live) {
-    T* sp = s + w * KP + lane * CS;
-    // pass A: local forward sweep  y_k = beta_k + alpha_k y_{k-1}
-    T yy = T(0), pi = T(1);
+    const T* zc = zbase + (long long)sel * slot_z + col;
 #pragma unroll
     for (int r = 0; r < MMAX; ++r) {
+      const int k = k0 + r;
       if (r < m) {
-        const T zz = z[r];
-        const T al = sa[r * 32 + lane] * zz;
-        const T be = sp[r] * norm * zz;
-        yy = fma(al, yy, be);
-        pi *= al;
+        if (live && k < nn) cp_async_elem(zs + r * NT + tid, zc + (long long)k * ncol);
+        else zs[r * NT + tid] = T(0);
       }
+    }
+  }
+  // right-hand side into registers
+  T y[MMAX];
+  {
+    const T* pc = p + col;
+#pragma unroll
+    for (int r = 0; r < MMAX; ++r) {
+      const int k = k0 + r;
+      y[r] = (r < m && live && k < nn) ? pc[(long long)k * D.sk] : T(0);
+    }
+  }
+  for (int e = tid; e < CB_TH_CHUNKS * m; e += NT) {
+    const int ge = e / m, re = e - ge * m;
+    sa[ge * (m | 1) + re] = (e < nn) ? D.a[e] : T(0);
+    sc[ge * (m | 1) + re] = (e < nn) ? D.c[e] : T(0);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // forward: y_k = (p_k norm - a_k y_{k-1}) z_k, chunk-local with y_{k0-1} := 0
+  T yy = T(0), pi = T(1);
+#pragma unroll
+  for (int r = 0; r < MMAX; ++r) {
+    if (r < m) {
+      const T zz = zs[r * NT + tid];
+      const T al = -(sa[cs0 + r] * zz);
+      yy = fma(al, yy, y[r] * norm * zz);
+      pi *= al;
       y[r] = yy;
     }
-    // inclusive scan of the affine maps v -> Y + Pi v over the lanes
-    T Y = yy, Pi = pi;
+  }
+  sY[tid] = yy;
+  sP[tid] = pi;
+  __syncthreads();
+  T vin = T(0);
+  for (int gg = 0; gg < g; ++gg) vin = fma(sP[gg * CB_TH_COLS + c], vin, sY[gg * CB_TH_COLS + c]);
+  pi = T(1);
 #pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const T Yp = __shfl_up_sync(0xffffffffu, Y, dlt);
-      const T Pp = __shfl_up_sync(0xffffffffu, Pi, dlt);
-      if (lane >= dlt) { Y = fma(Pi, Yp, Y); Pi *= Pp; }
+  for (int r = 0; r < MMAX; ++r) {
+    if (r < m) {
+      pi *= -(sa[cs0 + r] * zs[r * NT + tid]);
+      y[r] = fma(pi, vin, y[r]);
     }
-    T Yin = __shfl_up_sync(0xffffffffu, Y, 1);
-    if (lane == 0) Yin = T(0);
-    // pass B: fix-up with the incoming value
-    pi = T(1);
-#pragma unroll
-    for (int r = 0; r < MMAX; ++r) {
-      if (r < m) {
-        pi *= sa[r * 32 + lane] * z[r];
-        y[r] = fma(pi, Yin, y[r]);
-      }
-    }
-    // pass C: local backward sweep  x_k = y_k - d_k x_{k+1}
-    T xx = T(0), rho = T(1);
-#pragma unroll
-    for (int r = MMAX - 1; r >= 0; --r) {
-      if (r < m) {
-        const T nd = -(sc[r * 32 + lane] * z[r]);
-        xx = fma(nd, xx, y[r]);
-        rho *= nd;
-        y[r] = xx;
-      }
-    }
-    T X = xx, R = rho;
-#pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const T Xp = __shfl_down_sync(0xffffffffu, X, dlt);
-      const T Rp = __shfl_down_sync(0xffffffffu, R, dlt);
-      if (lane + dlt < 32) { X = fma(R, Xp, X); R *= Rp; }
-    }
-    T Xin = __shfl_down_sync(0xffffffffu, X, 1);
-    if (lane == 31) Xin = T(0);
-    // pass D: fix-up
-    rho = T(1);
-#pragma unroll
-    for (int r = MMAX - 1; r >= 0; --r) {
-      if (r < m) {
-        rho *= -(sc[r * 32 + lane] * z[r]);
-        y[r] = fma(rho, Xin, y[r]);
-      }
-    }
-    if (D.periodic) {
-      // closure value and Sherman-Morrison correction, src/solver.f90:272-306
-      const int ls = (nn - 1) / m, rs = (nn - 1) - ls * m;
-      T v = T(0);
-#pragma unroll
-      for (int r = 0; r < MMAX; ++r) if (r == rs) v = y[r];
-      const T x_last = __shfl_sync(0xffffffffu, v, ls);
-      const T x_first = __shfl_sync(0xffffffffu, y[0], 0);
-      const T den = denbase[(long long)sel * slot_den + col];
-      const int lq = nn / m, rq = nn - lq * m;
-      const T pnn = s[w * KP + lq * CS + rq];
-      const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], x_first)), mul_rn(D.a[nn], x_last));
-      const T pcl = (den == T(0)) ? T(0) : div_rn(num, den);
-      const T* p2c = p2base + (long long)sel * slot_z + col * m * 32 + lane;
-#pragma unroll
-      for (int r = 0; r < MMAX; ++r)
-        if (r < m) y[r] = fma(p2c[(long long)r * 32], pcl, y[r]);
-      __syncwarp();
-      if (lane == 0) s[w * KP + lq * CS + rq] = pcl;
-      __syncwarp();
-    }
-#pragma unroll
-    for (int r = 0; r < MMAX; ++r)
-      if (r < m && lane * m + r < nn) sp[r] = y[r];
   }
   __syncthreads();
-  for (int e = tid; e < n * CX; e += 32 * CX) {
-    const int k = e / CX, c = e - k * CX;
-    const int l = k / m, r = k - l * m;
-    if (i0 + c < D.nx) pg[(long long)k * D.sk + c] = s[c * KP + l * CS + r];
+  // backward: x_k = y_k - d_k x_{k+1}, d_k = c_k z_k
+  T xx = T(0), rho = T(1);
+#pragma unroll
+  for (int r = MMAX - 1; r >= 0; --r) {
+    if (r < m) {
+      const T nd = -(sc[cs0 + r] * zs[r * NT + tid]);
+      xx = fma(nd, xx, y[r]);
+      rho *= nd;
+      y[r] = xx;
+    }
+  }
+  sY[tid] = xx;
+  sP[tid] = rho;
+  __syncthreads();
+  vin = T(0);
+  for (int gg = CB_TH_CHUNKS - 1; gg > g; --gg) vin = fma(sP[gg * CB_TH_COLS + c], vin, sY[gg * CB_TH_COLS + c]);
+  rho = T(1);
+#pragma unroll
+  for (int r = MMAX - 1; r >= 0; --r) {
+    if (r < m) {
+      rho *= -(sc[cs0 + r] * zs[r * NT + tid]);
+      y[r] = fma(rho, vin, y[r]);
+    }
+  }
+  if (D.periodic) {
+    // closure value and rank-one correction, src/solver.f90:272-306
+    __syncthreads();
+    const int kl = nn - 1;
+    if (g == 0) sY[c] = y[0];                  // x_1
+    if (kl >= k0 && kl < k0 + m) {
+#pragma unroll
+      for (int r = 0; r < MMAX; ++r)
+        if (k0 + r == kl) sY[CB_TH_COLS + c] = y[r];   // x_nn
+    }
+    __syncthreads();
+    if (g == 0) {
+      T pcl = T(0);
+      if (live) {
+        const T den = denbase[(long long)sel * slot_den + col];
+        const T pnn = p[(long long)nn * D.sk + col];
+        const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[CB_TH_COLS + c]));
+        pcl = (den == T(0)) ? T(0) : div_rn(num, den);
+        p[(long long)nn * D.sk + col] = pcl;
+      }
+      sP[c] = pcl;
+    }
+    __syncthreads();
+    const T pcl = sP[c];
+    const T* p2c = p2base + (long long)sel * slot_z + col;
+#pragma unroll
+    for (int r = 0; r < MMAX; ++r) {
+      const int k = k0 + r;
+      if (r < m && live && k < nn) y[r] = fma(p2c[(long long)k * ncol], pcl, y[r]);
+    }
+  }
+  {
+    T* pc = p + col;
+#pragma unroll
+    for (int r = 0; r < MMAX; ++r) {
+      const int k = k0 + r;
+      if (r < m && live && k < nn) pc[(long long)k * D.sk] = y[r];
+    }
   }
 }
 

@@ -79,6 +79,15 @@ class Context:
     def handle(self):
         return self._h
 
+    def force_generic_engine(self, on: bool = True):
+        """Route every transform through the generic shared-memory engine (tests)."""
+        check(lib.cansb200_ctx_set(self._h, 0, int(on)), "ctx_set")
+
+    def set_variant(self, x: int = 0, y: int = 0):
+        """Tuning variants of the fast transforms (thread / radix split), see r2r2_inst.cuh."""
+        check(lib.cansb200_ctx_set(self._h, 1, int(x)), "ctx_set")
+        check(lib.cansb200_ctx_set(self._h, 2, int(y)), "ctx_set")
+
     def set_profiling(self, on: bool):
         check(lib.cansb200_set_profiling(self._h, int(on)), "set_profiling")
 

@@ -114,6 +114,15 @@ int cansb200_plan_stats(cansb200_plan* plan, unsigned long long stats[4]);
  * [3] tridiagonal substitution, [4] fft y bwd, [5] fft x bwd.  ms[] are sums over nsolves. */
 int cansb200_set_profiling(cansb200_ctx* ctx, int on);
 int cansb200_get_profile(cansb200_ctx* ctx, double ms[8], unsigned long long* nsolves);
+/* context switches: what = CANSB200_CTX_FORCE_GENERIC (value 0/1) routes every transform through the
+ * generic shared-memory engine instead of the two-for-one register kernels (both are CUDA paths; tests
+ * use it to cover the generic engine on lengths the fast path also serves). */
+enum {
+  CANSB200_CTX_FORCE_GENERIC = 0,
+  CANSB200_CTX_X_VARIANT = 1,   /* tuning variant (thread / radix split) of the contiguous transforms, 0 = default */
+  CANSB200_CTX_Y_VARIANT = 2    /* same for the strided transforms */
+};
+int cansb200_ctx_set(cansb200_ctx* ctx, int what, int value);
 /* workspace the OpenACC host may alias as `work` / `solver_buf_0` (src/rk.f90:26-30) */
 int cansb200_get_work(cansb200_ctx* ctx, int which, void** ptr, size_t* nelem);
 
