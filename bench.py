@@ -178,6 +178,10 @@ def main():
     ap.add_argument("--thomas", type=int, default=-1)
     ap.add_argument("--fft-x-lines", type=int, default=-1)
     ap.add_argument("--fft-y-lines", type=int, default=-1)
+    ap.add_argument("--x-variant", type=int, default=0)
+    ap.add_argument("--y-variant", type=int, default=0)
+    ap.add_argument("--chain-cols", type=int, default=0)
+    ap.add_argument("--chain-streams", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -209,6 +213,8 @@ def main():
     dzc, dzf = gridgen.initgrid(1, ng[2], gr, l[2], per_z)
     dli = [ng[0] / l[0], ng[1] / l[1], ng[2] / l[2]]
     ctx = cb.Context(ng)
+    ctx.set_variant(args.x_variant, args.y_variant)
+    ctx.set_chain(args.chain_cols, args.chain_streams)
     sd = cb.initsolver(ctx, ng, dli, 1.0 / dzc, 1.0 / dzf, cbc, [[0.0, 0.0]] * 3, cf, device=dev,
                        thomas_variant=args.thomas, fft_x_lines=args.fft_x_lines, fft_y_lines=args.fft_y_lines)
     shp = (ng[2] + 2, ng[1] + 2, ng[0] + 2)

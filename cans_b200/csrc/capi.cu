@@ -82,6 +82,7 @@ struct cansb200_ctx {
   int ng[3], dims[2], ipencil_axis, rank, nranks, is_fp32;
   int n[3], lo[3], n_z[3], lo_z[3];
   size_t esz;
+  int num_sms = 148;
   DevBuf scratch;   // haloless field buffer A (x pencil)
   DevBuf staging;   // haloed p when the caller's p is host memory
   DevBuf coef;      // a, b, c, lambdaxy staged from the host
@@ -93,6 +94,13 @@ struct cansb200_ctx {
   std::map<int, R2Tables<float>> r2tabs32;
   int force_generic = 0;                       // tests: route every transform through the generic engine
   int r2_variant[2] = {0, 0};                  // tuning variant of the fast path, [x, y]
+  // L2-resident chain: fft-y -> tridiagonal -> ifft-y run per window of `chain_cols` x columns, windows
+  // round-robin on auxiliary streams, so that the two intermediate fields never leave the L2 cache
+  int chain_cols = 0;                          // 0 = off (three full-field passes)
+  int chain_nstreams = 2;
+  std::vector<cudaStream_t> aux;
+  std::vector<cudaEvent_t> aux_done;
+  cudaEvent_t fork_ev = nullptr;
   unsigned long long launches = 0;
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
   bool profiling = false;
@@ -334,24 +342,71 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   ThomasDev<T> D;
   D.nx = nx; D.ny = ny; D.n = n_rows; D.periodic = periodic; D.nn = periodic ? n_rows - 1 : n_rows;
   D.sj = sj; D.sk = sk; D.a = a; D.b = b; D.c = c; D.lam = lam; D.lam_sj = nx;
-  D.m = pl->th_m; D.chunk_layout = 0;
+  D.m = pl->th_m; D.chunk_layout = 0; D.xb = 0; D.xn = nx;
   return D;
 }
 
-template <class T, int MMAX>
-static int launch_reg(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, cudaStream_t st) {
-  auto kfn = thomas_reg_kernel<T, MMAX>;
-  const size_t smem = thomas_reg_smem<T, MMAX>();
+template <class T, int MMAX, bool EXACT, bool VEC>
+static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, cudaStream_t st) {
+  auto kfn = thomas_pipe_kernel<T, MMAX, EXACT, VEC>;
+  const size_t smem = thomas_pipe_smem<T, MMAX>();
   static bool attr = false;
   if (!attr) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
+  const long long tiles = (long long)((D.xn + CB_TH_COLS - 1) / CB_TH_COLS) * D.ny;
+  const unsigned grid = (unsigned)(tiles < ctx->num_sms ? tiles : ctx->num_sms);   // persistent: one CTA per SM
+  kfn<<<grid, CB_TH_THREADS, smem, st>>>(D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
+                                         (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// pivot cache: content hash of (a, b, c, lambda) -> slot select -> factorisation on a miss
+template <class T> static int gaussel_prepare(cansb200_plan* pl, const ThomasDev<T>& D, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  CacheState* cs = (CacheState*)pl->state.p;
   const long long ncol = (long long)D.nx * D.ny;
-  const long long tiles = (ncol + CB_TH_COLS - 1) / CB_TH_COLS;
-  kfn<<<(unsigned)tiles, CB_TH_COLS * CB_TH_CHUNKS, smem, st>>>(D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p,
-                                                              (const T*)pl->p2cache.p, (const T*)pl->dencache.p, pl->slot_z,
-                                                              pl->slot_den, p, norm);
+  const long long total = 3LL * D.n + ncol;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 592) blocks = 592;
+  thomas_hash_kernel<T><<<blocks, 256, 0, st>>>(D, cs);
+  thomas_select_kernel<<<1, 32, 0, st>>>(cs);
+  thomas_factor_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(D, cs, (T*)pl->zcache.p, (T*)pl->p2cache.p,
+                                                                        (T*)pl->dencache.p, pl->slot_z, pl->slot_den);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// substitution on the column window D.xb .. D.xb + D.xn - 1
+template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T>& D, T* p, T norm, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  CacheState* cs = (CacheState*)pl->state.p;
+  if (pl->th_variant == 1) {
+    // 16-byte tile copies need every row segment aligned: even (FP64) / multiple-of-4 (FP32) column counts and offsets
+    const long long vw = 16 / (long long)sizeof(T);
+    const bool vec = (D.nx % vw) == 0 && (D.xb % vw) == 0 && (D.sk % vw) == 0 && ((uintptr_t)p % 16) == 0 &&
+                     ((uintptr_t)pl->zcache.p % 16) == 0 && (pl->slot_z % vw) == 0 && (D.xn % vw) == 0;
+    const bool exact = D.m == pl->th_mmax;
+    if (pl->th_mmax == 4) {
+      if (exact && vec) return launch_pipe<T, 4, true, true>(ctx, D, pl, p, norm, st);
+      if (vec) return launch_pipe<T, 4, false, true>(ctx, D, pl, p, norm, st);
+      return launch_pipe<T, 4, false, false>(ctx, D, pl, p, norm, st);
+    }
+    if (pl->th_mmax == 8) {
+      if (exact && vec) return launch_pipe<T, 8, true, true>(ctx, D, pl, p, norm, st);
+      if (vec) return launch_pipe<T, 8, false, true>(ctx, D, pl, p, norm, st);
+      return launch_pipe<T, 8, false, false>(ctx, D, pl, p, norm, st);
+    }
+    return fail(CANSB200_EUNSUPPORTED, "gaussel: no pipelined kernel for this chunk length");
+  }
+  if (D.xb != 0 || D.xn != D.nx) return fail(CANSB200_EUNSUPPORTED, "gaussel: the sequential variant has no column windows");
+  const long long ncol = (long long)D.nx * D.ny;
+  thomas_seq_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(D, cs, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
+                                                                     (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -360,38 +415,14 @@ static int launch_reg(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_p
 template <class T>
 static int run_gaussel(cansb200_plan* pl, T* p, int nx, int ny, long long sj, long long sk, int n_rows, int periodic, T norm,
                        const T* lam, const T* a, const T* b, const T* c, cudaStream_t st) {
-  cansb200_ctx* ctx = pl->ctx;
   if (n_rows != pl->th_n || periodic != pl->periodic_z)
     return fail(CANSB200_EINVAL, "gaussel: n_rows / periodicity differ from the plan's");
   if (pl->th_nn < 1) return fail(CANSB200_EINVAL, "gaussel: empty system");
   ThomasDev<T> D = make_thomas<T>(pl, nx, ny, sj, sk, n_rows, periodic, lam, a, b, c);
-  CacheState* cs = (CacheState*)pl->state.p;
-  const long long ncol = (long long)nx * ny;
-  {
-    const long long total = 3LL * D.n + ncol;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 592) blocks = 592;
-    thomas_hash_kernel<T><<<blocks, 256, 0, st>>>(D, cs);
-    thomas_select_kernel<<<1, 32, 0, st>>>(cs);
-    thomas_factor_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(D, cs, (T*)pl->zcache.p, (T*)pl->p2cache.p,
-                                                                          (T*)pl->dencache.p, pl->slot_z, pl->slot_den);
-    ctx->launches += 3;
-    CK(cudaGetLastError());
-  }
-  prof_mark(ctx, st);
-  if (pl->th_variant == 1) {
-    switch (pl->th_mmax) {
-      case 4: return launch_reg<T, 4>(ctx, D, pl, p, norm, st);
-      case 8: return launch_reg<T, 8>(ctx, D, pl, p, norm, st);
-      case 16: return launch_reg<T, 16>(ctx, D, pl, p, norm, st);
-      default: return launch_reg<T, 32>(ctx, D, pl, p, norm, st);
-    }
-  }
-  thomas_seq_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(D, cs, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
-                                                                     (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm);
-  ctx->launches++;
-  CK(cudaGetLastError());
-  return 0;
+  int rc = gaussel_prepare<T>(pl, D, st);
+  if (rc) return rc;
+  prof_mark(pl->ctx, st);
+  return gaussel_apply<T>(pl, D, p, norm, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -434,6 +465,11 @@ int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ip
   c->dims[0] = dims[0]; c->dims[1] = dims[1]; c->ipencil_axis = ipencil_axis; c->rank = rank; c->nranks = nranks;
   c->is_fp32 = is_fp32 ? 1 : 0;
   c->esz = is_fp32 ? 4 : 8;
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      c->num_sms = sms;
+  }
   const size_t nel = (size_t)c->n[0] * c->n[1] * c->n[2];
   if (c->scratch.ensure(nel * c->esz)) { delete c; return fail(CANSB200_ENOMEM, "init: scratch allocation failed"); }
   *out = c;
@@ -445,6 +481,9 @@ int cansb200_finalize(cansb200_ctx* c) {
   c->scratch.release(); c->staging.release(); c->coef.release();
   for (auto& kv : c->tabs64) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (auto& kv : c->tabs32) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
+  for (cudaStream_t q : c->aux) cudaStreamDestroy(q);
+  for (cudaEvent_t q : c->aux_done) cudaEventDestroy(q);
+  if (c->fork_ev) cudaEventDestroy(c->fork_ev);
   for (auto& kv : c->r2tabs64) { for (int q = 0; q < 4; ++q) cudaFree(kv.second.tw[q]); cudaFree(kv.second.mak); }
   for (auto& kv : c->r2tabs32) { for (int q = 0; q < 4; ++q) cudaFree(kv.second.tw[q]); cudaFree(kv.second.mak); }
   for (auto& kv : c->dtabs64) cudaFree(kv.second.cs);
@@ -467,6 +506,16 @@ int cansb200_get_extents(const cansb200_ctx* c, int n[3], int lo[3], int n_z[3],
 int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
   if (!c) return fail(CANSB200_EINVAL, "null ctx");
   if (what == CANSB200_CTX_FORCE_GENERIC) { c->force_generic = value ? 1 : 0; return 0; }
+  if (what == CANSB200_CTX_CHAIN_COLS) {
+    if (value < 0 || (value % 16) != 0) return fail(CANSB200_EINVAL, "ctx_set: chain_cols must be a non-negative multiple of 16");
+    c->chain_cols = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_CHAIN_STREAMS) {
+    if (value < 1 || value > 8) return fail(CANSB200_EINVAL, "ctx_set: chain_streams must be 1..8");
+    c->chain_nstreams = value;
+    return 0;
+  }
   if (what == CANSB200_CTX_X_VARIANT || what == CANSB200_CTX_Y_VARIANT) {
     if (value < 0 || value > 3) return fail(CANSB200_EINVAL, "ctx_set: variant must be 0..3");
     c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
@@ -518,11 +567,11 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   pl->th_n = ctx->ng[2] - pl->q;
   pl->th_nn = pl->periodic_z ? pl->th_n - 1 : pl->th_n;
   if (pl->th_nn < 1) return fail(CANSB200_EINVAL, "plan_create: z system is empty");
-  pl->th_m = (pl->th_nn + 31) / 32;
+  pl->th_m = (pl->th_nn + CB_TH_CHUNKS - 1) / CB_TH_CHUNKS;
   int variant = o.thomas_variant >= 0 ? o.thomas_variant : 1;
-  if (pl->th_m > 32) variant = 0;
+  if (pl->th_m > 8) variant = 0;   // nz > 512: the sequential kernel (a wider pipelined tile is future work)
   pl->th_variant = variant;
-  pl->th_mmax = pl->th_m <= 4 ? 4 : pl->th_m <= 8 ? 8 : pl->th_m <= 16 ? 16 : 32;
+  pl->th_mmax = pl->th_m <= 4 ? 4 : 8;
   pl->nslots = o.cache_slots >= 1 ? (o.cache_slots > CB_MAX_SLOTS ? CB_MAX_SLOTS : o.cache_slots) : 1;
   const long long ncol = (long long)ctx->n_z[0] * ctx->n_z[1];
   pl->slot_z = ncol * pl->th_nn;
@@ -626,19 +675,56 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
   if (rc) return rc;
   prof_mark(ctx, st);
-  // forward y, in place in A
   R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nz, ny, 1};
-  rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
-  if (rc) return rc;
-  prof_mark(ctx, st);
-  // tridiagonal solve in z
-  rc = run_gaussel<T>(pl, A, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, (T)normfft, lam, a, b, c, st);
-  if (rc) return rc;
-  prof_mark(ctx, st);
-  // backward y, backward x
-  rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
-  if (rc) return rc;
-  prof_mark(ctx, st);
+  const int W = ctx->chain_cols;
+  if (W > 0 && W < nx && pl->th_variant == 1 && !ctx->profiling) {
+    // ---- L2-resident chain over x windows, round-robin on auxiliary streams
+    ThomasDev<T> D = make_thomas<T>(pl, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, lam, a, b, c);
+    rc = gaussel_prepare<T>(pl, D, st);
+    if (rc) return rc;
+    const int ns = ctx->chain_nstreams;
+    while ((int)ctx->aux.size() < ns) {
+      cudaStream_t q; cudaEvent_t e;
+      CK(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->aux.push_back(q); ctx->aux_done.push_back(e);
+    }
+    if (!ctx->fork_ev) CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->fork_ev, st));
+    for (int q = 0; q < ns; ++q) CK(cudaStreamWaitEvent(ctx->aux[q], ctx->fork_ev, 0));
+    int iw = 0;
+    for (int x0 = 0; x0 < nx; x0 += W, ++iw) {
+      cudaStream_t sq = ctx->aux[iw % ns];
+      const int w = (nx - x0 < W) ? nx - x0 : W;
+      R2RGeom gw = gy;
+      gw.lines_per_group = w;
+      rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + x0, A + x0, gw, pl->opt.fft_y_lines, sq);
+      if (rc) return rc;
+      D.xb = x0; D.xn = w;
+      rc = gaussel_apply<T>(pl, D, A, (T)normfft, sq);
+      if (rc) return rc;
+      rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A + x0, A + x0, gw, pl->opt.fft_y_lines, sq);
+      if (rc) return rc;
+    }
+    for (int q = 0; q < ns; ++q) {
+      CK(cudaEventRecord(ctx->aux_done[q], ctx->aux[q]));
+      CK(cudaStreamWaitEvent(st, ctx->aux_done[q], 0));
+    }
+  } else {
+    // forward y, in place in A
+    rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
+    if (rc) return rc;
+    prof_mark(ctx, st);
+    // tridiagonal solve in z
+    rc = run_gaussel<T>(pl, A, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, (T)normfft, lam, a, b, c, st);
+    if (rc) return rc;
+    prof_mark(ctx, st);
+    // backward y
+    rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
+    if (rc) return rc;
+    prof_mark(ctx, st);
+  }
+  // backward x
   R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nz, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
   if (rc) return rc;

@@ -33,7 +33,8 @@ template <class T> struct ThomasDev {
   long long sj, sk;   // field strides: p[k*sk + j*sj + i]
   const T* a; const T* b; const T* c;  // device, length >= n
   const T* lam; long long lam_sj;      // lambdaxy[j*lam_sj + i]
-  int m;              // rows per lane in the chunk layout = ceil(nn/32)
+  int xb, xn;         // column window of this launch: i in [xb, xb + xn) for every j (thomas_reg_kernel)
+  int m;              // rows per chunk of the chunked substitution = ceil(nn/32)
   int chunk_layout;   // 0: z[k][j][i]   1: z[((j*nx+i)*m + r)*32 + lane], k = lane*m + r
 };
 
@@ -223,19 +224,24 @@ __global__ void __launch_bounds__(128) thomas_seq_kernel(const ThomasDev<T> D, c
   for (int k = 0; k < nn; ++k) pc[(long long)k * D.sk] = add_rn(pc[(long long)k * D.sk], mul_rn(p2[zidx(D, i, j, k)], pcl));
 }
 
-// ---- register-resident chunked substitution -----------------------------------
-// CTA = 16 consecutive columns (one 128-byte row segment of the z pencil) x 32
-// chunks of m consecutive rows.  Thread (c, g) owns rows g*m .. g*m+m-1 of
-// column c: its m right-hand-side values are loaded straight into registers
-// (the 16 lanes of a half warp read one full 128-byte line), its m pivots are
-// fetched with cp.async into a private shared-memory strip (so that registers
-// stay below 64 and two CTAs share an SM: one computes while the other's loads
-// are in flight).  Both first-order recurrences are evaluated chunk-parallel:
-// local sweep -> (value, product) of every chunk to shared memory -> each thread
-// folds the chunks before (after) its own -> fix-up.  Nothing but the final
-// result is written; traffic = read p + read z + write p = 24 B/point.
+// ---- pipelined chunked substitution ---------------------------------------------
+// Persistent kernel, one CTA of 1024 threads per SM.  A tile is 16 consecutive
+// columns (one 128-byte row segment of the z pencil) x all rows; thread (c, g)
+// owns the m = ceil(nn / 64) consecutive rows g*m .. g*m+m-1 of column c.
+//   * its m right-hand-side values live in registers (the 16 lanes of a half
+//     warp read / write one full 128-byte line);
+//   * its m pivots are fetched with cp.async into a private strip of a DOUBLE
+//     BUFFERED shared-memory tile;
+//   * while tile i is being solved, the pivots of tile i+1 are in flight to the
+//     other buffer and its right-hand side to a second register set, so HBM
+//     latency is hidden by the pipeline, not by occupancy.
+// Both first-order recurrences are evaluated chunk-parallel: local sweep ->
+// (value, product) of every chunk to shared memory -> one warp per column folds
+// the 64 chunk maps with a shuffle scan -> fix-up.  Nothing but the final result
+// is written: traffic = read p + read z + write p = 24 B/point (FP64).
 #define CB_TH_COLS 16
-#define CB_TH_CHUNKS 32
+#define CB_TH_CHUNKS 64
+#define CB_TH_THREADS (CB_TH_COLS * CB_TH_CHUNKS)
 
 __device__ __forceinline__ void cp_async_elem(double* dst_smem, const double* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -245,150 +251,249 @@ __device__ __forceinline__ void cp_async_elem(float* dst_smem, const float* src)
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <class T, int MMAX> constexpr size_t thomas_reg_smem() {
-  return ((size_t)MMAX * CB_TH_COLS * CB_TH_CHUNKS + 2 * CB_TH_CHUNKS * (MMAX + 1) + 2 * CB_TH_COLS * CB_TH_CHUNKS) * sizeof(T);
+// shared memory: pivot tile [64 m rows][16], right-hand-side tile [64 m rows][16], a/c tables, fold arrays
+template <class T, int MMAX> constexpr size_t thomas_pipe_smem() {
+  return ((size_t)2 * MMAX * CB_TH_THREADS + 2 * CB_TH_CHUNKS * (MMAX + 2) + 2 * CB_TH_COLS * (CB_TH_CHUNKS + 1)) * sizeof(T);
+}
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 
-template <class T, int MMAX>
-__global__ void __launch_bounds__(CB_TH_COLS* CB_TH_CHUNKS, (MMAX <= 16 ? 2 : 1))
-thomas_reg_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, const T* p2base, const T* denbase,
-                  long long slot_z, long long slot_den, T* p, T norm) {
-  constexpr int NT = CB_TH_COLS * CB_TH_CHUNKS;
+__device__ __forceinline__ double shfl_up_t(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ float shfl_up_t(float v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_down_t(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ float shfl_down_t(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+
+// Fold of the 64 chunk maps v -> Y_g + P_g v of every column: warp w < 16 owns column w, lane l owns the
+// chunk pair (2l, 2l+1); Kogge-Stone scan of the pair maps with shuffles; result = value entering each
+// chunk, written over sY.  FWD: chunk 0 upward; otherwise chunk 63 downward.
+template <class T, bool FWD>
+__device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid) {
+  constexpr int LD = CB_TH_CHUNKS + 1;
+  const int w = tid >> 5, lane = tid & 31;
+  if (w < CB_TH_COLS) {
+    T* rowY = sY + w * LD;
+    const T* rowP = sP + w * LD;
+    const T y0 = rowY[2 * lane], y1 = rowY[2 * lane + 1], p0 = rowP[2 * lane], p1 = rowP[2 * lane + 1];
+    // map of the pair, in application order (FWD: chunk 2l then 2l+1; else 2l+1 then 2l)
+    T Y = FWD ? fma(p1, y0, y1) : fma(p0, y1, y0);
+    T P = p0 * p1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const T Yp = FWD ? shfl_up_t(Y, d) : shfl_down_t(Y, d);
+      const T Pp = FWD ? shfl_up_t(P, d) : shfl_down_t(P, d);
+      const bool on = FWD ? (lane >= d) : (lane + d < 32);
+      if (on) { Y = fma(P, Yp, Y); P *= Pp; }
+    }
+    T vin = FWD ? shfl_up_t(Y, 1) : shfl_down_t(Y, 1);
+    if (FWD ? (lane == 0) : (lane == 31)) vin = T(0);
+    if (FWD) {
+      rowY[2 * lane] = vin;
+      rowY[2 * lane + 1] = fma(p0, vin, y0);
+    } else {
+      rowY[2 * lane + 1] = vin;
+      rowY[2 * lane] = fma(p1, vin, y1);
+    }
+  }
+}
+
+// EXACT: the rows per chunk equal MMAX (no per-row predicates in the sweeps).
+// VEC: columns come in aligned 16-byte groups, so the tile copies use 16-byte cp.async.
+template <class T, int MMAX, bool EXACT, bool VEC>
+__global__ void __launch_bounds__(CB_TH_THREADS, 1)
+thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, const T* p2base, const T* denbase,
+                   long long slot_z, long long slot_den, T* p, T norm) {
+  constexpr int NT = CB_TH_THREADS;
+  constexpr int LD = CB_TH_CHUNKS + 1;
+  constexpr int CSA = MMAX + 2;                     // chunk stride of the a/c tables (16-byte aligned, bank spread)
+  constexpr int VW = 16 / sizeof(T);                // elements per 16-byte piece
   extern __shared__ __align__(16) unsigned char cb_smem_raw[];
-  T* zs = reinterpret_cast<T*>(cb_smem_raw);   // [r][tid]
-  T* sa = zs + (size_t)MMAX * NT;              // a_k at [g][r], chunk stride m|1: the two chunks of a warp hit different banks
-  T* sc = sa + CB_TH_CHUNKS * (MMAX + 1);      // c_k
-  T* sY = sc + CB_TH_CHUNKS * (MMAX + 1);      // [g][c] chunk value
-  T* sP = sY + NT;                             // [g][c] chunk product
+  T* zs = reinterpret_cast<T*>(cb_smem_raw);        // [row][16] pivots of the tile in flight / being consumed
+  T* ps = zs + (size_t)MMAX * NT;                   // [row][16] right-hand side
+  T* sa = ps + (size_t)MMAX * NT;                   // a_k at [g][r]
+  T* sc = sa + CB_TH_CHUNKS * CSA;                  // c_k
+  T* sY = sc + CB_TH_CHUNKS * CSA;                  // [c][g] chunk value, row stride 65
+  T* sP = sY + CB_TH_COLS * LD;                     // [c][g] chunk product
   const int tid = threadIdx.x, c = tid & (CB_TH_COLS - 1), g = tid / CB_TH_COLS;
-  const int m = D.m, nn = D.nn;
+  const int m = EXACT ? MMAX : D.m, nn = D.nn;
+  const int nrows_tile = CB_TH_CHUNKS * m;
   const long long ncol = (long long)D.nx * D.ny;
-  const long long col = (long long)blockIdx.x * CB_TH_COLS + c;
-  const bool live = col < ncol;
+  const long long sk = D.sk;
+  const int tiles_x = (D.xn + CB_TH_COLS - 1) / CB_TH_COLS;
+  const int ntiles = tiles_x * D.ny;
   const int sel = st->sel;
   const int k0 = g * m;
-  const int cs0 = g * (m | 1);
+  const int nrow_full = nn - k0 < 0 ? 0 : (nn - k0 < m ? nn - k0 : m);   // my rows inside the system
+  const T* zsel = zbase + (long long)sel * slot_z;
 
-  // pivots: asynchronous copies into my strip
-  {
-    const T* zc = zbase + (long long)sel * slot_z + col;
+  for (int e = tid; e < nrows_tile; e += NT) {
+    const int ge = e / m, re = e - ge * m;
+    sa[ge * CSA + re] = (e < nn) ? D.a[e] : T(0);
+    sc[ge * CSA + re] = (e < nn) ? D.c[e] : T(0);
+  }
+
+  // tile -> (flat column of its first thread, live columns)
+  auto tile_col0 = [&](int tile, int& ncols) -> long long {
+    const int tj = tile / tiles_x;
+    const int ti0 = (tile - tj * tiles_x) * CB_TH_COLS;
+    ncols = D.xn - ti0 < CB_TH_COLS ? D.xn - ti0 : CB_TH_COLS;
+    return (long long)tj * D.nx + D.xb + ti0;
+  };
+  // asynchronous copy of one tile of pivots and right-hand sides into [row][16]; rows >= nn and dead
+  // columns are zero filled so that the chunk maps of padding rows are exact identities / zeros
+  auto prefetch = [&](long long col0, int ncols) {
+    if (VEC) {
+      constexpr int PPR = CB_TH_COLS / VW;          // pieces per row
+      for (int q = tid; q < nrows_tile * PPR; q += NT) {
+        const int row = q / PPR, pc = (q - row * PPR) * VW;
+        T* zd = zs + row * CB_TH_COLS + pc;
+        T* pd = ps + row * CB_TH_COLS + pc;
+        if (row < nn && pc < ncols) {
+          cp_async_16(zd, zsel + (long long)row * ncol + col0 + pc);
+          cp_async_16(pd, p + (long long)row * sk + col0 + pc);
+        } else {
 #pragma unroll
-    for (int r = 0; r < MMAX; ++r) {
-      const int k = k0 + r;
-      if (r < m) {
-        if (live && k < nn) cp_async_elem(zs + r * NT + tid, zc + (long long)k * ncol);
-        else zs[r * NT + tid] = T(0);
+          for (int e = 0; e < VW; ++e) { zd[e] = T(0); pd[e] = T(0); }
+        }
+      }
+    } else {
+      for (int q = tid; q < nrows_tile * CB_TH_COLS; q += NT) {
+        const int row = q / CB_TH_COLS, pc = q - row * CB_TH_COLS;
+        if (row < nn && pc < ncols) {
+          cp_async_elem(zs + q, zsel + (long long)row * ncol + col0 + pc);
+          cp_async_elem(ps + q, p + (long long)row * sk + col0 + pc);
+        } else {
+          zs[q] = T(0);
+          ps[q] = T(0);
+        }
       }
     }
-  }
-  // right-hand side into registers
-  T y[MMAX];
-  {
-    const T* pc = p + col;
+    cp_async_commit();
+  };
+
+  int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  int ncols;
+  long long col0 = tile_col0(tile, ncols);
+  prefetch(col0, ncols);
+  for (; tile < ntiles; tile += gridDim.x) {
+    cp_async_wait<0>();
+    __syncthreads();   // this tile has landed (copies of all threads); also orders the previous tile's sY reads
+    T y[MMAX], z[MMAX];
+#pragma unroll
+    for (int r = 0; r < MMAX; ++r)
+      if (EXACT || r < m) {
+        y[r] = ps[(k0 + r) * CB_TH_COLS + c];
+        z[r] = zs[(k0 + r) * CB_TH_COLS + c];
+      }
+    const bool live = c < ncols;
+    const int nrow = live ? nrow_full : 0;
+    const long long col = col0 + c;
+
+    // forward: y_k = (p_k norm - a_k y_{k-1}) z_k, chunk-local with y_{k0-1} := 0
+    T yy = T(0), pi = T(1);
 #pragma unroll
     for (int r = 0; r < MMAX; ++r) {
-      const int k = k0 + r;
-      y[r] = (r < m && live && k < nn) ? pc[(long long)k * D.sk] : T(0);
+      if (EXACT || r < m) {
+        const T al = -(sa[g * CSA + r] * z[r]);
+        yy = fma(al, yy, y[r] * norm * z[r]);
+        pi *= al;
+        y[r] = yy;
+      }
     }
-  }
-  for (int e = tid; e < CB_TH_CHUNKS * m; e += NT) {
-    const int ge = e / m, re = e - ge * m;
-    sa[ge * (m | 1) + re] = (e < nn) ? D.a[e] : T(0);
-    sc[ge * (m | 1) + re] = (e < nn) ? D.c[e] : T(0);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  // forward: y_k = (p_k norm - a_k y_{k-1}) z_k, chunk-local with y_{k0-1} := 0
-  T yy = T(0), pi = T(1);
-#pragma unroll
-  for (int r = 0; r < MMAX; ++r) {
-    if (r < m) {
-      const T zz = zs[r * NT + tid];
-      const T al = -(sa[cs0 + r] * zz);
-      yy = fma(al, yy, y[r] * norm * zz);
-      pi *= al;
-      y[r] = yy;
+    sY[c * LD + g] = yy;
+    sP[c * LD + g] = pi;
+    __syncthreads();   // every thread holds its tile values in registers: the tile buffers are free again
+    const int tnext = tile + gridDim.x;
+    int ncols_n = 0;
+    long long col0_n = 0;
+    if (tnext < ntiles) {
+      col0_n = tile_col0(tnext, ncols_n);
+      prefetch(col0_n, ncols_n);
     }
-  }
-  sY[tid] = yy;
-  sP[tid] = pi;
-  __syncthreads();
-  T vin = T(0);
-  for (int gg = 0; gg < g; ++gg) vin = fma(sP[gg * CB_TH_COLS + c], vin, sY[gg * CB_TH_COLS + c]);
-  pi = T(1);
-#pragma unroll
-  for (int r = 0; r < MMAX; ++r) {
-    if (r < m) {
-      pi *= -(sa[cs0 + r] * zs[r * NT + tid]);
-      y[r] = fma(pi, vin, y[r]);
-    }
-  }
-  __syncthreads();
-  // backward: x_k = y_k - d_k x_{k+1}, d_k = c_k z_k
-  T xx = T(0), rho = T(1);
-#pragma unroll
-  for (int r = MMAX - 1; r >= 0; --r) {
-    if (r < m) {
-      const T nd = -(sc[cs0 + r] * zs[r * NT + tid]);
-      xx = fma(nd, xx, y[r]);
-      rho *= nd;
-      y[r] = xx;
-    }
-  }
-  sY[tid] = xx;
-  sP[tid] = rho;
-  __syncthreads();
-  vin = T(0);
-  for (int gg = CB_TH_CHUNKS - 1; gg > g; --gg) vin = fma(sP[gg * CB_TH_COLS + c], vin, sY[gg * CB_TH_COLS + c]);
-  rho = T(1);
-#pragma unroll
-  for (int r = MMAX - 1; r >= 0; --r) {
-    if (r < m) {
-      rho *= -(sc[cs0 + r] * zs[r * NT + tid]);
-      y[r] = fma(rho, vin, y[r]);
-    }
-  }
-  if (D.periodic) {
-    // closure value and rank-one correction, src/solver.f90:272-306
+    thomas_fold<T, true>(sY, sP, tid);
     __syncthreads();
-    const int kl = nn - 1;
-    if (g == 0) sY[c] = y[0];                  // x_1
-    if (kl >= k0 && kl < k0 + m) {
+    T vin = sY[c * LD + g];
+    pi = T(1);
+#pragma unroll
+    for (int r = 0; r < MMAX; ++r) {
+      if (EXACT || r < m) {
+        pi *= -(sa[g * CSA + r] * z[r]);
+        y[r] = fma(pi, vin, y[r]);
+      }
+    }
+    // backward: x_k = y_k - d_k x_{k+1}, d_k = c_k z_k
+    T xx = T(0), rho = T(1);
+#pragma unroll
+    for (int r = MMAX - 1; r >= 0; --r) {
+      if (EXACT || r < m) {
+        const T nd = -(sc[g * CSA + r] * z[r]);
+        xx = fma(nd, xx, y[r]);
+        rho *= nd;
+        y[r] = xx;
+      }
+    }
+    sY[c * LD + g] = xx;   // own slot: only this thread read it since the fold
+    sP[c * LD + g] = rho;
+    __syncthreads();
+    thomas_fold<T, false>(sY, sP, tid);
+    __syncthreads();
+    vin = sY[c * LD + g];
+    rho = T(1);
+#pragma unroll
+    for (int r = MMAX - 1; r >= 0; --r) {
+      if (EXACT || r < m) {
+        rho *= -(sc[g * CSA + r] * z[r]);
+        y[r] = fma(rho, vin, y[r]);
+      }
+    }
+    if (D.periodic) {
+      // closure value and rank-one correction, src/solver.f90:272-306
+      __syncthreads();
+      const int kl = nn - 1;
+      if (g == 0) sY[c] = y[0];                  // x_1
+      if (kl >= k0 && kl < k0 + m) {
+#pragma unroll
+        for (int r = 0; r < MMAX; ++r)
+          if (k0 + r == kl) sY[CB_TH_COLS + c] = y[r];   // x_nn
+      }
+      __syncthreads();
+      if (g == 0) {
+        T pcl = T(0);
+        if (live) {
+          const T den = denbase[(long long)sel * slot_den + col];
+          const T pnn = p[(long long)nn * sk + col];
+          const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[CB_TH_COLS + c]));
+          pcl = (den == T(0)) ? T(0) : div_rn(num, den);
+          p[(long long)nn * sk + col] = pcl;
+        }
+        sP[c] = pcl;
+      }
+      __syncthreads();
+      const T pcl = sP[c];
+      const T* p2c = p2base + (long long)sel * slot_z + col + (long long)k0 * ncol;
 #pragma unroll
       for (int r = 0; r < MMAX; ++r)
-        if (k0 + r == kl) sY[CB_TH_COLS + c] = y[r];   // x_nn
+        if (r < nrow) y[r] = fma(p2c[r * ncol], pcl, y[r]);
     }
-    __syncthreads();
-    if (g == 0) {
-      T pcl = T(0);
-      if (live) {
-        const T den = denbase[(long long)sel * slot_den + col];
-        const T pnn = p[(long long)nn * D.sk + col];
-        const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[CB_TH_COLS + c]));
-        pcl = (den == T(0)) ? T(0) : div_rn(num, den);
-        p[(long long)nn * D.sk + col] = pcl;
+    {
+      T* pc = p + (long long)k0 * sk + col;
+      if (nrow == m) {
+#pragma unroll
+        for (int r = 0; r < MMAX; ++r)
+          if (EXACT || r < m) pc[r * sk] = y[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < MMAX; ++r)
+          if (r < nrow) pc[r * sk] = y[r];
       }
-      sP[c] = pcl;
     }
-    __syncthreads();
-    const T pcl = sP[c];
-    const T* p2c = p2base + (long long)sel * slot_z + col;
-#pragma unroll
-    for (int r = 0; r < MMAX; ++r) {
-      const int k = k0 + r;
-      if (r < m && live && k < nn) y[r] = fma(p2c[(long long)k * ncol], pcl, y[r]);
-    }
-  }
-  {
-    T* pc = p + col;
-#pragma unroll
-    for (int r = 0; r < MMAX; ++r) {
-      const int k = k0 + r;
-      if (r < m && live && k < nn) pc[(long long)k * D.sk] = y[r];
-    }
+    col0 = col0_n;
+    ncols = ncols_n;
   }
 }
 

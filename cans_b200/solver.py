@@ -88,6 +88,11 @@ class Context:
         check(lib.cansb200_ctx_set(self._h, 1, int(x)), "ctx_set")
         check(lib.cansb200_ctx_set(self._h, 2, int(y)), "ctx_set")
 
+    def set_chain(self, cols: int = 0, streams: int = 2):
+        """L2-resident fft-y -> tridiagonal -> ifft-y chain over x windows of `cols` columns (0 = off)."""
+        check(lib.cansb200_ctx_set(self._h, 3, int(cols)), "ctx_set")
+        check(lib.cansb200_ctx_set(self._h, 4, int(streams)), "ctx_set")
+
     def set_profiling(self, on: bool):
         check(lib.cansb200_set_profiling(self._h, int(on)), "set_profiling")
 

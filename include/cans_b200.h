@@ -43,7 +43,7 @@ enum { CANSB200_MEM_HOST = 0, CANSB200_MEM_DEVICE = 1 };
 
 /* Tunables; negative = library default.  Read once by cansb200_plan_create. */
 typedef struct cansb200_options {
-  int thomas_variant;   /* 0 = sequential two-sweep (any nz), 1 = warp-per-column on-chip (nz <= 1024) */
+  int thomas_variant;   /* 0 = sequential two-sweep (any nz), 1 = pipelined chunk-parallel on-chip (nz <= 1024) */
   int cache_slots;      /* factorisation cache entries per plan (1..8); Helmholtz plans want 3 */
   int fft_x_lines;      /* lines per tile of the contiguous transforms (0 = auto) */
   int fft_y_lines;      /* 8 or 16: x-width of the strided-transform tile (0 = auto) */
@@ -120,7 +120,9 @@ int cansb200_get_profile(cansb200_ctx* ctx, double ms[8], unsigned long long* ns
 enum {
   CANSB200_CTX_FORCE_GENERIC = 0,
   CANSB200_CTX_X_VARIANT = 1,   /* tuning variant (thread / radix split) of the contiguous transforms, 0 = default */
-  CANSB200_CTX_Y_VARIANT = 2    /* same for the strided transforms */
+  CANSB200_CTX_Y_VARIANT = 2,   /* same for the strided transforms */
+  CANSB200_CTX_CHAIN_COLS = 3,  /* x-window (multiple of 16 columns) of the L2-resident fft-y -> tridiagonal -> ifft-y chain; 0 = off */
+  CANSB200_CTX_CHAIN_STREAMS = 4 /* auxiliary streams the windows are issued on (1..8) */
 };
 int cansb200_ctx_set(cansb200_ctx* ctx, int what, int value);
 /* workspace the OpenACC host may alias as `work` / `solver_buf_0` (src/rk.f90:26-30) */
