@@ -11,6 +11,7 @@
 
 #include "../../include/cans_b200.h"
 #include "aux_kernels.cuh"
+#include "dist_kernels.cuh"
 #include "fft_kernels.cuh"
 #include "fft_plan.hpp"
 #include "r2r2.cuh"
@@ -20,12 +21,14 @@ using namespace cb;
 
 namespace cb {
 // explicit instantiations live in r2r2_{x,y}{64,32}.cu
-template <class T, bool YMODE> int r2r2_run(const R2Args<T>& A, int n, int var, bool fwd, cudaStream_t st);
+template <class T, bool YMODE, bool SPLIT> int r2r2_run(const R2Args<T>& A, int n, int var, bool fwd, cudaStream_t st);
 template <bool YMODE> int r2r2_query(int n, int var, int radix[4]);
-extern template int r2r2_run<double, false>(const R2Args<double>&, int, int, bool, cudaStream_t);
-extern template int r2r2_run<double, true>(const R2Args<double>&, int, int, bool, cudaStream_t);
-extern template int r2r2_run<float, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
-extern template int r2r2_run<float, true>(const R2Args<float>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<double, false, false>(const R2Args<double>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<double, true, false>(const R2Args<double>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<float, false, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<float, true, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<double, true, true>(const R2Args<double>&, int, int, bool, cudaStream_t);
+extern template int r2r2_run<float, true, true>(const R2Args<float>&, int, int, bool, cudaStream_t);
 extern template int r2r2_query<false>(int, int, int[4]);
 extern template int r2r2_query<true>(int, int, int[4]);
 }  // namespace cb
@@ -94,6 +97,16 @@ struct cansb200_ctx {
   std::map<int, R2Tables<float>> r2tabs32;
   int force_generic = 0;                       // tests: route every transform through the generic engine
   int r2_variant[2] = {0, 0};                  // tuning variant of the fast path, [x, y]
+  // ---- z-slab decomposition over the GPUs of one box (dims = [1, P]); see dist_kernels.cuh
+  std::vector<int> ys, zs;                     // split starts of y and z, size P + 1
+  void* region = nullptr;                      // IPC-exported: [flags][C = z pencil][XB = way-back buffer]
+  size_t region_bytes = 0, off_C = 0, off_XB = 0;
+  std::vector<void*> peer;                     // peer-mapped region bases (own rank: region)
+  std::vector<size_t> peer_off_XB;             // offset of XB inside every rank's region
+  bool connected = false;
+  unsigned long long epoch = 0;
+  int* dist_status = nullptr;
+  DevBuf ytab_fwd, ytab_bwd, ztab;
   // L2-resident chain: fft-y -> tridiagonal -> ifft-y run per window of `chain_cols` x columns, windows
   // round-robin on auxiliary streams, so that the two intermediate fields never leave the L2 cache
   int chain_cols = 0;                          // 0 = off (three full-field passes)
@@ -233,6 +246,7 @@ template <class T> static int get_direct_tables(cansb200_ctx* ctx, int n, int ki
 struct R2RGeom {
   long long in_es, out_es, in_ls, out_ls, in_gs, out_gs;
   int lines_per_group, ngroups, line_len, ymode;
+  const void* row_tab = nullptr;   // distributed y transforms: peer-mapped output (forward) / input (backward) rows
 };
 
 template <class T>
@@ -263,8 +277,10 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
       A.lines_per_group = g.lines_per_group; A.ngroups = g.ngroups; A.line_len = g.line_len; A.kind = kind;
       for (int s = 0; s < 4; ++s) A.tw[s] = rt->tw[s];
       A.mak = rt->mak;
-      const int rc = g.ymode ? r2r2_run<T, true>(A, nt, var, kind_is_forward(kind), st)
-                             : r2r2_run<T, false>(A, nt, var, kind_is_forward(kind), st);
+      A.row_tab = (const R2Row<T>*)g.row_tab;
+      const int rc = !g.ymode ? r2r2_run<T, false, false>(A, nt, var, kind_is_forward(kind), st)
+                     : g.row_tab ? r2r2_run<T, true, true>(A, nt, var, kind_is_forward(kind), st)
+                                 : r2r2_run<T, true, false>(A, nt, var, kind_is_forward(kind), st);
       if (rc < 0) return fail(CANSB200_ECUDA, "r2r: fast-path launch failed");
       if (rc == 0) {
         ctx->launches++;
@@ -273,6 +289,7 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
       }
     }
   }
+  if (g.row_tab) return fail(CANSB200_EUNSUPPORTED, "r2r: the distributed solve needs a fast-path y length (64..2048, 2^k or 3*2^k)");
   FftTables<T>* tb;
   int rc = get_tables<T>(ctx, nt, &tb);
   if (rc) return rc;
@@ -342,7 +359,7 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   ThomasDev<T> D;
   D.nx = nx; D.ny = ny; D.n = n_rows; D.periodic = periodic; D.nn = periodic ? n_rows - 1 : n_rows;
   D.sj = sj; D.sk = sk; D.a = a; D.b = b; D.c = c; D.lam = lam; D.lam_sj = nx;
-  D.m = pl->th_m; D.chunk_layout = 0; D.xb = 0; D.xn = nx;
+  D.m = pl->th_m; D.chunk_layout = 0; D.xb = 0; D.xn = nx; D.out_rows = nullptr;
   return D;
 }
 
@@ -449,19 +466,39 @@ extern "C" {
 const char* cansb200_last_error(void) { return g_err.c_str(); }
 int cansb200_version(void) { return 100; }
 
+static void split_starts(int n, int P, std::vector<int>& st) {
+  // first n mod P ranks get one extra point (dependencies/2decomp-fft/src/decomp_2d.f90:1018-1029,
+  // dependencies/cuDecomp/src/cudecomp.cc:1348-1357)
+  st.assign(P + 1, 0);
+  const int base = n / P, rem = n % P;
+  for (int r = 0; r < P; ++r) st[r + 1] = st[r] + base + (r < rem ? 1 : 0);
+}
+
+struct DistBlob {
+  cudaIpcMemHandle_t handle;
+  int rank, device;
+  unsigned long long bytes;
+};
+
 int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ipencil_axis, int rank, int nranks,
                   const void* nccl_id, int is_fp32) {
-  (void)nccl_id;
+  (void)nccl_id;   // the exchange runs over CUDA IPC peer mappings (cansb200_dist_export / _connect), not NCCL
   if (!out || !ng || !dims) return fail(CANSB200_EINVAL, "init: null argument");
   if (ng[0] < 1 || ng[1] < 1 || ng[2] < 1) return fail(CANSB200_EINVAL, "init: ng must be positive");
   if (ipencil_axis != 1) return fail(CANSB200_EUNSUPPORTED, "init: only ipencil_axis = 1 (x pencils) is implemented");
-  if (nranks != 1 || dims[0] != 1 || dims[1] != 1)
-    return fail(CANSB200_EUNSUPPORTED, "init: multi-rank contexts are created with cansb200_init_dist");
+  if (nranks < 1 || nranks > CB_MAX_RANKS || rank < 0 || rank >= nranks) return fail(CANSB200_EINVAL, "init: bad rank / nranks");
+  if (dims[0] != 1 || dims[1] != nranks)
+    return fail(CANSB200_EUNSUPPORTED, "init: only dims = [1, nranks] (z slabs) is implemented");
+  if (nranks > ng[1] || nranks > ng[2]) return fail(CANSB200_EINVAL, "init: more ranks than y or z planes");
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (ndev < 1) return fail(CANSB200_ECUDA, "init: no CUDA device");
   auto* c = new cansb200_ctx();
+  split_starts(ng[1], nranks, c->ys);
+  split_starts(ng[2], nranks, c->zs);
   for (int d = 0; d < 3; ++d) { c->ng[d] = ng[d]; c->n[d] = ng[d]; c->lo[d] = 1; c->n_z[d] = ng[d]; c->lo_z[d] = 1; }
+  c->n[2] = c->zs[rank + 1] - c->zs[rank];   c->lo[2] = c->zs[rank] + 1;      // x pencil: (nx, ny, nz/P)
+  c->n_z[1] = c->ys[rank + 1] - c->ys[rank]; c->lo_z[1] = c->ys[rank] + 1;    // z pencil: (nx, ny/P, nz)
   c->dims[0] = dims[0]; c->dims[1] = dims[1]; c->ipencil_axis = ipencil_axis; c->rank = rank; c->nranks = nranks;
   c->is_fp32 = is_fp32 ? 1 : 0;
   c->esz = is_fp32 ? 4 : 8;
@@ -472,7 +509,102 @@ int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ip
   }
   const size_t nel = (size_t)c->n[0] * c->n[1] * c->n[2];
   if (c->scratch.ensure(nel * c->esz)) { delete c; return fail(CANSB200_ENOMEM, "init: scratch allocation failed"); }
+  if (nranks > 1) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t nel_z = (size_t)c->n_z[0] * c->n_z[1] * c->n_z[2];
+    c->off_C = 4096;
+    c->off_XB = c->off_C + up(nel_z * c->esz);
+    c->region_bytes = c->off_XB + up(nel * c->esz);
+    if (cudaMalloc(&c->region, c->region_bytes) != cudaSuccess) { c->scratch.release(); delete c; return fail(CANSB200_ENOMEM, "init: exchange region"); }
+    cudaMemset(c->region, 0, 4096);
+    if (cudaMalloc((void**)&c->dist_status, sizeof(int)) != cudaSuccess) { delete c; return fail(CANSB200_ENOMEM, "init: status word"); }
+    cudaMemset(c->dist_status, 0, sizeof(int));
+    c->peer.assign(nranks, nullptr);
+    c->peer[rank] = c->region;
+  }
   *out = c;
+  return 0;
+}
+
+int cansb200_dist_blob_size(void) { return (int)sizeof(DistBlob); }
+
+int cansb200_dist_export(cansb200_ctx* c, void* blob) {
+  if (!c || !blob) return fail(CANSB200_EINVAL, "dist_export: null argument");
+  if (c->nranks < 2) return fail(CANSB200_EINVAL, "dist_export: single-rank context");
+  DistBlob b;
+  memset(&b, 0, sizeof(b));
+  CK(cudaIpcGetMemHandle(&b.handle, c->region));
+  CK(cudaGetDevice(&b.device));
+  b.rank = c->rank;
+  b.bytes = c->region_bytes;
+  memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+}  // extern "C"
+
+// device-side row tables of the peer-mapped stores / loads
+template <class T> static int build_dist_tables(cansb200_ctx* c) {
+  const int P = c->nranks, r = c->rank;
+  const long long nx = c->ng[0];
+  const int ny = c->ng[1], nz = c->ng[2];
+  const long long nzl_r = c->zs[r + 1] - c->zs[r], nyl_r = c->ys[r + 1] - c->ys[r];
+  std::vector<R2Row<T>> yf(ny), yb(ny);
+  for (int s = 0; s < P; ++s) {
+    const long long nyl_s = c->ys[s + 1] - c->ys[s];
+    T* C_s = (T*)((char*)c->peer[s] + c->off_C);        // C sits at the same offset in every rank's region
+    T* XB_r = (T*)((char*)c->region + c->off_XB);
+    for (int j = c->ys[s]; j < c->ys[s + 1]; ++j) {
+      // forward y output row j of my plane g: z pencil of rank s, plane zs[r] + g, row j - ys[s]
+      yf[j].ptr = C_s + ((long long)c->zs[r] * nyl_s + (j - c->ys[s])) * nx;
+      yf[j].gs = nyl_s * nx;
+      // backward y input row j of my plane g: block s of my way-back buffer [s][g][j - ys[s]][i]
+      yb[j].ptr = XB_r + (nzl_r * c->ys[s] + (j - c->ys[s])) * nx;
+      yb[j].gs = nyl_s * nx;
+    }
+  }
+  std::vector<T*> zt(nz);
+  for (int s = 0; s < P; ++s) {
+    const long long nzl_s = c->zs[s + 1] - c->zs[s];
+    T* XB_s = (T*)((char*)c->peer[s] + c->peer_off_XB[s]);
+    for (int k = c->zs[s]; k < c->zs[s + 1]; ++k)   // result row k of my columns: block r of rank s's way-back buffer
+      zt[k] = XB_s + nzl_s * c->ys[r] * nx + (long long)(k - c->zs[s]) * nyl_r * nx;
+  }
+  if (c->ytab_fwd.ensure(sizeof(R2Row<T>) * ny) || c->ytab_bwd.ensure(sizeof(R2Row<T>) * ny) || c->ztab.ensure(sizeof(T*) * nz))
+    return fail(CANSB200_ENOMEM, "dist_connect: tables");
+  CK(cudaMemcpy(c->ytab_fwd.p, yf.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->ytab_bwd.p, yb.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->ztab.p, zt.data(), sizeof(T*) * nz, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" {
+
+int cansb200_dist_connect(cansb200_ctx* c, const void* blobs) {
+  if (!c || !blobs) return fail(CANSB200_EINVAL, "dist_connect: null argument");
+  if (c->nranks < 2) return fail(CANSB200_EINVAL, "dist_connect: single-rank context");
+  const DistBlob* b = (const DistBlob*)blobs;
+  c->peer_off_XB.assign(c->nranks, 0);
+  for (int s = 0; s < c->nranks; ++s) {
+    if (b[s].rank != s) return fail(CANSB200_EINVAL, "dist_connect: blobs must be ordered by rank");
+    // offsets inside rank s's region follow from the global splits
+    const size_t nel_z = (size_t)c->ng[0] * (c->ys[s + 1] - c->ys[s]) * c->ng[2];
+    c->peer_off_XB[s] = 4096 + ((nel_z * c->esz + 255) & ~(size_t)255);
+    if (s == c->rank) continue;
+    void* q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, b[s].handle, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[s] = q;
+  }
+  const int rc = c->is_fp32 ? build_dist_tables<float>(c) : build_dist_tables<double>(c);
+  if (rc) return rc;
+  c->connected = true;
+  return 0;
+}
+
+int cansb200_dist_status(cansb200_ctx* c, int* status) {
+  if (!c || !status) return fail(CANSB200_EINVAL, "dist_status: null argument");
+  *status = 0;
+  if (c->dist_status) CK(cudaMemcpy(status, c->dist_status, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -481,6 +613,11 @@ int cansb200_finalize(cansb200_ctx* c) {
   c->scratch.release(); c->staging.release(); c->coef.release();
   for (auto& kv : c->tabs64) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (auto& kv : c->tabs32) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
+  for (int q = 0; q < (int)c->peer.size(); ++q)
+    if (q != c->rank && c->peer[q]) cudaIpcCloseMemHandle(c->peer[q]);
+  if (c->region) cudaFree(c->region);
+  if (c->dist_status) cudaFree(c->dist_status);
+  c->ytab_fwd.release(); c->ytab_bwd.release(); c->ztab.release();
   for (cudaStream_t q : c->aux) cudaStreamDestroy(q);
   for (cudaEvent_t q : c->aux_done) cudaEventDestroy(q);
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
@@ -644,6 +781,84 @@ int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
+// device-side barrier over the ranks of the box, stream ordered (dist_kernels.cuh)
+static int dist_barrier(cansb200_ctx* c, cudaStream_t st) {
+  DistPeers pp;
+  for (int s = 0; s < CB_MAX_RANKS; ++s) pp.flags[s] = s < c->nranks ? (unsigned long long*)c->peer[s] : nullptr;
+  c->epoch += 1;
+  dist_barrier_kernel<<<1, 32, 0, st>>>(pp, c->rank, c->nranks, c->epoch, c->dist_status, 20ULL * 1000000000ULL);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// the z-slab decomposed solve: x and y transforms on my slab, tridiagonal stage on my z pencil
+template <class T>
+static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, const T* lam, const T* a, const T* b,
+                      const T* c, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  if (!ctx->connected) return fail(CANSB200_ECOMM, "solve: cansb200_dist_connect has not been called");
+  const int nx = n[0], ny = n[1], nzl = n[2];
+  const int nyl = ctx->n_z[1], nz = ctx->ng[2];
+  const long long px = nx + 2, py = ny + 2;
+  T* A = (T*)ctx->scratch.p;
+  T* Cz = (T*)((char*)ctx->region + ctx->off_C);
+  T* XB = (T*)((char*)ctx->region + ctx->off_XB);
+  T* pin = p + (px * py + px + 1);
+  int rc;
+  prof_mark(ctx, st);
+  R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nzl, nx, 0};
+  rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  // forward y: rows go straight to the z pencils of their owners (pack + wire + unpack = one peer store)
+  R2RGeom gyf{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nzl, ny, 1};
+  gyf.row_tab = ctx->ytab_fwd.p;
+  rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, A, gyf, pl->opt.fft_y_lines, st);
+  if (rc) return rc;
+  rc = dist_barrier(ctx, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  // tridiagonal solve on my z pencil (nx, ny/P, nz); result rows go straight to the slabs of their owners
+  if (pl->th_n != nz - pl->q) return fail(CANSB200_EINVAL, "solve: plan / grid mismatch");
+  ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam, a, b, c);
+  D.out_rows = (T* const*)ctx->ztab.p;
+  rc = gaussel_prepare<T>(pl, D, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  if (pl->th_variant == 1) {
+    rc = gaussel_apply<T>(pl, D, Cz, (T)normfft, st);
+    if (rc) return rc;
+    if (pl->th_n < nz) {   // face-centred Dirichlet: the last plane is not part of the system but still travels back
+      scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, D.out_rows, pl->th_n, nz, (long long)nx * nyl);
+      ctx->launches++;
+    }
+  } else {
+    ThomasDev<T> D2 = D;
+    D2.out_rows = nullptr;
+    rc = gaussel_apply<T>(pl, D2, Cz, (T)normfft, st);
+    if (rc) return rc;
+    scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, D.out_rows, 0, nz, (long long)nx * nyl);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  rc = dist_barrier(ctx, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  // backward y: gathers its rows from the way-back buffer, writes the natural slab
+  R2RGeom gyb{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nzl, ny, 1};
+  gyb.row_tab = ctx->ytab_bwd.p;
+  rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], XB, A, gyb, pl->opt.fft_y_lines, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nzl, nx, 0};
+  rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 template <class T>
 static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double normfft, const void* lam_any, const void* a_any,
                       const void* b_any, const void* c_any, int mem_kind, cudaStream_t st) {
@@ -655,16 +870,27 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   const T *lam = (const T*)lam_any, *a = (const T*)a_any, *b = (const T*)b_any, *c = (const T*)c_any;
   if (mem_kind == CANSB200_MEM_HOST) {
     if (ctx->staging.ensure(nh * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: staging");
-    const size_t ncoef = 3 * (size_t)nz + (size_t)nx * ny;
+    const size_t nzg = (size_t)ctx->n_z[2], nlam = (size_t)ctx->n_z[0] * ctx->n_z[1];   // a, b, c(n_z(3)); lambdaxy(n_z(1), n_z(2))
+    const size_t ncoef = 3 * nzg + nlam;
     if (ctx->coef.ensure(ncoef * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: coefficient staging");
     T* cf = (T*)ctx->coef.p;
     CK(cudaMemcpyAsync(ctx->staging.p, p_any, nh * sizeof(T), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(cf, a_any, nz * sizeof(T), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(cf + nz, b_any, nz * sizeof(T), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(cf + 2 * nz, c_any, nz * sizeof(T), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(cf + 3 * nz, lam_any, (size_t)nx * ny * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf, a_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf + nzg, b_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf + 2 * nzg, c_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf + 3 * nzg, lam_any, nlam * sizeof(T), cudaMemcpyHostToDevice, st));
     p = (T*)ctx->staging.p;
-    a = cf; b = cf + nz; c = cf + 2 * nz; lam = cf + 3 * nz;
+    a = cf; b = cf + nzg; c = cf + 2 * nzg; lam = cf + 3 * nzg;
+  }
+  if (ctx->nranks > 1) {
+    const int rcd = solve_dist<T>(pl, p, n, normfft, lam, a, b, c, st);
+    if (rcd) return rcd;
+    if (mem_kind == CANSB200_MEM_HOST) {
+      CK(cudaMemcpyAsync(p_any, ctx->staging.p, nh * sizeof(T), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    pl->solves++;
+    return 0;
   }
   T* A = (T*)ctx->scratch.p;
   T* pin = p + (px * py + px + 1);  // p(1,1,1)

@@ -196,6 +196,9 @@ template <int N_, int TPL_, int G_, int MINB_, int R0_, int R1_ = 1, int R2_ = 1
   }
 };
 
+// distributed y transforms: row i of a line lives at ptr + g * gs + x on some GPU of the box (peer-mapped)
+template <class T> struct __align__(16) R2Row { T* ptr; long long gs; };
+
 template <class T> struct R2Args {
   const T* in;
   T* out;
@@ -206,6 +209,7 @@ template <class T> struct R2Args {
   int kind;
   const Cx<T>* tw[4];        // per stage s: (R_s - 1) * L_s entries, w_{Ns}^{o r} at [(r-1) L + o]
   const Cx<T>* mak;          // (cos, sin)(pi k / (2N)), k = 0..N/2
+  const R2Row<T>* row_tab;   // SPLIT kernels: where each output (forward) / input (backward) row lives
 };
 
 template <class T, class Cfg, bool YMODE> struct R2Lay {
@@ -244,6 +248,7 @@ template <class Cfg, bool YMODE> __device__ __forceinline__ void r2_group_sync(i
 template <class T> struct R2Loc {
   long long ia, ib, oa, ob;  // offsets of sequences a and b (x mode: two lines; y mode: ib = ia + 1)
   bool has_a, has_b;
+  int g, x;                  // y mode: group (z plane) and first column of my pair
 };
 
 template <class T, class Cfg, bool YMODE>
@@ -259,6 +264,8 @@ __device__ __forceinline__ R2Loc<T> r2_locate(const R2Args<T>& A, int c) {
     L.ob = L.oa + A.out_ls;
     L.has_a = x < A.lines_per_group;
     L.has_b = x + 1 < A.lines_per_group;
+    L.g = g;
+    L.x = x;
   } else {
     const long long nl = (long long)A.lines_per_group * A.ngroups;
     const long long la = ((long long)blockIdx.x * Cfg::G + c) * 2, lb = la + 1;
@@ -270,6 +277,8 @@ __device__ __forceinline__ R2Loc<T> r2_locate(const R2Args<T>& A, int c) {
     L.ob = gb * A.out_gs + jb * A.out_ls;
     L.has_a = la < nl;
     L.has_b = lb < nl;
+    L.g = 0;
+    L.x = 0;
   }
   return L;
 }
@@ -296,6 +305,39 @@ __device__ __forceinline__ void r2_store(T* __restrict__ p, const R2Loc<T>& L, l
     if (L.has_a) p[L.oa + i] = a;
     if (L.has_b) p[L.ob + i] = b;
   }
+}
+
+// split (peer-mapped) rows of the distributed y transforms
+__device__ __forceinline__ R2Row<double> r2_row(const R2Row<double>* tab, int i) {
+  const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(tab + i));
+  R2Row<double> r;
+  r.ptr = reinterpret_cast<double*>(v.x);
+  r.gs = v.y;
+  return r;
+}
+__device__ __forceinline__ R2Row<float> r2_row(const R2Row<float>* tab, int i) {
+  const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(tab + i));
+  R2Row<float> r;
+  r.ptr = reinterpret_cast<float*>(v.x);
+  r.gs = v.y;
+  return r;
+}
+template <class T>
+__device__ __forceinline__ Cx<T> r2_load_split(const R2Row<T>* tab, const R2Loc<T>& L, int i) {
+  const R2Row<T> e = r2_row(tab, i);
+  const T* q = e.ptr + (long long)L.g * e.gs + L.x;
+  if (L.has_b) return *reinterpret_cast<const Cx<T>*>(q);
+  Cx<T> v;
+  v.x = L.has_a ? *q : T(0);
+  v.y = T(0);
+  return v;
+}
+template <class T>
+__device__ __forceinline__ void r2_store_split(const R2Row<T>* tab, const R2Loc<T>& L, int i, T a, T b) {
+  const R2Row<T> e = r2_row(tab, i);
+  T* q = e.ptr + (long long)L.g * e.gs + L.x;
+  if (L.has_b) { *reinterpret_cast<Cx<T>*>(q) = Cx<T>{a, b}; return; }
+  if (L.has_a) *q = a;
 }
 
 // Makhoul permutation: position j of v holds input sample vperm(j)
@@ -356,8 +398,9 @@ __device__ __forceinline__ void r2_dit_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T
 }
 
 // ---- forward kinds: R2HC, REDFT10, RODFT10 ---------------------------------------------------------
-template <class T, class Cfg, bool YMODE>
+template <class T, class Cfg, bool YMODE, bool SPLIT = false>
 __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(const R2Args<T> A) {
+  static_assert(!SPLIT || YMODE, "split rows exist only for the strided (y) transforms");
   using C = Cx<T>;
   using Lay = R2Lay<T, Cfg, YMODE>;
   extern __shared__ __align__(16) unsigned char cb_smem_raw[];
@@ -370,6 +413,10 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
   const int kind = A.kind;
   const bool trig = kind != K_R2HC;
   const bool neg_odd = kind == K_RODFT10;
+  auto put = [&](int i, T a, T b) {
+    if (SPLIT) r2_store_split<T>(A.row_tab, loc, i, a, b);
+    else r2_store<T, YMODE>(A.out, loc, A.out_es, i, a, b);
+  };
 
   C v[E];
   {
@@ -386,10 +433,10 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
       }
   }
   // copy the untransformed tail when the result goes to another array
-  if (A.line_len > N && A.in != A.out) {
+  if (A.line_len > N && (SPLIT || A.in != A.out)) {
     for (int i = N + t; i < A.line_len; i += TPL) {
       const C x = r2_load<T, YMODE>(A.in, loc, A.in_es, i);
-      r2_store<T, YMODE>(A.out, loc, A.out_es, i, x.x, x.y);
+      put(i, x.x, x.y);
     }
   }
   r2_dif_stage<T, Cfg, YMODE, 0>(v, sm, A, c, t);
@@ -407,15 +454,15 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
     const T sx = zk.x + zm.x, dx = zk.x - zm.x, sy = zk.y + zm.y, dy = zk.y - zm.y;
     if (!trig) {
       // A_k = (sx, dy) / 2, B_k = (sy, -dx) / 2 ; halfcomplex: re at k, im at N - k
-      r2_store<T, YMODE>(A.out, loc, A.out_es, k, T(0.5) * sx, T(0.5) * sy);
-      if (k > 0 && 2 * k != N) r2_store<T, YMODE>(A.out, loc, A.out_es, N - k, T(0.5) * dy, T(-0.5) * dx);
+      put(k, T(0.5) * sx, T(0.5) * sy);
+      if (k > 0 && 2 * k != N) put(N - k, T(0.5) * dy, T(-0.5) * dx);
     } else {
       const C cs = cx_ldg(A.mak + k);
       const T xa = cs.x * sx + cs.y * dy, xb = cs.x * sy - cs.y * dx;
-      r2_store<T, YMODE>(A.out, loc, A.out_es, rev_out ? N - 1 - k : k, xa, xb);
+      put(rev_out ? N - 1 - k : k, xa, xb);
       if (k > 0) {
         const T ya = cs.y * sx - cs.x * dy, yb = cs.y * sy + cs.x * dx;
-        r2_store<T, YMODE>(A.out, loc, A.out_es, rev_out ? k - 1 : N - k, ya, yb);
+        put(rev_out ? k - 1 : N - k, ya, yb);
       }
     }
   };
@@ -426,8 +473,9 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
 }
 
 // ---- backward kinds: HC2R, REDFT01, RODFT01 --------------------------------------------------------
-template <class T, class Cfg, bool YMODE>
+template <class T, class Cfg, bool YMODE, bool SPLIT = false>
 __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(const R2Args<T> A) {
+  static_assert(!SPLIT || YMODE, "split rows exist only for the strided (y) transforms");
   using C = Cx<T>;
   using Lay = R2Lay<T, Cfg, YMODE>;
   extern __shared__ __align__(16) unsigned char cb_smem_raw[];
@@ -440,6 +488,10 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
   const int kind = A.kind;
   const bool trig = kind != K_HC2R;
   const bool rv = kind == K_RODFT01;
+  auto get = [&](int i) -> C {
+    if (SPLIT) return r2_load_split<T>(A.row_tab, loc, i);
+    return r2_load<T, YMODE>(A.in, loc, A.in_es, i);
+  };
 
   // pre-pass: Z_k = W^a_k + i W^b_k and Z_{N-k} = conj W^a_k + i conj W^b_k, stored re/im swapped.
   // Two steps so that all global loads of a thread are in flight together.
@@ -449,11 +501,11 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
     const int km = N - k;
     xm = C{T(0), T(0)};
     if (!trig) {
-      xk = r2_load<T, YMODE>(A.in, loc, A.in_es, k);
-      if (k > 0 && 2 * k != N) xm = r2_load<T, YMODE>(A.in, loc, A.in_es, km);
+      xk = get(k);
+      if (k > 0 && 2 * k != N) xm = get(km);
     } else {
-      xk = r2_load<T, YMODE>(A.in, loc, A.in_es, rv ? N - 1 - k : k);
-      if (k > 0) xm = r2_load<T, YMODE>(A.in, loc, A.in_es, rv ? k - 1 : km);  // X_N := 0
+      xk = get(rv ? N - 1 - k : k);
+      if (k > 0) xm = get(rv ? k - 1 : km);  // X_N := 0
     }
   };
   auto scatter = [&](int k, const C& xk, const C& xm) {
@@ -483,9 +535,9 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
       scatter(N / 2, a0, a1);
     }
   }
-  if (A.line_len > N && A.in != A.out) {
+  if (A.line_len > N && (SPLIT || A.in != A.out)) {
     for (int i = N + t; i < A.line_len; i += TPL) {
-      const C x = r2_load<T, YMODE>(A.in, loc, A.in_es, i);
+      const C x = get(i);
       r2_store<T, YMODE>(A.out, loc, A.out_es, i, x.x, x.y);
     }
   }

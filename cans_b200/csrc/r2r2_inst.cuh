@@ -1,5 +1,5 @@
 // Instantiation table + launcher of the two-for-one transforms (r2r2.cuh).
-// One translation unit per (precision, mode) includes this header and explicitly
+// One translation unit per (precision, mode, split) includes this header and explicitly
 // instantiates r2r2_run / r2r2_query, so the four units compile in parallel.
 #pragma once
 #include "r2r2.cuh"
@@ -34,7 +34,7 @@ namespace cb {
   X(384, 0, 32, 8, 1, 12, 4, 4, 2)    \
   X(768, 0, 64, 4, 3, 12, 4, 4, 4)
 
-template <class T, class Cfg, bool YMODE>
+template <class T, class Cfg, bool YMODE, bool SPLIT>
 static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
   using Lay = R2Lay<T, Cfg, YMODE>;
   const size_t smem = Lay::smem_bytes();
@@ -48,7 +48,7 @@ static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
   if (grid > 0x7fffffffLL) return -2;
   static bool attr_fwd = false, attr_bwd = false;
   if (fwd) {
-    auto k = r2r2_fwd_kernel<T, Cfg, YMODE>;
+    auto k = r2r2_fwd_kernel<T, Cfg, YMODE, SPLIT>;
     if (!attr_fwd) {
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
       cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -56,7 +56,7 @@ static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
     }
     k<<<(unsigned)grid, Cfg::TPL * Cfg::G, smem, st>>>(A);
   } else {
-    auto k = r2r2_bwd_kernel<T, Cfg, YMODE>;
+    auto k = r2r2_bwd_kernel<T, Cfg, YMODE, SPLIT>;
     if (!attr_bwd) {
       if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
       cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -68,9 +68,9 @@ static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
 }
 
 // 0 = launched, 1 = no instantiation for this length, < 0 = error
-template <class T, bool YMODE> int r2r2_run(const R2Args<T>& A, int n, int var, bool fwd, cudaStream_t st) {
+template <class T, bool YMODE, bool SPLIT> int r2r2_run(const R2Args<T>& A, int n, int var, bool fwd, cudaStream_t st) {
 #define CB_R2_CASE(N_, V_, TPL_, G_, MB_, R0_, R1_, R2_, R3_) \
-  case N_ * 4 + V_: return r2r2_launch<T, R2Cfg<N_, TPL_, G_, MB_, R0_, R1_, R2_, R3_>, YMODE>(A, fwd, st);
+  case N_ * 4 + V_: return r2r2_launch<T, R2Cfg<N_, TPL_, G_, MB_, R0_, R1_, R2_, R3_>, YMODE, SPLIT>(A, fwd, st);
   if constexpr (YMODE) {
     switch (n * 4 + var) { CB_R2_Y_CONFIGS(CB_R2_CASE) default: return 1; }
   } else {

@@ -1,6 +1,5 @@
 // explicit instantiation: two-for-one transforms, float, x mode (see r2r2_inst.cuh)
 #include "r2r2_inst.cuh"
 namespace cb {
-template int r2r2_run<float, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
-
+template int r2r2_run<float, false, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
 }  // namespace cb

@@ -33,6 +33,8 @@ template <class T> struct ThomasDev {
   long long sj, sk;   // field strides: p[k*sk + j*sj + i]
   const T* a; const T* b; const T* c;  // device, length >= n
   const T* lam; long long lam_sj;      // lambdaxy[j*lam_sj + i]
+  T* const* out_rows; // distributed solve: row k of the result goes to out_rows[k][column] (a peer-mapped pointer);
+                      // nullptr = in place
   int xb, xn;         // column window of this launch: i in [xb, xb + xn) for every j (thomas_reg_kernel)
   int m;              // rows per chunk of the chunked substitution = ceil(nn/32)
   int chunk_layout;   // 0: z[k][j][i]   1: z[((j*nx+i)*m + r)*32 + lane], k = lane*m + r
@@ -469,7 +471,8 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
           const T pnn = p[(long long)nn * sk + col];
           const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[CB_TH_COLS + c]));
           pcl = (den == T(0)) ? T(0) : div_rn(num, den);
-          p[(long long)nn * sk + col] = pcl;
+          if (D.out_rows) D.out_rows[nn][col] = pcl;
+          else p[(long long)nn * sk + col] = pcl;
         }
         sP[c] = pcl;
       }
@@ -480,7 +483,12 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       for (int r = 0; r < MMAX; ++r)
         if (r < nrow) y[r] = fma(p2c[r * ncol], pcl, y[r]);
     }
-    {
+    if (D.out_rows) {
+      T* const* rows = D.out_rows + k0;
+#pragma unroll
+      for (int r = 0; r < MMAX; ++r)
+        if (r < nrow) rows[r][col] = y[r];
+    } else {
       T* pc = p + (long long)k0 * sk + col;
       if (nrow == m) {
 #pragma unroll

@@ -60,13 +60,16 @@ def _stream_ptr(stream=None) -> int:
 
 
 class Context:
-    """cansb200_ctx: replaces initmpi's decomposition setup + workspaces (single rank: dims = [1,1])."""
+    """cansb200_ctx: replaces initmpi's decomposition setup + workspaces.  One rank: dims = [1, 1];
+    several ranks (one per GPU of a box): dims = [1, nranks], z slabs, followed by `connect()`."""
 
-    def __init__(self, ng: Sequence[int], is_fp32: bool = False, dims=(1, 1), ipencil_axis: int = 1, rank: int = 0,
+    def __init__(self, ng: Sequence[int], is_fp32: bool = False, dims=None, ipencil_axis: int = 1, rank: int = 0,
                  nranks: int = 1, nccl_id: Optional[bytes] = None):
         self.ng = [int(v) for v in ng]
         self.is_fp32 = bool(is_fp32)
         self.dtype = np.float32 if is_fp32 else np.float64
+        self.rank, self.nranks = int(rank), int(nranks)
+        dims = (1, self.nranks) if dims is None else dims
         self._h = C.c_void_p()
         idp = C.cast(C.c_char_p(nccl_id), C.c_void_p) if nccl_id else None
         check(lib.cansb200_init(C.byref(self._h), i3(self.ng), i3(dims), ipencil_axis, rank, nranks, idp, int(is_fp32)),
@@ -74,6 +77,27 @@ class Context:
         n, lo, nz, loz = i3([0] * 3), i3([0] * 3), i3([0] * 3), i3([0] * 3)
         check(lib.cansb200_get_extents(self._h, n, lo, nz, loz), "get_extents")
         self.n, self.lo, self.n_z, self.lo_z = list(n), list(lo), list(nz), list(loz)
+
+    def connect(self, group=None):
+        """Rendezvous of the ranks of one box: gather every rank's IPC blob (torch.distributed plays the role
+        MPI_Allgather has in a Fortran host) and map the peers' exchange regions."""
+        if self.nranks < 2:
+            return
+        import torch.distributed as dist
+        nb = lib.cansb200_dist_blob_size()
+        mine = (C.c_ubyte * nb)()
+        check(lib.cansb200_dist_export(self._h, mine), "dist_export")
+        blobs = [None] * self.nranks
+        dist.all_gather_object(blobs, bytes(mine), group=group)
+        allb = b"".join(blobs)
+        buf = (C.c_ubyte * len(allb)).from_buffer_copy(allb)
+        check(lib.cansb200_dist_connect(self._h, buf), "dist_connect")
+        dist.barrier(group=group)
+
+    def dist_status(self) -> int:
+        st = C.c_int()
+        check(lib.cansb200_dist_status(self._h, C.byref(st)), "dist_status")
+        return int(st.value)
 
     @property
     def handle(self):
@@ -254,6 +278,9 @@ def initsolver(ctx: Context, ng, dli, dzci_g, dzfi_g, cbc, bc, c_or_f, device=No
     dzfi_g = np.asarray(dzfi_g, dtype=dt)
     lx = eigenvalues(ng[0], cbc[0], c_or_f[0], dt) * dli[0] ** 2
     ly = eigenvalues(ng[1], cbc[1], c_or_f[1], dt) * dli[1] ** 2
+    # lambdaxy(lo_z(1):hi_z(1), lo_z(2):hi_z(2)): the z-pencil slice of this rank (src/initsolver.f90:54-58)
+    y0 = ctx.lo_z[1] - 1
+    ly = ly[y0:y0 + ctx.n_z[1]]
     lambdaxy = np.ascontiguousarray((lx[None, :] + ly[:, None]).astype(dt))
     a, b, c = tridmatrix(cbc[2], ng[2], dzci_g, dzfi_g, c_or_f[2], dt)
     dl = [dt(1.0) / v for v in dli]

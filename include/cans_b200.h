@@ -53,12 +53,24 @@ typedef struct cansb200_options {
 
 /* -- context: replaces initmpi's cuDecomp setup (src/initmpi.f90:84-146), common_cudecomp.f90
  *    and workspaces.f90's init_wspace_arrays.  ng = global grid, dims = processor grid
- *    (only dims = [1, nranks], z slabs / x pencils, is implemented), nccl_id = 128-byte
- *    ncclUniqueId broadcast by the host (cuDecomp does the same: cudecomp.cc:65-69) or
- *    NULL when nranks == 1. */
+ *    (only dims = [1, nranks], z slabs / x pencils, is implemented).  nccl_id is accepted for signature
+ *    parity with cuDecomp's rendezvous (cudecomp.cc:65-69) and ignored: the exchange uses CUDA IPC peer
+ *    mappings, see cansb200_dist_export / cansb200_dist_connect below. */
 int cansb200_init(cansb200_ctx** ctx, const int ng[3], const int dims[2], int ipencil_axis,
                   int rank, int nranks, const void* nccl_id, int is_fp32);
 int cansb200_finalize(cansb200_ctx* ctx);
+
+/* -- multi-GPU rendezvous (one rank per GPU, all on one NVLink box).  The transposes of the reference
+ *    (cudecompTranspose{YtoZ,ZtoY}: src/solver_gpu.f90:157,167) are peer-mapped stores issued by the
+ *    producing kernels, so each rank must map its peers' exchange regions once:
+ *      1. every rank calls cansb200_dist_export into a blob of cansb200_dist_blob_size() bytes,
+ *      2. the host gathers the blobs of all ranks in rank order (MPI_Allgather / torch.distributed),
+ *      3. every rank calls cansb200_dist_connect with the gathered array.
+ *    cansb200_dist_status returns non-zero if a device-side barrier ever timed out (a rank went missing). */
+int cansb200_dist_blob_size(void);
+int cansb200_dist_export(cansb200_ctx* ctx, void* blob);
+int cansb200_dist_connect(cansb200_ctx* ctx, const void* blobs);
+int cansb200_dist_status(cansb200_ctx* ctx, int* status);
 
 /* local extents of this rank: n = x-pencil (nx, ny, nz/P) as main.f90 sees it, lo_z / n_z =
  * z-pencil (nx, ny/P, nz) that lambdaxy is indexed by (src/initsolver.f90:54-58). 1-based lo. */

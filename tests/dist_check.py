@@ -1,0 +1,92 @@
+"""Distributed (z-slab) solve against the single-rank oracle.  Launched by tests/test_gpu_dist.py as
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/dist_check.py
+
+Every rank solves its slab of the same global problem through the C ABI (peer-mapped exchange over
+NVLink) and compares it with the oracle's global solution.  Prints `DIST_OK <max err>` on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+import cans_b200 as cb  # noqa: E402
+from cans_b200.decomp import SlabDecomp  # noqa: E402
+
+P, N = ["P", "P"], ["N", "N"]
+C3 = ["c"] * 3
+# name -> (ng, l, cbc, c_or_f, gr, dtype, helmholtz)
+DIST_CASES = {
+    "chan_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),
+    "tgv_64x128x64": ([64, 128, 64], [6.2832] * 3, [P, P, P], C3, 0.0, np.float64, False),
+    "duct_128x64x96": ([128, 64, 96], [6.0, 2.0, 2.0], [P, N, N], C3, 1.5, np.float64, False),
+    "uneven_64x64x70": ([64, 64, 70], [1.0, 1.0, 1.0], [N, P, ["D", "D"]], C3, 1.0, np.float64, False),
+    "helm_w_64x64x64": ([64, 64, 64], [1.0, 1.0, 1.0], [P, P, ["D", "D"]], ["c", "c", "f"], 1.0, np.float64, True),
+    "fp32_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float32, False),
+}
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("gloo")
+    from oracle import cans_oracle as O
+    worst = 0.0
+    for name, (ng, l, cbc, cf, gr, dt, helm) in DIST_CASES.items():
+        cs = O.make_case(ng, l, cbc, c_or_f=cf, gr=gr, dtype=dt)
+        p = cases.make_rhs(cs)
+        ref = p.copy()
+        if helm:
+            O.solve_helmholtz(ng, ng, cs["arrplan"], cs["normfft"], cases.ALPHA, cs["lambdaxy"], cs["a"], cs["b"], cs["c"],
+                              None, None, None, cbc, cf, ref)
+        else:
+            O.solver(ng, ng, cs["arrplan"], cs["normfft"], cs["lambdaxy"], cs["a"], cs["b"], cs["c"], cbc, cf, ref)
+        ctx = cb.Context(ng, is_fp32=dt == np.float32, rank=rank, nranks=world)
+        dec = SlabDecomp(ng, world, rank)
+        assert ctx.n == dec.n and ctx.lo == dec.lo and ctx.n_z == dec.n_z and ctx.lo_z == dec.lo_z, (ctx.n, dec.n)
+        ctx.connect()
+        sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], cf, device=dev)
+        z0, z1 = dec.z_range()
+        pl = np.zeros((z1 - z0 + 2, ng[1] + 2, ng[0] + 2), dtype=dt)
+        pl[1:-1] = p[1 + z0:1 + z1]
+        pd = torch.from_numpy(pl).to(dev)
+        for rep in range(3):   # repeated solves exercise buffer reuse across the device-side barriers
+            pd.copy_(torch.from_numpy(pl))
+            if helm:
+                cb.solve_helmholtz(ctx.n, ng, sd.arrplan, sd.normfft, cases.ALPHA, sd.lambdaxy, sd.a, sd.b, sd.c, None, None,
+                                   None, cbc, cf, pd)
+            else:
+                cb.solver(ctx.n, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, pd)
+        torch.cuda.synchronize()
+        assert ctx.dist_status() == 0, "a device-side barrier timed out"
+        got = pd.cpu().numpy()
+        # parity metric on the GLOBAL field: gather the slabs (the null-space rule needs the global mean)
+        parts = [None] * world
+        dist.all_gather_object(parts, got[1:-1, 1:-1, 1:-1])
+        full = np.concatenate(parts, axis=0)
+        err = cases.parity_error(cs, full, ref[1:-1, 1:-1, 1:-1], helm)
+        tol = 1e-12 if dt == np.float64 else 1e-5
+        if rank == 0:
+            print(f"{name}: rel L2 = {err:.3e}", flush=True)
+        assert err < tol, f"{name}: {err}"
+        worst = max(worst, err / tol)
+        halo = np.ones(got.shape, bool)
+        halo[1:-1, 1:-1, 1:-1] = False
+        assert np.array_equal(got[halo], pl[halo]), "halo cells were modified"
+        dist.barrier()
+        sd.arrplan.destroy()
+        ctx.close()
+    if rank == 0:
+        print(f"DIST_OK {worst:.3e}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
