@@ -212,22 +212,32 @@ def main():
     from cans_b200 import gridgen
     dzc, dzf = gridgen.initgrid(1, ng[2], gr, l[2], per_z)
     dli = [ng[0] / l[0], ng[1] / l[1], ng[2] / l[2]]
-    ctx = cb.Context(ng)
+    # N > 1: ONE global grid, z slabs over the N GPUs of the box (strong scaling, BASELINE.json "1/2/4/8 B200")
+    ctx = cb.Context(ng, rank=rank, nranks=world)
+    ctx.connect()
     ctx.set_variant(args.x_variant, args.y_variant)
     ctx.set_chain(args.chain_cols, args.chain_streams)
     sd = cb.initsolver(ctx, ng, dli, 1.0 / dzc, 1.0 / dzf, cbc, [[0.0, 0.0]] * 3, cf, device=dev,
                        thomas_variant=args.thomas, fft_x_lines=args.fft_x_lines, fft_y_lines=args.fft_y_lines)
-    shp = (ng[2] + 2, ng[1] + 2, ng[0] + 2)
-    npts = ng[0] * ng[1] * ng[2]
+    nl = ctx.n                      # local x pencil (nx, ny, nz / N)
+    shp = (nl[2] + 2, nl[1] + 2, nl[0] + 2)
+    npts = ng[0] * ng[1] * ng[2]    # global points
+    npts_local = nl[0] * nl[1] * nl[2]
     p = torch.empty(shp, dtype=torch.float64, device=dev)
-    S.fill_hash(ctx, p, ng, [1, 1, 1], 1, 123 + rank)
+    S.fill_hash(ctx, p, nl, ctx.lo, 1, 123)   # hash of the GLOBAL index: every decomposition sees the same field
     I = (slice(1, -1),) * 3
     if all(b[0] in "PN" for b in cbc):
-        wz = torch.from_numpy(dzf[1:-1]).to(dev)[:, None, None]
-        p[I] -= (p[I] * wz).sum() / (wz.sum() * ng[0] * ng[1])
+        z0 = ctx.lo[2] - 1
+        wz = torch.from_numpy(dzf[1 + z0:1 + z0 + nl[2]]).to(dev)[:, None, None]
+        num = (p[I] * wz).sum()
+        den = wz.sum() * ng[0] * ng[1]
+        if world > 1:
+            dist.all_reduce(num)
+            dist.all_reduce(den)
+        p[I] -= num / den
 
     def step():
-        cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, p)
+        cb.solver(nl, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, p)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -258,7 +268,8 @@ def main():
         ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     assert bool(torch.isfinite(p[I]).all()), "solution is not finite"
-    total_pts = npts * world  # replicas: every rank solves its own full grid
+    assert ctx.dist_status() == 0, "a device-side barrier timed out"
+    total_pts = npts  # one global grid, whatever N
     value = ms_per_step * 1e6 / total_pts
 
     # ---- per-stage device times (live, CUDA events on the solve's stream) -> roofline of the dominant kernel
@@ -271,7 +282,14 @@ def main():
     peak, peak_src = measured_peaks()
     heavy = {k: v for k, v in stage_ms.items() if k != "pivot_cache"}
     dom = max(heavy, key=heavy.get)
-    stage_bytes = STAGE_BYTES_PER_POINT_FP64 * npts
+    if world > 1:   # max over ranks of every stage time
+        keys = sorted(stage_ms)
+        t = torch.tensor([stage_ms[k] for k in keys], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stage_ms = {k: float(v) for k, v in zip(keys, t.tolist())}
+        heavy = {k: v for k, v in stage_ms.items() if k != "pivot_cache"}
+        dom = max(heavy, key=heavy.get)
+    stage_bytes = STAGE_BYTES_PER_POINT_FP64 * npts_local   # per GPU: each rank's launch covers its local points
     achieved = stage_bytes / (stage_ms[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -283,9 +301,17 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes,
                 "stage_ms": stage_ms,
-                "solve": {"algorithmic_bytes": ALGO_BYTES_PER_POINT_FP64 * npts,
-                          "achieved": ALGO_BYTES_PER_POINT_FP64 * npts / (ms_per_step * 1e-3) / 1e9,
-                          "frac": ALGO_BYTES_PER_POINT_FP64 * npts / (ms_per_step * 1e-3) / 1e9 / peak}}
+                "solve": {"algorithmic_bytes_per_gpu": ALGO_BYTES_PER_POINT_FP64 * npts_local,
+                          "achieved": ALGO_BYTES_PER_POINT_FP64 * npts_local / (ms_per_step * 1e-3) / 1e9,
+                          "frac": ALGO_BYTES_PER_POINT_FP64 * npts_local / (ms_per_step * 1e-3) / 1e9 / peak}}
+    if world > 1:
+        # two exchanges per solve, each sends (P-1)/P of the local field per GPU per direction
+        nvb = 2.0 * (world - 1) / world * npts_local * 8.0
+        roofline["nvlink"] = {"bytes_per_gpu_per_direction_per_solve": nvb, "peak_GBs": 770.0,
+                              "peak_source": "B200_PROFILING.md measured peer copy (900 nominal)",
+                              "floor_ms": nvb / 770e9 * 1e3,
+                              "note": "peer stores are issued by the y-transform and tridiagonal kernels themselves; "
+                                      "their stage times above include the wire time"}
 
     # ---- e2e: the host-memory API (mode A of SURVEY 8b): pinned host p, H2D + solve + D2H per step
     e2e = None
@@ -296,19 +322,20 @@ def main():
         pn = ph.numpy()
         hs = sd.host
         ne2e = max(1, min(args.steps, 5))
-        cb.solver(ng, ng, sd.arrplan, sd.normfft, hs["lambdaxy"], hs["a"], hs["b"], hs["c"], cbc, cf, pn)  # warm-up
+        cb.solver(nl, ng, sd.arrplan, sd.normfft, hs["lambdaxy"], hs["a"], hs["b"], hs["c"], cbc, cf, pn)  # warm-up
         sync_all()
         t0 = time.perf_counter()
         for _ in range(ne2e):
-            cb.solver(ng, ng, sd.arrplan, sd.normfft, hs["lambdaxy"], hs["a"], hs["b"], hs["c"], cbc, cf, pn)
+            cb.solver(nl, ng, sd.arrplan, sd.normfft, hs["lambdaxy"], hs["a"], hs["b"], hs["c"], cbc, cf, pn)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([el], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
-        e2e = {"value": el / ne2e * 1e9 / total_pts, "unit": UNIT, "h2d_bytes_per_step": nb + 8 * (3 * ng[2] + ng[0] * ng[1]),
-               "d2h_bytes_per_step": nb, "steps": ne2e, "ms_per_step": el / ne2e * 1e3}
+        e2e = {"value": el / ne2e * 1e9 / total_pts, "unit": UNIT,
+               "h2d_bytes_per_step": (nb + 8 * (3 * ng[2] + ctx.n_z[0] * ctx.n_z[1])) * world,
+               "d2h_bytes_per_step": nb * world, "steps": ne2e, "ms_per_step": el / ne2e * 1e3}
         del ph
 
     cpu = None
@@ -319,10 +346,11 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak" if world > 1 else "strong",
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "grid": ng, "bc": "".join(b[0] + b[1] for b in cbc), "gr": gr,
-                       "decomposition": "single GPU" if world == 1 else f"{world} independent replicas (distributed solve: see DESIGN.md)",
+                       "decomposition": "single GPU" if world == 1 else f"z slabs over {world} GPUs (x pencils, dims=[1,{world}]), "
+                                        "transposes = peer-mapped stores over NVLink",
                        "l2": "inputs (2.15 GB/field) larger than L2, no flush", "solves_per_s": 1e3 / ms_per_step * world,
                        "thomas_variant": int(sd.arrplan.stats()["thomas_variant"])},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -12,11 +12,11 @@ namespace cb {
   X(64, 0, 4, 32, 1, 16, 4, 1, 1)     \
   X(128, 0, 8, 16, 1, 16, 8, 1, 1)    \
   X(256, 0, 16, 8, 1, 16, 16, 1, 1)   \
-  X(512, 0, 32, 8, 2, 16, 8, 4, 1)    \
-  X(512, 1, 64, 4, 4, 8, 8, 8, 1)     \
-  X(1024, 0, 64, 4, 3, 16, 8, 8, 1)   \
+  X(512, 0, 64, 4, 4, 8, 8, 8, 1)     \
+  X(512, 1, 32, 8, 2, 16, 8, 4, 1)    \
+  X(1024, 0, 64, 2, 5, 16, 8, 8, 1)   \
   X(1024, 1, 128, 2, 4, 8, 8, 4, 4)   \
-  X(1024, 2, 64, 2, 5, 16, 8, 8, 1)   \
+  X(1024, 2, 64, 4, 3, 16, 8, 8, 1)   \
   X(2048, 0, 128, 2, 1, 16, 16, 8, 1) \
   X(384, 0, 32, 8, 1, 12, 4, 4, 2)    \
   X(768, 0, 64, 4, 1, 12, 4, 4, 4)
@@ -25,8 +25,8 @@ namespace cb {
   X(64, 0, 4, 8, 1, 16, 4, 1, 1)      \
   X(128, 0, 8, 8, 1, 16, 8, 1, 1)     \
   X(256, 0, 16, 8, 1, 16, 16, 1, 1)   \
-  X(512, 0, 32, 8, 3, 16, 8, 4, 1)    \
-  X(512, 1, 64, 8, 2, 8, 8, 8, 1)     \
+  X(512, 0, 64, 8, 2, 8, 8, 8, 1)     \
+  X(512, 1, 32, 8, 3, 16, 8, 4, 1)    \
   X(512, 2, 64, 4, 4, 8, 8, 8, 1)     \
   X(1024, 0, 64, 8, 1, 16, 8, 8, 1)   \
   X(1024, 1, 128, 4, 2, 8, 8, 4, 4)   \
