@@ -4,13 +4,17 @@ THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only `tests/`,
 `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
 `bench.py` may import it.  The product path (`cans_b200`) never does.
 
-Parity status: the reference cannot be built in this image (no gfortran / MPI /
-FFTW3), and the reference holds no stored single-solve vectors.  The oracle is
-pinned by (a) the reference's own in-binary self-test properties
-(`src/sanity.f90:206-409`: post-correction divergence < `small`, Helmholtz
-residual < `small`), see `tests/test_oracle.py`, and (b) a replay of the
-reference's only golden vector, `tests/lid_driven_cavity/data_ldc_re1000.txt`,
-through `oracle/ldc_replay.py` (see that file's header for its status).
+Parity status: PINNED by the reference's only stored result.  The reference cannot be built in
+this image (no gfortran / MPI / FFTW3) and holds no stored single-solve vectors, but its regression
+vector `tests/lid_driven_cavity/data_ldc_re1000.txt` (64 FP64 values after 1500 time steps = 4500 calls of
+`solver`, compared at rtol = 1e-7 by `tests/lid_driven_cavity/test.py:8`) is reproduced by
+`oracle/ldc_replay.py` -- the explicit CaNS time loop restated around THIS file's `solver` -- to
+3.6e-8 relative, i.e. to the 8 printed digits (`tests/test_ldc_golden.py`; the same replay with the CUDA
+solver: `tests/test_gpu_ldc.py`).  That pins R2HC/HC2R, REDFT10/01 and gaussel (Neumann-Neumann, with the
+singular-pivot pin).  The kinds the golden case does not reach (RODFT*, REDFT00/11, periodic z, stretched z,
+Helmholtz) are pinned by the reference's in-binary self-test properties (`src/sanity.f90:206-409`:
+post-correction divergence < `small`, Helmholtz residual < `small`; `tests/test_oracle.py`) and by
+brute-force evaluation of FFTW's published r2r definitions.
 
 Third-party arithmetic: FFTW3 (system package, version unpinned by the
 reference: `.github/actions/build/scripts/install-GNU.sh:5`).  Its r2r kinds
