@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--thomas", type=int, default=-1)
     ap.add_argument("--fft-x-lines", type=int, default=-1)
     ap.add_argument("--fft-y-lines", type=int, default=-1)
+    ap.add_argument("--r2-flags", type=int, default=-1)
     ap.add_argument("--x-variant", type=int, default=0)
     ap.add_argument("--y-variant", type=int, default=0)
     ap.add_argument("--chain-cols", type=int, default=0)
@@ -216,6 +217,8 @@ def main():
     ctx = cb.Context(ng, rank=rank, nranks=world)
     ctx.connect()
     ctx.set_variant(args.x_variant, args.y_variant)
+    if args.r2_flags >= 0:
+        ctx.set_r2_flags(args.r2_flags)
     ctx.set_chain(args.chain_cols, args.chain_streams)
     sd = cb.initsolver(ctx, ng, dli, 1.0 / dzc, 1.0 / dzf, cbc, [[0.0, 0.0]] * 3, cf, device=dev,
                        thomas_variant=args.thomas, fft_x_lines=args.fft_x_lines, fft_y_lines=args.fft_y_lines)

@@ -29,10 +29,12 @@ extern template int r2r2_run<float, false, false>(const R2Args<float>&, int, int
 extern template int r2r2_run<float, true, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
 extern template int r2r2_run<double, true, true>(const R2Args<double>&, int, int, bool, cudaStream_t);
 extern template int r2r2_run<float, true, true>(const R2Args<float>&, int, int, bool, cudaStream_t);
+extern int g_r2_default_carveout;   // 1: do not force the maximum shared-memory carveout (capi.cu owns it)
 extern template int r2r2_query<false>(int, int, int[4]);
 extern template int r2r2_query<true>(int, int, int[4]);
 }  // namespace cb
 
+namespace cb { int g_r2_default_carveout = 1; }
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -97,6 +99,7 @@ struct cansb200_ctx {
   std::map<int, R2Tables<float>> r2tabs32;
   int force_generic = 0;                       // tests: route every transform through the generic engine
   int r2_variant[2] = {0, 0};                  // tuning variant of the fast path, [x, y]
+  int r2_flags = 0;                            // cache hints of the fast path (CANSB200_CTX_R2_FLAGS)
   // ---- z-slab decomposition over the GPUs of one box (dims = [1, P]); see dist_kernels.cuh
   std::vector<int> ys, zs;                     // split starts of y and z, size P + 1
   void* region = nullptr;                      // IPC-exported: [flags][C = z pencil][XB = way-back buffer]
@@ -138,7 +141,7 @@ struct cansb200_plan {
   int q, periodic_z;
   cansb200_options opt;
   // thomas
-  int th_n, th_nn, th_m, th_variant, th_mmax, nslots;
+  int th_n, th_nn, th_m, th_variant, th_mmax, th_cols, nslots;
   long long slot_z, slot_den;
   DevBuf zcache, p2cache, dencache, state;
   unsigned long long solves = 0;
@@ -278,6 +281,8 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
       for (int s = 0; s < 4; ++s) A.tw[s] = rt->tw[s];
       A.mak = rt->mak;
       A.row_tab = (const R2Row<T>*)g.row_tab;
+      A.flags = ctx->r2_flags & 3;
+      cb::g_r2_default_carveout = (ctx->r2_flags & 4) ? 0 : 1;
       const int rc = !g.ymode ? r2r2_run<T, false, false>(A, nt, var, kind_is_forward(kind), st)
                      : g.row_tab ? r2r2_run<T, true, true>(A, nt, var, kind_is_forward(kind), st)
                                  : r2r2_run<T, true, false>(A, nt, var, kind_is_forward(kind), st);
@@ -363,22 +368,30 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   return D;
 }
 
-template <class T, int MMAX, bool EXACT, bool VEC>
+template <class T, int MMAX, bool EXACT, bool VEC, int COLS>
 static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, cudaStream_t st) {
-  auto kfn = thomas_pipe_kernel<T, MMAX, EXACT, VEC>;
-  const size_t smem = thomas_pipe_smem<T, MMAX>();
+  auto kfn = thomas_pipe_kernel<T, MMAX, EXACT, VEC, COLS>;
+  const size_t smem = thomas_pipe_smem<T, MMAX, COLS>();
   static bool attr = false;
   if (!attr) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const long long tiles = (long long)((D.xn + CB_TH_COLS - 1) / CB_TH_COLS) * D.ny;
+  const long long tiles = (long long)((D.xn + COLS - 1) / COLS) * D.ny;
   const unsigned grid = (unsigned)(tiles < ctx->num_sms ? tiles : ctx->num_sms);   // persistent: one CTA per SM
   kfn<<<grid, CB_TH_THREADS, smem, st>>>(D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
                                          (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
+}
+
+template <class T, int MMAX, int COLS>
+static int launch_pipe_sel(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, bool exact, bool vec,
+                           cudaStream_t st) {
+  if (exact && vec) return launch_pipe<T, MMAX, true, true, COLS>(ctx, D, pl, p, norm, st);
+  if (vec) return launch_pipe<T, MMAX, false, true, COLS>(ctx, D, pl, p, norm, st);
+  return launch_pipe<T, MMAX, false, false, COLS>(ctx, D, pl, p, norm, st);
 }
 
 // pivot cache: content hash of (a, b, c, lambda) -> slot select -> factorisation on a miss
@@ -408,15 +421,12 @@ template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T
     const bool vec = (D.nx % vw) == 0 && (D.xb % vw) == 0 && (D.sk % vw) == 0 && ((uintptr_t)p % 16) == 0 &&
                      ((uintptr_t)pl->zcache.p % 16) == 0 && (pl->slot_z % vw) == 0 && (D.xn % vw) == 0;
     const bool exact = D.m == pl->th_mmax;
-    if (pl->th_mmax == 4) {
-      if (exact && vec) return launch_pipe<T, 4, true, true>(ctx, D, pl, p, norm, st);
-      if (vec) return launch_pipe<T, 4, false, true>(ctx, D, pl, p, norm, st);
-      return launch_pipe<T, 4, false, false>(ctx, D, pl, p, norm, st);
-    }
-    if (pl->th_mmax == 8) {
-      if (exact && vec) return launch_pipe<T, 8, true, true>(ctx, D, pl, p, norm, st);
-      if (vec) return launch_pipe<T, 8, false, true>(ctx, D, pl, p, norm, st);
-      return launch_pipe<T, 8, false, false>(ctx, D, pl, p, norm, st);
+    if (pl->th_cols == 16) {
+      if (pl->th_mmax == 4) return launch_pipe_sel<T, 4, 16>(ctx, D, pl, p, norm, exact, vec, st);
+      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16>(ctx, D, pl, p, norm, exact, vec, st);
+    } else if (pl->th_cols == 8) {
+      if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 8>(ctx, D, pl, p, norm, exact, vec, st);
+      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 8>(ctx, D, pl, p, norm, exact, vec, st);
     }
     return fail(CANSB200_EUNSUPPORTED, "gaussel: no pipelined kernel for this chunk length");
   }
@@ -658,6 +668,11 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
     c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
     return 0;
   }
+  if (what == CANSB200_CTX_R2_FLAGS) {
+    if (value < 0 || value > 7) return fail(CANSB200_EINVAL, "ctx_set: r2 flags must be 0..7");
+    c->r2_flags = value;
+    return 0;
+  }
   return fail(CANSB200_EINVAL, "ctx_set: unknown switch");
 }
 
@@ -704,11 +719,14 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   pl->th_n = ctx->ng[2] - pl->q;
   pl->th_nn = pl->periodic_z ? pl->th_n - 1 : pl->th_n;
   if (pl->th_nn < 1) return fail(CANSB200_EINVAL, "plan_create: z system is empty");
-  pl->th_m = (pl->th_nn + CB_TH_CHUNKS - 1) / CB_TH_CHUNKS;
+  // pipelined substitution: 16 columns x 64 chunks up to 512 rows, 8 columns x 128 chunks up to 1024 rows
+  pl->th_cols = pl->th_nn <= 512 ? 16 : 8;
+  const int chunks = CB_TH_THREADS / pl->th_cols;
+  pl->th_m = (pl->th_nn + chunks - 1) / chunks;
   int variant = o.thomas_variant >= 0 ? o.thomas_variant : 1;
-  if (pl->th_m > 8) variant = 0;   // nz > 512: the sequential kernel (a wider pipelined tile is future work)
+  if (pl->th_m > 8) variant = 0;   // nz > 1024: the sequential kernel
   pl->th_variant = variant;
-  pl->th_mmax = pl->th_m <= 4 ? 4 : 8;
+  pl->th_mmax = pl->th_cols == 16 ? (pl->th_m <= 4 ? 4 : 8) : (pl->th_m <= 6 ? 6 : 8);
   pl->nslots = o.cache_slots >= 1 ? (o.cache_slots > CB_MAX_SLOTS ? CB_MAX_SLOTS : o.cache_slots) : 1;
   const long long ncol = (long long)ctx->n_z[0] * ctx->n_z[1];
   pl->slot_z = ncol * pl->th_nn;

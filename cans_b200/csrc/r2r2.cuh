@@ -51,6 +51,35 @@ __device__ __forceinline__ Cx<float> cx_ldg(const Cx<float>* p) {
   return {v.x, v.y};
 }
 
+// field loads that bypass L1 allocation (the field is streamed once; L1 is left to the twiddle tables) and
+// streaming (evict-first) stores
+__device__ __forceinline__ double ld_na(const double* p) {
+  double v;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_na(const float* p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ Cx<double> ld_na(const Cx<double>* p) {
+  Cx<double> v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ Cx<float> ld_na(const Cx<float>* p) {
+  Cx<float> v;
+  asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_cs(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_cs(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_cs(Cx<double>* p, Cx<double> v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+__device__ __forceinline__ void st_cs(Cx<float>* p, Cx<float> v) { __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y)); }
+#define CB_R2_LD_NA 1   // R2Args::flags
+#define CB_R2_ST_CS 2
+
 // ---- register butterflies: forward sign, natural in, natural out --------------------------------
 template <class T> __device__ __forceinline__ void bf2(Cx<T>* a) {
   const Cx<T> t = a[0];
@@ -210,6 +239,7 @@ template <class T> struct R2Args {
   const Cx<T>* tw[4];        // per stage s: (R_s - 1) * L_s entries, w_{Ns}^{o r} at [(r-1) L + o]
   const Cx<T>* mak;          // (cos, sin)(pi k / (2N)), k = 0..N/2
   const R2Row<T>* row_tab;   // SPLIT kernels: where each output (forward) / input (backward) row lives
+  int flags;                 // CB_R2_LD_NA | CB_R2_ST_CS
 };
 
 template <class T, class Cfg, bool YMODE> struct R2Lay {
@@ -227,6 +257,10 @@ template <int ID, int CNT> __device__ __forceinline__ void r2_named_bar() {
 }
 // barrier among the TPL threads of one transform.  Barrier ids are compile-time constants so that
 // ptxas reserves G + 1 hardware barriers per CTA, not all 16 (which would cap the CTAs per SM at 4).
+// does r2_group_sync involve only the threads of one transform (so that a whole transform may exit early)?
+template <class Cfg> __host__ __device__ constexpr bool r2_group_local() {
+  return Cfg::G == 1 || (Cfg::TPL <= 32 && (32 % Cfg::TPL) == 0) || ((Cfg::TPL % 32) == 0 && Cfg::G <= 8);
+}
 template <class Cfg, bool YMODE> __device__ __forceinline__ void r2_group_sync(int c) {
   if (YMODE || Cfg::G == 1) __syncthreads();
   else if (Cfg::TPL <= 32 && (32 % Cfg::TPL) == 0) __syncwarp();
@@ -277,33 +311,50 @@ __device__ __forceinline__ R2Loc<T> r2_locate(const R2Args<T>& A, int c) {
     L.ob = gb * A.out_gs + jb * A.out_ls;
     L.has_a = la < nl;
     L.has_b = lb < nl;
+    if (!L.has_b) { L.ib = L.ia; L.ob = L.oa; }   // odd line count: b aliases a, and a is stored last (r2_store)
     L.g = 0;
     L.x = 0;
   }
   return L;
 }
 
-template <class T, bool YMODE>
-__device__ __forceinline__ Cx<T> r2_load(const T* __restrict__ p, const R2Loc<T>& L, long long es, int i) {
+// FULL: every column pair of the CTA exists (y mode; the host checks it).  x mode never predicates: a transform
+// without lines exits at kernel entry, and a missing second line aliases the first (see r2_locate).
+template <class T, bool YMODE, bool FULL>
+__device__ __forceinline__ Cx<T> r2_load(const T* __restrict__ p, const R2Loc<T>& L, long long es, int i, int flags) {
   Cx<T> v;
+  const bool na = flags & CB_R2_LD_NA;
   if (YMODE) {
-    if (L.has_b) return *reinterpret_cast<const Cx<T>*>(p + L.ia + (long long)i * es);
-    v.x = L.has_a ? p[L.ia + (long long)i * es] : T(0);
+    const T* q = p + L.ia + (long long)i * es;
+    if (FULL || L.has_b) return na ? ld_na(reinterpret_cast<const Cx<T>*>(q)) : *reinterpret_cast<const Cx<T>*>(q);
+    v.x = L.has_a ? *q : T(0);
     v.y = T(0);
+  } else if (na) {
+    v.x = ld_na(p + L.ia + i);
+    v.y = ld_na(p + L.ib + i);
   } else {
-    v.x = L.has_a ? p[L.ia + i] : T(0);
-    v.y = L.has_b ? p[L.ib + i] : T(0);
+    v.x = p[L.ia + i];
+    v.y = p[L.ib + i];
   }
   return v;
 }
-template <class T, bool YMODE>
-__device__ __forceinline__ void r2_store(T* __restrict__ p, const R2Loc<T>& L, long long es, int i, T a, T b) {
+template <class T, bool YMODE, bool FULL>
+__device__ __forceinline__ void r2_store(T* __restrict__ p, const R2Loc<T>& L, long long es, int i, T a, T b, int flags) {
+  const bool cs = flags & CB_R2_ST_CS;
   if (YMODE) {
-    if (L.has_b) { *reinterpret_cast<Cx<T>*>(p + L.oa + (long long)i * es) = Cx<T>{a, b}; return; }
-    if (L.has_a) p[L.oa + (long long)i * es] = a;
+    T* q = p + L.oa + (long long)i * es;
+    if (FULL || L.has_b) {
+      if (cs) st_cs(reinterpret_cast<Cx<T>*>(q), Cx<T>{a, b});
+      else *reinterpret_cast<Cx<T>*>(q) = Cx<T>{a, b};
+      return;
+    }
+    if (L.has_a) *q = a;
+  } else if (cs) {
+    st_cs(p + L.ob + i, b);
+    st_cs(p + L.oa + i, a);
   } else {
-    if (L.has_a) p[L.oa + i] = a;
-    if (L.has_b) p[L.ob + i] = b;
+    p[L.ob + i] = b;
+    p[L.oa + i] = a;
   }
 }
 
@@ -322,21 +373,21 @@ __device__ __forceinline__ R2Row<float> r2_row(const R2Row<float>* tab, int i) {
   r.gs = v.y;
   return r;
 }
-template <class T>
+template <class T, bool FULL>
 __device__ __forceinline__ Cx<T> r2_load_split(const R2Row<T>* tab, const R2Loc<T>& L, int i) {
   const R2Row<T> e = r2_row(tab, i);
   const T* q = e.ptr + (long long)L.g * e.gs + L.x;
-  if (L.has_b) return *reinterpret_cast<const Cx<T>*>(q);
+  if (FULL || L.has_b) return *reinterpret_cast<const Cx<T>*>(q);
   Cx<T> v;
   v.x = L.has_a ? *q : T(0);
   v.y = T(0);
   return v;
 }
-template <class T>
+template <class T, bool FULL>
 __device__ __forceinline__ void r2_store_split(const R2Row<T>* tab, const R2Loc<T>& L, int i, T a, T b) {
   const R2Row<T> e = r2_row(tab, i);
   T* q = e.ptr + (long long)L.g * e.gs + L.x;
-  if (L.has_b) { *reinterpret_cast<Cx<T>*>(q) = Cx<T>{a, b}; return; }
+  if (FULL || L.has_b) { *reinterpret_cast<Cx<T>*>(q) = Cx<T>{a, b}; return; }
   if (L.has_a) *q = a;
 }
 
@@ -398,8 +449,10 @@ __device__ __forceinline__ void r2_dit_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T
 }
 
 // ---- forward kinds: R2HC, REDFT10, RODFT10 ---------------------------------------------------------
-template <class T, class Cfg, bool YMODE, bool SPLIT = false>
+template <class T, class Cfg, bool YMODE, bool SPLIT, int KIND, bool FULL>
 __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(const R2Args<T> A) {
+  static_assert(KIND == K_R2HC || KIND == K_REDFT10 || KIND == K_RODFT10, "forward kinds");
+  static_assert(YMODE || r2_group_local<Cfg>(), "x mode relies on per-transform barriers");
   static_assert(!SPLIT || YMODE, "split rows exist only for the strided (y) transforms");
   using C = Cx<T>;
   using Lay = R2Lay<T, Cfg, YMODE>;
@@ -410,12 +463,12 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
   const int c = YMODE ? tid % G : tid / TPL;
   const int t = YMODE ? tid / G : tid % TPL;
   const R2Loc<T> loc = r2_locate<T, Cfg, YMODE>(A, c);
-  const int kind = A.kind;
-  const bool trig = kind != K_R2HC;
-  const bool neg_odd = kind == K_RODFT10;
+  if (!YMODE && !loc.has_a) return;   // x mode: group barriers only (r2_group_sync), so a lineless transform may leave
+  constexpr bool trig = KIND != K_R2HC;
+  constexpr bool neg_odd = KIND == K_RODFT10;
   auto put = [&](int i, T a, T b) {
-    if (SPLIT) r2_store_split<T>(A.row_tab, loc, i, a, b);
-    else r2_store<T, YMODE>(A.out, loc, A.out_es, i, a, b);
+    if (SPLIT) r2_store_split<T, FULL>(A.row_tab, loc, i, a, b);
+    else r2_store<T, YMODE, FULL>(A.out, loc, A.out_es, i, a, b, A.flags);
   };
 
   C v[E];
@@ -427,7 +480,7 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
       for (int q = 0; q < R0; ++q) {
         const int j = q * L0 + t + TPL * m;
         const int i = r2_vperm(trig, N, j);
-        C x = r2_load<T, YMODE>(A.in, loc, A.in_es, i);
+        C x = r2_load<T, YMODE, FULL>(A.in, loc, A.in_es, i, A.flags);
         if (neg_odd && (i & 1)) x = {-x.x, -x.y};
         v[m * R0 + q] = x;
       }
@@ -435,7 +488,7 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
   // copy the untransformed tail when the result goes to another array
   if (A.line_len > N && (SPLIT || A.in != A.out)) {
     for (int i = N + t; i < A.line_len; i += TPL) {
-      const C x = r2_load<T, YMODE>(A.in, loc, A.in_es, i);
+      const C x = r2_load<T, YMODE, FULL>(A.in, loc, A.in_es, i, A.flags);
       put(i, x.x, x.y);
     }
   }
@@ -446,7 +499,7 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
   if (NS > 3) { r2_dif_stage<T, Cfg, YMODE, (NS > 3 ? 3 : 0)>(v, sm, A, c, t); r2_group_sync<Cfg, YMODE>(c); }
 
   // separation pass over pairs (k, N - k): k = t + m TPL covers 0 .. N/2 - 1, thread 0 adds k = N/2
-  const bool rev_out = kind == K_RODFT10;
+  constexpr bool rev_out = KIND == K_RODFT10;
   auto separate = [&](int k) {
     const int km = k ? N - k : 0;
     const C zk = sm[Lay::at(c, Cfg::rev(k))];
@@ -473,8 +526,10 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
 }
 
 // ---- backward kinds: HC2R, REDFT01, RODFT01 --------------------------------------------------------
-template <class T, class Cfg, bool YMODE, bool SPLIT = false>
+template <class T, class Cfg, bool YMODE, bool SPLIT, int KIND, bool FULL>
 __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(const R2Args<T> A) {
+  static_assert(KIND == K_HC2R || KIND == K_REDFT01 || KIND == K_RODFT01, "backward kinds");
+  static_assert(YMODE || r2_group_local<Cfg>(), "x mode relies on per-transform barriers");
   static_assert(!SPLIT || YMODE, "split rows exist only for the strided (y) transforms");
   using C = Cx<T>;
   using Lay = R2Lay<T, Cfg, YMODE>;
@@ -485,12 +540,12 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
   const int c = YMODE ? tid % G : tid / TPL;
   const int t = YMODE ? tid / G : tid % TPL;
   const R2Loc<T> loc = r2_locate<T, Cfg, YMODE>(A, c);
-  const int kind = A.kind;
-  const bool trig = kind != K_HC2R;
-  const bool rv = kind == K_RODFT01;
+  if (!YMODE && !loc.has_a) return;
+  constexpr bool trig = KIND != K_HC2R;
+  constexpr bool rv = KIND == K_RODFT01;
   auto get = [&](int i) -> C {
-    if (SPLIT) return r2_load_split<T>(A.row_tab, loc, i);
-    return r2_load<T, YMODE>(A.in, loc, A.in_es, i);
+    if (SPLIT) return r2_load_split<T, FULL>(A.row_tab, loc, i);
+    return r2_load<T, YMODE, FULL>(A.in, loc, A.in_es, i, A.flags);
   };
 
   // pre-pass: Z_k = W^a_k + i W^b_k and Z_{N-k} = conj W^a_k + i conj W^b_k, stored re/im swapped.
@@ -538,7 +593,7 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
   if (A.line_len > N && (SPLIT || A.in != A.out)) {
     for (int i = N + t; i < A.line_len; i += TPL) {
       const C x = get(i);
-      r2_store<T, YMODE>(A.out, loc, A.out_es, i, x.x, x.y);
+      r2_store<T, YMODE, FULL>(A.out, loc, A.out_es, i, x.x, x.y, A.flags);
     }
   }
   r2_group_sync<Cfg, YMODE>(c);
@@ -558,7 +613,7 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
         const int i = r2_vperm(trig, N, j);
         C x = v[m * R0 + q];
         if (rv && (i & 1)) x = {-x.x, -x.y};
-        r2_store<T, YMODE>(A.out, loc, A.out_es, i, x.y, x.x);
+        r2_store<T, YMODE, FULL>(A.out, loc, A.out_es, i, x.y, x.x, A.flags);
       }
   }
 }

@@ -2,6 +2,7 @@
 // One translation unit per (precision, mode, split) includes this header and explicitly
 // instantiates r2r2_run / r2r2_query, so the four units compile in parallel.
 #pragma once
+#include <set>
 #include "r2r2.cuh"
 
 namespace cb {
@@ -34,6 +35,22 @@ namespace cb {
   X(384, 0, 32, 8, 1, 12, 4, 4, 2)    \
   X(768, 0, 64, 4, 3, 12, 4, 4, 4)
 
+extern int g_r2_default_carveout;
+
+template <class K>
+static int r2r2_launch_kernel(K k, const void* args, unsigned grid, unsigned block, size_t smem, cudaStream_t st) {
+  // one attribute call per kernel and process (keyed by the function address)
+  static std::set<const void*> done;
+  if (!done.count((const void*)k)) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+    if (!g_r2_default_carveout)
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    done.insert((const void*)k);
+  }
+  void* kargs[1] = {const_cast<void*>(args)};
+  return cudaLaunchKernel((const void*)k, dim3(grid), dim3(block), kargs, smem, st) == cudaSuccess ? 0 : -4;
+}
+
 template <class T, class Cfg, bool YMODE, bool SPLIT>
 static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
   using Lay = R2Lay<T, Cfg, YMODE>;
@@ -46,25 +63,26 @@ static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
   }
   if (grid < 1) return 0;
   if (grid > 0x7fffffffLL) return -2;
-  static bool attr_fwd = false, attr_bwd = false;
-  if (fwd) {
-    auto k = r2r2_fwd_kernel<T, Cfg, YMODE, SPLIT>;
-    if (!attr_fwd) {
-      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
-      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_fwd = true;
-    }
-    k<<<(unsigned)grid, Cfg::TPL * Cfg::G, smem, st>>>(A);
-  } else {
-    auto k = r2r2_bwd_kernel<T, Cfg, YMODE, SPLIT>;
-    if (!attr_bwd) {
-      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
-      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      attr_bwd = true;
-    }
-    k<<<(unsigned)grid, Cfg::TPL * Cfg::G, smem, st>>>(A);
+  const unsigned g = (unsigned)grid, b = Cfg::TPL * Cfg::G;
+  // y mode: the unpredicated kernels need every column pair of every CTA to exist
+  const bool full = !YMODE || (A.lines_per_group % (2 * Cfg::G)) == 0;
+#define CB_R2_LAUNCH(KERNEL, KIND_)                                                                        \
+  case KIND_:                                                                                              \
+    if constexpr (YMODE) {                                                                                 \
+      if (!full) return r2r2_launch_kernel(KERNEL<T, Cfg, YMODE, SPLIT, KIND_, false>, &A, g, b, smem, st); \
+    }                                                                                                      \
+    return r2r2_launch_kernel(KERNEL<T, Cfg, YMODE, SPLIT, KIND_, true>, &A, g, b, smem, st);
+  switch (A.kind) {
+    CB_R2_LAUNCH(r2r2_fwd_kernel, K_R2HC)
+    CB_R2_LAUNCH(r2r2_fwd_kernel, K_REDFT10)
+    CB_R2_LAUNCH(r2r2_fwd_kernel, K_RODFT10)
+    CB_R2_LAUNCH(r2r2_bwd_kernel, K_HC2R)
+    CB_R2_LAUNCH(r2r2_bwd_kernel, K_REDFT01)
+    CB_R2_LAUNCH(r2r2_bwd_kernel, K_RODFT01)
+    default: return -5;
   }
-  return 0;
+#undef CB_R2_LAUNCH
+  (void)fwd;
 }
 
 // 0 = launched, 1 = no instantiation for this length, < 0 = error

@@ -227,23 +227,22 @@ __global__ void __launch_bounds__(128) thomas_seq_kernel(const ThomasDev<T> D, c
 }
 
 // ---- pipelined chunked substitution ---------------------------------------------
-// Persistent kernel, one CTA of 1024 threads per SM.  A tile is 16 consecutive
-// columns (one 128-byte row segment of the z pencil) x all rows; thread (c, g)
-// owns the m = ceil(nn / 64) consecutive rows g*m .. g*m+m-1 of column c.
-//   * its m right-hand-side values live in registers (the 16 lanes of a half
-//     warp read / write one full 128-byte line);
-//   * its m pivots are fetched with cp.async into a private strip of a DOUBLE
-//     BUFFERED shared-memory tile;
-//   * while tile i is being solved, the pivots of tile i+1 are in flight to the
-//     other buffer and its right-hand side to a second register set, so HBM
-//     latency is hidden by the pipeline, not by occupancy.
+// Persistent kernel, one CTA of 1024 threads per SM.  A tile is COLS consecutive
+// columns (one 128-byte row segment of the z pencil for COLS = 16 in FP64, 64 bytes
+// for COLS = 8) x all rows; thread (c, g) owns the m = ceil(nn / CHUNKS) consecutive
+// rows g*m .. g*m+m-1 of column c.  COLS x CHUNKS = 1024 threads always:
+//   nz <= 512  : 16 columns x 64 chunks  (m <= 8)
+//   nz <= 1024 :  8 columns x 128 chunks (m <= 8), same shared-memory footprint
+//   * the tile of pivots and right-hand sides arrives by 16-byte cp.async into
+//     shared memory; every thread then keeps its m values and pivots in registers;
+//   * while tile i is being solved, tile i+1 is already in flight to the (free
+//     again) shared-memory tile, so HBM latency is hidden by the pipeline, not by
+//     occupancy.
 // Both first-order recurrences are evaluated chunk-parallel: local sweep ->
 // (value, product) of every chunk to shared memory -> one warp per column folds
-// the 64 chunk maps with a shuffle scan -> fix-up.  Nothing but the final result
+// the CHUNKS chunk maps with a shuffle scan -> fix-up.  Nothing but the final result
 // is written: traffic = read p + read z + write p = 24 B/point (FP64).
-#define CB_TH_COLS 16
-#define CB_TH_CHUNKS 64
-#define CB_TH_THREADS (CB_TH_COLS * CB_TH_CHUNKS)
+#define CB_TH_THREADS 1024
 
 __device__ __forceinline__ void cp_async_elem(double* dst_smem, const double* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -256,9 +255,9 @@ __device__ __forceinline__ void cp_async_elem(float* dst_smem, const float* src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// shared memory: pivot tile [64 m rows][16], right-hand-side tile [64 m rows][16], a/c tables, fold arrays
-template <class T, int MMAX> constexpr size_t thomas_pipe_smem() {
-  return ((size_t)2 * MMAX * CB_TH_THREADS + 2 * CB_TH_CHUNKS * (MMAX + 2) + 2 * CB_TH_COLS * (CB_TH_CHUNKS + 1)) * sizeof(T);
+// shared memory: pivot tile [CHUNKS m rows][COLS], right-hand-side tile likewise, a/c tables, fold arrays
+template <class T, int MMAX, int COLS> constexpr size_t thomas_pipe_smem() {
+  return ((size_t)2 * MMAX * CB_TH_THREADS + 2 * (CB_TH_THREADS / COLS) * (MMAX + 2) + 2 * COLS * (CB_TH_THREADS / COLS + 1)) * sizeof(T);
 }
 __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -270,20 +269,29 @@ __device__ __forceinline__ float shfl_up_t(float v, int d) { return __shfl_up_sy
 __device__ __forceinline__ double shfl_down_t(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ float shfl_down_t(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 
-// Fold of the 64 chunk maps v -> Y_g + P_g v of every column: warp w < 16 owns column w, lane l owns the
-// chunk pair (2l, 2l+1); Kogge-Stone scan of the pair maps with shuffles; result = value entering each
-// chunk, written over sY.  FWD: chunk 0 upward; otherwise chunk 63 downward.
-template <class T, bool FWD>
+// Fold of the CHUNKS chunk maps v -> Y_g + P_g v of every column: warp w < COLS owns column w, lane l owns
+// the CPL = CHUNKS / 32 consecutive chunks l*CPL ..; Kogge-Stone scan of the lane aggregates with shuffles;
+// result = value entering each chunk, written over sY.  FWD: chunk 0 upward; otherwise the last chunk downward.
+template <class T, bool FWD, int COLS, int CHUNKS>
 __device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid) {
-  constexpr int LD = CB_TH_CHUNKS + 1;
+  constexpr int LD = CHUNKS + 1, CPL = CHUNKS / 32;
+  static_assert(CHUNKS % 32 == 0, "chunks per column must be a multiple of the warp size");
   const int w = tid >> 5, lane = tid & 31;
-  if (w < CB_TH_COLS) {
-    T* rowY = sY + w * LD;
-    const T* rowP = sP + w * LD;
-    const T y0 = rowY[2 * lane], y1 = rowY[2 * lane + 1], p0 = rowP[2 * lane], p1 = rowP[2 * lane + 1];
-    // map of the pair, in application order (FWD: chunk 2l then 2l+1; else 2l+1 then 2l)
-    T Y = FWD ? fma(p1, y0, y1) : fma(p0, y1, y0);
-    T P = p0 * p1;
+  if (w < COLS) {
+    T* rowY = sY + w * LD + lane * CPL;
+    const T* rowP = sP + w * LD + lane * CPL;
+    T y[CPL], p[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) { y[q] = rowY[q]; p[q] = rowP[q]; }
+    // aggregate map of the lane, in application order
+    T Y = FWD ? y[0] : y[CPL - 1];
+    T P = FWD ? p[0] : p[CPL - 1];
+#pragma unroll
+    for (int s = 1; s < CPL; ++s) {
+      const int q = FWD ? s : CPL - 1 - s;
+      Y = fma(p[q], Y, y[q]);
+      P *= p[q];
+    }
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const T Yp = FWD ? shfl_up_t(Y, d) : shfl_down_t(Y, d);
@@ -293,39 +301,39 @@ __device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid) {
     }
     T vin = FWD ? shfl_up_t(Y, 1) : shfl_down_t(Y, 1);
     if (FWD ? (lane == 0) : (lane == 31)) vin = T(0);
-    if (FWD) {
-      rowY[2 * lane] = vin;
-      rowY[2 * lane + 1] = fma(p0, vin, y0);
-    } else {
-      rowY[2 * lane + 1] = vin;
-      rowY[2 * lane] = fma(p1, vin, y1);
+#pragma unroll
+    for (int s = 0; s < CPL; ++s) {
+      const int q = FWD ? s : CPL - 1 - s;
+      rowY[q] = vin;
+      vin = fma(p[q], vin, y[q]);
     }
   }
 }
 
 // EXACT: the rows per chunk equal MMAX (no per-row predicates in the sweeps).
 // VEC: columns come in aligned 16-byte groups, so the tile copies use 16-byte cp.async.
-template <class T, int MMAX, bool EXACT, bool VEC>
+template <class T, int MMAX, bool EXACT, bool VEC, int COLS>
 __global__ void __launch_bounds__(CB_TH_THREADS, 1)
 thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, const T* p2base, const T* denbase,
                    long long slot_z, long long slot_den, T* p, T norm) {
   constexpr int NT = CB_TH_THREADS;
-  constexpr int LD = CB_TH_CHUNKS + 1;
+  constexpr int CHUNKS = NT / COLS;
+  constexpr int LD = CHUNKS + 1;
   constexpr int CSA = MMAX + 2;                     // chunk stride of the a/c tables (16-byte aligned, bank spread)
   constexpr int VW = 16 / sizeof(T);                // elements per 16-byte piece
   extern __shared__ __align__(16) unsigned char cb_smem_raw[];
-  T* zs = reinterpret_cast<T*>(cb_smem_raw);        // [row][16] pivots of the tile in flight / being consumed
-  T* ps = zs + (size_t)MMAX * NT;                   // [row][16] right-hand side
+  T* zs = reinterpret_cast<T*>(cb_smem_raw);        // [row][COLS] pivots of the tile in flight / being consumed
+  T* ps = zs + (size_t)MMAX * NT;                   // [row][COLS] right-hand side
   T* sa = ps + (size_t)MMAX * NT;                   // a_k at [g][r]
-  T* sc = sa + CB_TH_CHUNKS * CSA;                  // c_k
-  T* sY = sc + CB_TH_CHUNKS * CSA;                  // [c][g] chunk value, row stride 65
-  T* sP = sY + CB_TH_COLS * LD;                     // [c][g] chunk product
-  const int tid = threadIdx.x, c = tid & (CB_TH_COLS - 1), g = tid / CB_TH_COLS;
+  T* sc = sa + CHUNKS * CSA;                        // c_k
+  T* sY = sc + CHUNKS * CSA;                        // [c][g] chunk value, row stride CHUNKS + 1
+  T* sP = sY + COLS * LD;                           // [c][g] chunk product
+  const int tid = threadIdx.x, c = tid & (COLS - 1), g = tid / COLS;
   const int m = EXACT ? MMAX : D.m, nn = D.nn;
-  const int nrows_tile = CB_TH_CHUNKS * m;
+  const int nrows_tile = CHUNKS * m;
   const long long ncol = (long long)D.nx * D.ny;
   const long long sk = D.sk;
-  const int tiles_x = (D.xn + CB_TH_COLS - 1) / CB_TH_COLS;
+  const int tiles_x = (D.xn + COLS - 1) / COLS;
   const int ntiles = tiles_x * D.ny;
   const int sel = st->sel;
   const int k0 = g * m;
@@ -341,19 +349,19 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   // tile -> (flat column of its first thread, live columns)
   auto tile_col0 = [&](int tile, int& ncols) -> long long {
     const int tj = tile / tiles_x;
-    const int ti0 = (tile - tj * tiles_x) * CB_TH_COLS;
-    ncols = D.xn - ti0 < CB_TH_COLS ? D.xn - ti0 : CB_TH_COLS;
+    const int ti0 = (tile - tj * tiles_x) * COLS;
+    ncols = D.xn - ti0 < COLS ? D.xn - ti0 : COLS;
     return (long long)tj * D.nx + D.xb + ti0;
   };
-  // asynchronous copy of one tile of pivots and right-hand sides into [row][16]; rows >= nn and dead
+  // asynchronous copy of one tile of pivots and right-hand sides into [row][COLS]; rows >= nn and dead
   // columns are zero filled so that the chunk maps of padding rows are exact identities / zeros
   auto prefetch = [&](long long col0, int ncols) {
     if (VEC) {
-      constexpr int PPR = CB_TH_COLS / VW;          // pieces per row
+      constexpr int PPR = COLS / VW;                // pieces per row
       for (int q = tid; q < nrows_tile * PPR; q += NT) {
         const int row = q / PPR, pc = (q - row * PPR) * VW;
-        T* zd = zs + row * CB_TH_COLS + pc;
-        T* pd = ps + row * CB_TH_COLS + pc;
+        T* zd = zs + row * COLS + pc;
+        T* pd = ps + row * COLS + pc;
         if (row < nn && pc < ncols) {
           cp_async_16(zd, zsel + (long long)row * ncol + col0 + pc);
           cp_async_16(pd, p + (long long)row * sk + col0 + pc);
@@ -363,8 +371,8 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         }
       }
     } else {
-      for (int q = tid; q < nrows_tile * CB_TH_COLS; q += NT) {
-        const int row = q / CB_TH_COLS, pc = q - row * CB_TH_COLS;
+      for (int q = tid; q < nrows_tile * COLS; q += NT) {
+        const int row = q / COLS, pc = q - row * COLS;
         if (row < nn && pc < ncols) {
           cp_async_elem(zs + q, zsel + (long long)row * ncol + col0 + pc);
           cp_async_elem(ps + q, p + (long long)row * sk + col0 + pc);
@@ -389,8 +397,8 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
 #pragma unroll
     for (int r = 0; r < MMAX; ++r)
       if (EXACT || r < m) {
-        y[r] = ps[(k0 + r) * CB_TH_COLS + c];
-        z[r] = zs[(k0 + r) * CB_TH_COLS + c];
+        y[r] = ps[(k0 + r) * COLS + c];
+        z[r] = zs[(k0 + r) * COLS + c];
       }
     const bool live = c < ncols;
     const int nrow = live ? nrow_full : 0;
@@ -417,7 +425,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       col0_n = tile_col0(tnext, ncols_n);
       prefetch(col0_n, ncols_n);
     }
-    thomas_fold<T, true>(sY, sP, tid);
+    thomas_fold<T, true, COLS, CHUNKS>(sY, sP, tid);
     __syncthreads();
     T vin = sY[c * LD + g];
     pi = T(1);
@@ -442,7 +450,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     sY[c * LD + g] = xx;   // own slot: only this thread read it since the fold
     sP[c * LD + g] = rho;
     __syncthreads();
-    thomas_fold<T, false>(sY, sP, tid);
+    thomas_fold<T, false, COLS, CHUNKS>(sY, sP, tid);
     __syncthreads();
     vin = sY[c * LD + g];
     rho = T(1);
@@ -461,7 +469,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       if (kl >= k0 && kl < k0 + m) {
 #pragma unroll
         for (int r = 0; r < MMAX; ++r)
-          if (k0 + r == kl) sY[CB_TH_COLS + c] = y[r];   // x_nn
+          if (k0 + r == kl) sY[COLS + c] = y[r];   // x_nn
       }
       __syncthreads();
       if (g == 0) {
@@ -469,7 +477,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         if (live) {
           const T den = denbase[(long long)sel * slot_den + col];
           const T pnn = p[(long long)nn * sk + col];
-          const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[CB_TH_COLS + c]));
+          const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[COLS + c]));
           pcl = (den == T(0)) ? T(0) : div_rn(num, den);
           if (D.out_rows) D.out_rows[nn][col] = pcl;
           else p[(long long)nn * sk + col] = pcl;

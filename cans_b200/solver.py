@@ -112,6 +112,11 @@ class Context:
         check(lib.cansb200_ctx_set(self._h, 1, int(x)), "ctx_set")
         check(lib.cansb200_ctx_set(self._h, 2, int(y)), "ctx_set")
 
+    def set_r2_flags(self, flags: int = 0):
+        """Cache hints of the fast transforms (CANSB200_CTX_R2_FLAGS): 1 = field loads bypass L1
+        allocation, 2 = streaming stores, 4 = force the maximum shared-memory carveout."""
+        check(lib.cansb200_ctx_set(self._h, 5, int(flags)), "ctx_set")
+
     def set_chain(self, cols: int = 0, streams: int = 2):
         """L2-resident fft-y -> tridiagonal -> ifft-y chain over x windows of `cols` columns (0 = off)."""
         check(lib.cansb200_ctx_set(self._h, 3, int(cols)), "ctx_set")

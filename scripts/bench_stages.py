@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--kinds", default="R2HC,HC2R")
     ap.add_argument("--variants", type=int, default=3)
     ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--no-thomas", action="store_true")
     args = ap.parse_args()
     ng = args.grid
     dev = torch.device("cuda:0")
@@ -52,6 +54,7 @@ def main():
     dt = torch.float32 if args.fp32 else torch.float64
     esz = 4 if args.fp32 else 8
     ctx = cb.Context(ng, is_fp32=args.fp32)
+    ctx.set_r2_flags(args.flags)
     arr = torch.rand((ng[2], ng[1], ng[0]), dtype=dt, device=dev)
     npts = ng[0] * ng[1] * ng[2]
     rows = []
@@ -63,7 +66,7 @@ def main():
                 rows.append((f"r2r axis={axis} n={n} {kname} var={var}", ms, 2 * esz * npts / ms / 1e6))
     ctx.set_variant(0, 0)
     # Thomas (Neumann-Neumann stretched, and periodic)
-    for cbcz, per in ((["N", "N"], False), (["P", "P"], True)):
+    for cbcz, per in (() if args.no_thomas else ((["N", "N"], False), (["P", "P"], True))):
         cbc = [["P", "P"], ["P", "P"], cbcz]
         dzc, dzf = gridgen.initgrid(1, ng[2], 0.0 if per else 2.0, 2.0, per)
         dli = [ng[0] / 12.0, ng[1] / 6.0, ng[2] / 2.0]

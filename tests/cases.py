@@ -23,6 +23,11 @@ CASES = {
     "periodic_z_odd": ([8, 6, 37], [1.0, 1.0, 1.0], [N, P, P], C3, 0.0, np.float64),
     "tiny_z": ([8, 8, 2], [1.0, 1.0, 1.0], [P, P, N], C3, 0.0, np.float64),
     "nz_gt_512": ([8, 8, 600], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    # 8-column pipelined Thomas tiles (512 < nz <= 1024) and the sequential fallback beyond
+    "nz_768_duct": ([16, 12, 768], [1.0, 1.0, 2.0], [P, N, N], C3, 1.5, np.float64),
+    "nz_1024": ([10, 8, 1024], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    "nz_1000_periodic": ([8, 6, 1000], [1.0, 1.0, 1.0], [P, P, P], C3, 0.0, np.float64),
+    "nz_gt_1024": ([8, 8, 1100], [1.0, 1.0, 2.0], [P, P, D], C3, 1.0, np.float64),
     # implicit-diffusion (Helmholtz) operators: face-centred in one direction, Dirichlet walls
     "helm_u_face_x": ([16, 12, 20], [1.0, 1.0, 1.0], [D, D, D], ["f", "c", "c"], 1.0, np.float64),
     "helm_v_face_y": ([16, 12, 20], [1.0, 1.0, 1.0], [P, D, D], ["c", "f", "c"], 1.0, np.float64),
