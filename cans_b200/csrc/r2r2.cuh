@@ -246,9 +246,19 @@ template <class T, class Cfg, bool YMODE> struct R2Lay {
   static constexpr int SW = sizeof(T) == 8 ? 3 : 4;
   static constexpr int NP = (Cfg::N + (1 << SW) - 1) & ~((1 << SW) - 1);
   static constexpr size_t smem_bytes() { return (YMODE ? (size_t)Cfg::N * Cfg::G : (size_t)NP * Cfg::G) * sizeof(Cx<T>); }
+  // encoded position: x mode = XOR-swizzled index (linear over GF(2)), y mode = the index itself
+  __host__ __device__ static constexpr int enc(int pos) {
+    return YMODE ? pos : (pos ^ (((pos >> SW) ^ (pos >> (2 * SW))) & ((1 << SW) - 1)));
+  }
   __device__ static __forceinline__ int at(int c, int pos) {
     if (YMODE) return pos * Cfg::G + c;
-    return c * NP + (pos ^ (((pos >> SW) ^ (pos >> (2 * SW))) & ((1 << SW) - 1)));
+    return c * NP + enc(pos);
+  }
+  // slot of position pa + pb given enc(pa), enc(pb), for pa and pb with DISJOINT bit sets (power-of-two plans: a
+  // per-thread part and a compile-time part), so that enc(pa + pb) = enc(pa) ^ enc(pb) (x) / enc(pa) + enc(pb) (y)
+  __device__ static __forceinline__ int join(int c, int ea, int eb) {
+    if (YMODE) return (ea + eb) * Cfg::G + c;
+    return c * NP + (ea ^ eb);
   }
 };
 
@@ -301,14 +311,16 @@ __device__ __forceinline__ R2Loc<T> r2_locate(const R2Args<T>& A, int c) {
     L.g = g;
     L.x = x;
   } else {
-    const long long nl = (long long)A.lines_per_group * A.ngroups;
-    const long long la = ((long long)blockIdx.x * Cfg::G + c) * 2, lb = la + 1;
-    const long long ga = la / A.lines_per_group, gb = lb / A.lines_per_group;
-    const long long ja = la - ga * A.lines_per_group, jb = lb - gb * A.lines_per_group;
-    L.ia = ga * A.in_gs + ja * A.in_ls;
-    L.oa = ga * A.out_gs + ja * A.out_ls;
-    L.ib = gb * A.in_gs + jb * A.in_ls;
-    L.ob = gb * A.out_gs + jb * A.out_ls;
+    // 32-bit index arithmetic (the launcher checks that the line count fits)
+    const unsigned lpg = (unsigned)A.lines_per_group;
+    const unsigned nl = lpg * (unsigned)A.ngroups;
+    const unsigned la = (blockIdx.x * (unsigned)Cfg::G + (unsigned)c) * 2u, lb = la + 1u;
+    const unsigned ga = la / lpg, ja = la - ga * lpg;
+    const unsigned gb = (ja + 1u == lpg) ? ga + 1u : ga, jb = (ja + 1u == lpg) ? 0u : ja + 1u;
+    L.ia = (long long)ga * A.in_gs + (long long)ja * A.in_ls;
+    L.oa = (long long)ga * A.out_gs + (long long)ja * A.out_ls;
+    L.ib = (long long)gb * A.in_gs + (long long)jb * A.in_ls;
+    L.ob = (long long)gb * A.out_gs + (long long)jb * A.out_ls;
     L.has_a = la < nl;
     L.has_b = lb < nl;
     if (!L.has_b) { L.ib = L.ia; L.ob = L.oa; }   // odd line count: b aliases a, and a is stored last (r2_store)
@@ -316,46 +328,6 @@ __device__ __forceinline__ R2Loc<T> r2_locate(const R2Args<T>& A, int c) {
     L.x = 0;
   }
   return L;
-}
-
-// FULL: every column pair of the CTA exists (y mode; the host checks it).  x mode never predicates: a transform
-// without lines exits at kernel entry, and a missing second line aliases the first (see r2_locate).
-template <class T, bool YMODE, bool FULL>
-__device__ __forceinline__ Cx<T> r2_load(const T* __restrict__ p, const R2Loc<T>& L, long long es, int i, int flags) {
-  Cx<T> v;
-  const bool na = flags & CB_R2_LD_NA;
-  if (YMODE) {
-    const T* q = p + L.ia + (long long)i * es;
-    if (FULL || L.has_b) return na ? ld_na(reinterpret_cast<const Cx<T>*>(q)) : *reinterpret_cast<const Cx<T>*>(q);
-    v.x = L.has_a ? *q : T(0);
-    v.y = T(0);
-  } else if (na) {
-    v.x = ld_na(p + L.ia + i);
-    v.y = ld_na(p + L.ib + i);
-  } else {
-    v.x = p[L.ia + i];
-    v.y = p[L.ib + i];
-  }
-  return v;
-}
-template <class T, bool YMODE, bool FULL>
-__device__ __forceinline__ void r2_store(T* __restrict__ p, const R2Loc<T>& L, long long es, int i, T a, T b, int flags) {
-  const bool cs = flags & CB_R2_ST_CS;
-  if (YMODE) {
-    T* q = p + L.oa + (long long)i * es;
-    if (FULL || L.has_b) {
-      if (cs) st_cs(reinterpret_cast<Cx<T>*>(q), Cx<T>{a, b});
-      else *reinterpret_cast<Cx<T>*>(q) = Cx<T>{a, b};
-      return;
-    }
-    if (L.has_a) *q = a;
-  } else if (cs) {
-    st_cs(p + L.ob + i, b);
-    st_cs(p + L.oa + i, a);
-  } else {
-    p[L.ob + i] = b;
-    p[L.oa + i] = a;
-  }
 }
 
 // split (peer-mapped) rows of the distributed y transforms
@@ -373,24 +345,6 @@ __device__ __forceinline__ R2Row<float> r2_row(const R2Row<float>* tab, int i) {
   r.gs = v.y;
   return r;
 }
-template <class T, bool FULL>
-__device__ __forceinline__ Cx<T> r2_load_split(const R2Row<T>* tab, const R2Loc<T>& L, int i) {
-  const R2Row<T> e = r2_row(tab, i);
-  const T* q = e.ptr + (long long)L.g * e.gs + L.x;
-  if (FULL || L.has_b) return *reinterpret_cast<const Cx<T>*>(q);
-  Cx<T> v;
-  v.x = L.has_a ? *q : T(0);
-  v.y = T(0);
-  return v;
-}
-template <class T, bool FULL>
-__device__ __forceinline__ void r2_store_split(const R2Row<T>* tab, const R2Loc<T>& L, int i, T a, T b) {
-  const R2Row<T> e = r2_row(tab, i);
-  T* q = e.ptr + (long long)L.g * e.gs + L.x;
-  if (FULL || L.has_b) { *reinterpret_cast<Cx<T>*>(q) = Cx<T>{a, b}; return; }
-  if (L.has_a) *q = a;
-}
-
 // Makhoul permutation: position j of v holds input sample vperm(j)
 __device__ __forceinline__ int r2_vperm(bool trig, int n, int j) {
   if (!trig) return j;
@@ -398,11 +352,83 @@ __device__ __forceinline__ int r2_vperm(bool trig, int n, int j) {
   return j < h ? 2 * j : 2 * (n - 1 - j) + 1;
 }
 
+// Row accessor of one transform: rows `base + off` with a per-thread `base` folded into the pointers once and a
+// compile-time `off`, so that the unrolled loads / stores use immediate offsets (x mode) or one multiply-add
+// (y mode).  x mode: two lines a, b; y mode: one 16-byte column pair per row; SPLIT: rows located through the
+// peer-mapped row table.
+template <class T, bool YMODE, bool SPLIT, bool FULL> struct R2Rows {
+  T* pa;
+  T* pb;
+  long long es;
+  const R2Row<T>* tab;
+  int g, x;
+  bool has_a, has_b;
+  __device__ __forceinline__ Cx<T> load(int off) const {
+    Cx<T> v;
+    if (SPLIT) {
+      const R2Row<T> e = r2_row(tab, off);
+      const T* q = e.ptr + (long long)g * e.gs + x;
+      if (FULL || has_b) return *reinterpret_cast<const Cx<T>*>(q);
+      v.x = has_a ? *q : T(0);
+      v.y = T(0);
+    } else if (YMODE) {
+      const T* q = pa + (long long)off * es;
+      if (FULL || has_b) return *reinterpret_cast<const Cx<T>*>(q);
+      v.x = has_a ? *q : T(0);
+      v.y = T(0);
+    } else {
+      v.x = pa[off];
+      v.y = pb[off];
+    }
+    return v;
+  }
+  __device__ __forceinline__ void store(int off, T a, T b) const {
+    if (SPLIT) {
+      const R2Row<T> e = r2_row(tab, off);
+      T* q = e.ptr + (long long)g * e.gs + x;
+      if (FULL || has_b) { *reinterpret_cast<Cx<T>*>(q) = Cx<T>{a, b}; return; }
+      if (has_a) *q = a;
+    } else if (YMODE) {
+      T* q = pa + (long long)off * es;
+      if (FULL || has_b) { *reinterpret_cast<Cx<T>*>(q) = Cx<T>{a, b}; return; }
+      if (has_a) *q = a;
+    } else {
+      pb[off] = b;   // b first: when the second line is missing it aliases the first and a must win
+      pa[off] = a;
+    }
+  }
+};
+template <class T, bool YMODE, bool SPLIT, bool FULL>
+__device__ __forceinline__ R2Rows<T, YMODE, SPLIT, FULL> r2_rows(const T* p, long long oa, long long ob, long long es,
+                                                                  const R2Row<T>* tab, const R2Loc<T>& L, int base) {
+  R2Rows<T, YMODE, SPLIT, FULL> R;
+  T* q = const_cast<T*>(p);
+  R.pa = q + oa + (YMODE ? (long long)base * es : (long long)base);
+  R.pb = q + ob + (long long)base;
+  R.es = es;
+  R.tab = SPLIT ? tab + base : nullptr;
+  R.g = L.g; R.x = L.x; R.has_a = L.has_a; R.has_b = L.has_b;
+  return R;
+}
+
+// thread part of the positions a thread touches in stage S (the part that does not depend on the unrolled
+// indices m, q), and the compile-time remainder; their bit sets are disjoint for power-of-two plans
+template <class Cfg, int S> __device__ __forceinline__ int r2_stage_tpos(int t) {
+  constexpr int Rs = Cfg::R(S), Ns = Cfg::Ns(S), L = Ns / Rs;
+  return (L >= Cfg::TPL) ? t : (t / L) * Ns + (t % L);
+}
+template <class Cfg, int S> __host__ __device__ constexpr int r2_stage_cpos(int m, int q) {
+  constexpr int Rs = Cfg::R(S), Ns = Cfg::Ns(S), L = Ns / Rs;
+  return ((Cfg::TPL * m) / L) * Ns + ((Cfg::TPL * m) % L) + q * L;
+}
+
 // one DIF stage on the shared tile (S > 0) or on registers already loaded (S == 0)
 template <class T, class Cfg, bool YMODE, int S>
 __device__ __forceinline__ void r2_dif_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T>& A, int c, int t) {
   using Lay = R2Lay<T, Cfg, YMODE>;
   constexpr int Rs = Cfg::R(S), Ns = Cfg::Ns(S), L = Ns / Rs, NB = Cfg::E / Rs, TPL = Cfg::TPL;
+  constexpr bool POW2 = (Cfg::N & (Cfg::N - 1)) == 0;
+  const int et = Lay::enc(r2_stage_tpos<Cfg, S>(t));
 #pragma unroll
   for (int m = 0; m < NB; ++m) {
     const int u = t + TPL * m;
@@ -411,7 +437,8 @@ __device__ __forceinline__ void r2_dif_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T
     Cx<T>* a = (S == 0) ? v + m * Rs : v;
     if (S > 0) {
 #pragma unroll
-      for (int q = 0; q < Rs; ++q) a[q] = sm[Lay::at(c, base + q * L)];
+      for (int q = 0; q < Rs; ++q)
+        a[q] = POW2 ? sm[Lay::join(c, et, Lay::enc(r2_stage_cpos<Cfg, S>(m, q)))] : sm[Lay::at(c, base + q * L)];
     }
     bfR<T, Rs>(a);
     if (L > 1) {
@@ -419,7 +446,10 @@ __device__ __forceinline__ void r2_dif_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T
       for (int r = 1; r < Rs; ++r) a[r] = cx_mul(a[r], cx_ldg(A.tw[S] + (r - 1) * L + o));
     }
 #pragma unroll
-    for (int r = 0; r < Rs; ++r) sm[Lay::at(c, base + r * L)] = a[r];
+    for (int r = 0; r < Rs; ++r) {
+      if (POW2) sm[Lay::join(c, et, Lay::enc(r2_stage_cpos<Cfg, S>(m, r)))] = a[r];
+      else sm[Lay::at(c, base + r * L)] = a[r];
+    }
   }
 }
 
@@ -428,6 +458,8 @@ template <class T, class Cfg, bool YMODE, int S>
 __device__ __forceinline__ void r2_dit_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T>& A, int c, int t) {
   using Lay = R2Lay<T, Cfg, YMODE>;
   constexpr int Rs = Cfg::R(S), Ns = Cfg::Ns(S), L = Ns / Rs, NB = Cfg::E / Rs, TPL = Cfg::TPL;
+  constexpr bool POW2 = (Cfg::N & (Cfg::N - 1)) == 0;
+  const int et = Lay::enc(r2_stage_tpos<Cfg, S>(t));
 #pragma unroll
   for (int m = 0; m < NB; ++m) {
     const int u = t + TPL * m;
@@ -435,7 +467,8 @@ __device__ __forceinline__ void r2_dit_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T
     const int base = blk * Ns + o;
     Cx<T>* a = (S == 0) ? v + m * Rs : v;
 #pragma unroll
-    for (int q = 0; q < Rs; ++q) a[q] = sm[Lay::at(c, base + q * L)];
+    for (int q = 0; q < Rs; ++q)
+      a[q] = POW2 ? sm[Lay::join(c, et, Lay::enc(r2_stage_cpos<Cfg, S>(m, q)))] : sm[Lay::at(c, base + q * L)];
     if (L > 1) {
 #pragma unroll
       for (int q = 1; q < Rs; ++q) a[q] = cx_mul(a[q], cx_ldg(A.tw[S] + (q - 1) * L + o));
@@ -443,10 +476,43 @@ __device__ __forceinline__ void r2_dit_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T
     bfR<T, Rs>(a);
     if (S > 0) {
 #pragma unroll
-      for (int r = 0; r < Rs; ++r) sm[Lay::at(c, base + r * L)] = a[r];
+      for (int r = 0; r < Rs; ++r) {
+        if (POW2) sm[Lay::join(c, et, Lay::enc(r2_stage_cpos<Cfg, S>(m, r)))] = a[r];
+        else sm[Lay::at(c, base + r * L)] = a[r];
+      }
     }
   }
 }
+
+// Pair pass bookkeeping.  Thread t owns the frequencies k = t + kc, kc = m TPL < N/2, and their mirrors
+//   N - k = (TPL - t) + (N - TPL - kc)            (t > 0)
+//         = N - kc                                 (t = 0; 0 when kc = 0)
+// so global rows are `t + const` ("up") or `(TPL - t) + const` ("dn"), and for power-of-two plans (digit
+// reversal = a bit permutation) the shared-memory slots split the same way into a per-thread and a
+// compile-time part.
+template <class T, class Cfg, bool YMODE> struct R2Pair {
+  using Lay = R2Lay<T, Cfg, YMODE>;
+  static constexpr bool POW2 = (Cfg::N & (Cfg::N - 1)) == 0;
+  int t, c, e_up, e_dn;
+  __device__ __forceinline__ R2Pair(int t_, int c_) : t(t_), c(c_) {
+    e_up = Lay::enc(Cfg::rev(t_));
+    e_dn = Lay::enc(Cfg::rev(t_ ? Cfg::TPL - t_ : 0));
+  }
+  // slot of Z_k, k = t + kc
+  __device__ __forceinline__ int slot_k(int kc) const {
+    if (POW2) return Lay::join(c, e_up, Lay::enc(Cfg::rev(kc)));
+    return Lay::at(c, Cfg::rev(t + kc));
+  }
+  // slot of Z_{N-k} (Z_0 for k = 0)
+  __device__ __forceinline__ int slot_m(int kc) const {
+    if (POW2) {
+      const int c1 = Lay::enc(Cfg::rev(Cfg::N - Cfg::TPL - kc)), c0 = Lay::enc(Cfg::rev((Cfg::N - kc) % Cfg::N));
+      return Lay::join(c, e_dn, t ? c1 : c0);
+    }
+    const int k = t + kc;
+    return Lay::at(c, Cfg::rev(k ? Cfg::N - k : 0));
+  }
+};
 
 // ---- forward kinds: R2HC, REDFT10, RODFT10 ---------------------------------------------------------
 template <class T, class Cfg, bool YMODE, bool SPLIT, int KIND, bool FULL>
@@ -459,37 +525,46 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
   extern __shared__ __align__(16) unsigned char cb_smem_raw[];
   C* sm = reinterpret_cast<C*>(cb_smem_raw);
   constexpr int N = Cfg::N, TPL = Cfg::TPL, E = Cfg::E, G = Cfg::G, NS = Cfg::NS;
+  static_assert((TPL & (TPL - 1)) == 0, "threads per transform must be a power of two");
   const int tid = threadIdx.x;
   const int c = YMODE ? tid % G : tid / TPL;
-  const int t = YMODE ? tid / G : tid % TPL;
+  const int t = (YMODE ? tid / G : tid) & (TPL - 1);
   const R2Loc<T> loc = r2_locate<T, Cfg, YMODE>(A, c);
   if (!YMODE && !loc.has_a) return;   // x mode: group barriers only (r2_group_sync), so a lineless transform may leave
   constexpr bool trig = KIND != K_R2HC;
   constexpr bool neg_odd = KIND == K_RODFT10;
-  auto put = [&](int i, T a, T b) {
-    if (SPLIT) r2_store_split<T, FULL>(A.row_tab, loc, i, a, b);
-    else r2_store<T, YMODE, FULL>(A.out, loc, A.out_es, i, a, b, A.flags);
-  };
+  using RowsIn = R2Rows<T, YMODE, false, FULL>;
+  using RowsOut = R2Rows<T, YMODE, SPLIT, FULL>;
 
   C v[E];
   {
+    // natural-order samples j = t + cj; Makhoul: input row 2 j (cj < N/2) or 2 (N - 1 - j) + 1
     constexpr int R0 = Cfg::R(0), L0 = N / R0;
+    const RowsIn in_up = r2_rows<T, YMODE, false, FULL>(A.in, loc.ia, loc.ib, A.in_es, nullptr, loc, trig ? 2 * t : t);
+    const RowsIn in_dn = r2_rows<T, YMODE, false, FULL>(A.in, loc.ia, loc.ib, A.in_es, nullptr, loc, -2 * t);
 #pragma unroll
     for (int m = 0; m < E / R0; ++m)
 #pragma unroll
       for (int q = 0; q < R0; ++q) {
-        const int j = q * L0 + t + TPL * m;
-        const int i = r2_vperm(trig, N, j);
-        C x = r2_load<T, YMODE, FULL>(A.in, loc, A.in_es, i, A.flags);
-        if (neg_odd && (i & 1)) x = {-x.x, -x.y};
+        const int cj = q * L0 + TPL * m;
+        C x;
+        if (!trig) x = in_up.load(cj);
+        else if (cj < N / 2) x = in_up.load(2 * cj);
+        else {
+          x = in_dn.load(2 * N - 1 - 2 * cj);
+          if (neg_odd) x = {-x.x, -x.y};   // odd input rows
+        }
         v[m * R0 + q] = x;
       }
   }
+  const RowsOut out_up = r2_rows<T, YMODE, SPLIT, FULL>(A.out, loc.oa, loc.ob, A.out_es, A.row_tab, loc, t);
+  const RowsOut out_dn = r2_rows<T, YMODE, SPLIT, FULL>(A.out, loc.oa, loc.ob, A.out_es, A.row_tab, loc, TPL - t);
   // copy the untransformed tail when the result goes to another array
   if (A.line_len > N && (SPLIT || A.in != A.out)) {
-    for (int i = N + t; i < A.line_len; i += TPL) {
-      const C x = r2_load<T, YMODE, FULL>(A.in, loc, A.in_es, i, A.flags);
-      put(i, x.x, x.y);
+    const RowsIn in_t = r2_rows<T, YMODE, false, FULL>(A.in, loc.ia, loc.ib, A.in_es, nullptr, loc, t);
+    for (int i = N; i + t < A.line_len; i += TPL) {
+      const C x = in_t.load(i);
+      out_up.store(i, x.x, x.y);
     }
   }
   r2_dif_stage<T, Cfg, YMODE, 0>(v, sm, A, c, t);
@@ -500,29 +575,47 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
 
   // separation pass over pairs (k, N - k): k = t + m TPL covers 0 .. N/2 - 1, thread 0 adds k = N/2
   constexpr bool rev_out = KIND == K_RODFT10;
-  auto separate = [&](int k) {
-    const int km = k ? N - k : 0;
-    const C zk = sm[Lay::at(c, Cfg::rev(k))];
-    const C zm = sm[Lay::at(c, Cfg::rev(km))];
+  static_assert(N % 2 == 0 && (N / 2) % TPL == 0, "pair pass needs TPL | N/2");
+  const R2Pair<T, Cfg, YMODE> P(t, c);
+  const C* mak_t = A.mak + t;
+#pragma unroll
+  for (int m = 0; m < (N / 2) / TPL; ++m) {
+    const int kc = m * TPL;                 // k = t + kc, N - k = (TPL - t) + kmc
+    const int kmc = N - TPL - kc;
+    const bool kpos = kc > 0 || t > 0;      // k > 0
+    const C zk = sm[P.slot_k(kc)];
+    const C zm = sm[P.slot_m(kc)];
     const T sx = zk.x + zm.x, dx = zk.x - zm.x, sy = zk.y + zm.y, dy = zk.y - zm.y;
     if (!trig) {
       // A_k = (sx, dy) / 2, B_k = (sy, -dx) / 2 ; halfcomplex: re at k, im at N - k
-      put(k, T(0.5) * sx, T(0.5) * sy);
-      if (k > 0 && 2 * k != N) put(N - k, T(0.5) * dy, T(-0.5) * dx);
+      out_up.store(kc, T(0.5) * sx, T(0.5) * sy);
+      if (kpos) out_dn.store(kmc, T(0.5) * dy, T(-0.5) * dx);
     } else {
-      const C cs = cx_ldg(A.mak + k);
+      const C cs = cx_ldg(mak_t + kc);
       const T xa = cs.x * sx + cs.y * dy, xb = cs.x * sy - cs.y * dx;
-      put(rev_out ? N - 1 - k : k, xa, xb);
-      if (k > 0) {
+      if (rev_out) out_dn.store(kmc - 1, xa, xb);   // N - 1 - k
+      else out_up.store(kc, xa, xb);
+      if (kpos) {
         const T ya = cs.y * sx - cs.x * dy, yb = cs.y * sy + cs.x * dx;
-        put(rev_out ? k - 1 : N - k, ya, yb);
+        if (rev_out) out_up.store(kc - 1, ya, yb);  // k - 1
+        else out_dn.store(kmc, ya, yb);             // N - k
       }
     }
-  };
-  static_assert(N % 2 == 0 && (N / 2) % TPL == 0, "pair pass needs TPL | N/2");
-#pragma unroll
-  for (int m = 0; m < (N / 2) / TPL; ++m) separate(t + m * TPL);
-  if (t == 0) separate(N / 2);
+  }
+  if (t == 0) {
+    // k = N/2 pairs with itself
+    const C zk = sm[Lay::at(c, Cfg::rev(N / 2))];
+    const T sx = zk.x + zk.x, sy = zk.y + zk.y;
+    if (!trig) {
+      out_up.store(N / 2, T(0.5) * sx, T(0.5) * sy);
+    } else {
+      const C cs = cx_ldg(A.mak + N / 2);
+      const T xa = cs.x * sx, xb = cs.x * sy;
+      out_up.store(rev_out ? N - 1 - N / 2 : N / 2, xa, xb);
+      const T ya = cs.y * sx, yb = cs.y * sy;
+      out_up.store(rev_out ? N / 2 - 1 : N - N / 2, ya, yb);
+    }
+  }
 }
 
 // ---- backward kinds: HC2R, REDFT01, RODFT01 --------------------------------------------------------
@@ -536,64 +629,87 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
   extern __shared__ __align__(16) unsigned char cb_smem_raw[];
   C* sm = reinterpret_cast<C*>(cb_smem_raw);
   constexpr int N = Cfg::N, TPL = Cfg::TPL, E = Cfg::E, G = Cfg::G, NS = Cfg::NS;
+  static_assert((TPL & (TPL - 1)) == 0, "threads per transform must be a power of two");
   const int tid = threadIdx.x;
   const int c = YMODE ? tid % G : tid / TPL;
-  const int t = YMODE ? tid / G : tid % TPL;
+  const int t = (YMODE ? tid / G : tid) & (TPL - 1);
   const R2Loc<T> loc = r2_locate<T, Cfg, YMODE>(A, c);
   if (!YMODE && !loc.has_a) return;
   constexpr bool trig = KIND != K_HC2R;
   constexpr bool rv = KIND == K_RODFT01;
-  auto get = [&](int i) -> C {
-    if (SPLIT) return r2_load_split<T, FULL>(A.row_tab, loc, i);
-    return r2_load<T, YMODE, FULL>(A.in, loc, A.in_es, i, A.flags);
-  };
+  using RowsIn = R2Rows<T, YMODE, SPLIT, FULL>;
+  using RowsOut = R2Rows<T, YMODE, false, FULL>;
+  const RowsIn in_up = r2_rows<T, YMODE, SPLIT, FULL>(A.in, loc.ia, loc.ib, A.in_es, A.row_tab, loc, t);
+  const RowsIn in_dn = r2_rows<T, YMODE, SPLIT, FULL>(A.in, loc.ia, loc.ib, A.in_es, A.row_tab, loc, TPL - t);
 
   // pre-pass: Z_k = W^a_k + i W^b_k and Z_{N-k} = conj W^a_k + i conj W^b_k, stored re/im swapped.
   // Two steps so that all global loads of a thread are in flight together.
   static_assert(N % 2 == 0 && (N / 2) % TPL == 0, "pair pass needs TPL | N/2");
   constexpr int NK = (N / 2) / TPL;
-  auto fetch = [&](int k, C& xk, C& xm) {
-    const int km = N - k;
-    xm = C{T(0), T(0)};
-    if (!trig) {
-      xk = get(k);
-      if (k > 0 && 2 * k != N) xm = get(km);
-    } else {
-      xk = get(rv ? N - 1 - k : k);
-      if (k > 0) xm = get(rv ? k - 1 : km);  // X_N := 0
-    }
-  };
-  auto scatter = [&](int k, const C& xk, const C& xm) {
-    const int km = N - k;
-    C wa, wb;  // spectra of the two real sequences at k
+  const R2Pair<T, Cfg, YMODE> P(t, c);
+  const C* mak_t = A.mak + t;
+  // spectra of the two real sequences at k from the rows at k (xk) and N - k (xm), scattered to the slots of
+  // Z_k and Z_{N-k}
+  auto combine = [&](const C& cs, const C& xk, const C& xm, C& zk, C& zm) {
+    C wa, wb;
     if (!trig) {
       wa = C{xk.x, xm.x};
       wb = C{xk.y, xm.y};
     } else {
-      const C cs = cx_ldg(A.mak + k);
       wa = C{cs.x * xk.x + cs.y * xm.x, cs.y * xk.x - cs.x * xm.x};
       wb = C{cs.x * xk.y + cs.y * xm.y, cs.y * xk.y - cs.x * xm.y};
     }
-    // Z_k = (wa.x - wb.y, wa.y + wb.x); swapped store
-    sm[Lay::at(c, Cfg::rev(k))] = C{wa.y + wb.x, wa.x - wb.y};
-    if (k > 0 && km != k) sm[Lay::at(c, Cfg::rev(km))] = C{wb.x - wa.y, wa.x + wb.y};
+    zk = C{wa.y + wb.x, wa.x - wb.y};   // Z_k = (wa.x - wb.y, wa.y + wb.x), stored swapped
+    zm = C{wb.x - wa.y, wa.x + wb.y};
   };
   {
     C xk[NK], xm[NK];
 #pragma unroll
-    for (int m = 0; m < NK; ++m) fetch(t + m * TPL, xk[m], xm[m]);
+    for (int m = 0; m < NK; ++m) {
+      const int kc = m * TPL, kmc = N - TPL - kc;
+      const bool kpos = kc > 0 || t > 0;
+      xm[m] = C{T(0), T(0)};
+      if (!trig) {
+        xk[m] = in_up.load(kc);
+        if (kpos) xm[m] = in_dn.load(kmc);
+      } else {
+        xk[m] = rv ? in_dn.load(kmc - 1) : in_up.load(kc);               // N - 1 - k : k
+        if (kpos) xm[m] = rv ? in_up.load(kc - 1) : in_dn.load(kmc);     // k - 1 : N - k   (X_N := 0)
+      }
+    }
 #pragma unroll
-    for (int m = 0; m < NK; ++m) scatter(t + m * TPL, xk[m], xm[m]);
+    for (int m = 0; m < NK; ++m) {
+      const int kc = m * TPL;
+      const bool kpos = kc > 0 || t > 0;
+      C cs = C{T(1), T(0)};
+      if (trig) cs = cx_ldg(mak_t + kc);
+      C zk, zm;
+      combine(cs, xk[m], xm[m], zk, zm);
+      sm[P.slot_k(kc)] = zk;
+      if (kpos) sm[P.slot_m(kc)] = zm;
+    }
     if (t == 0) {
-      C a0, a1;
-      fetch(N / 2, a0, a1);
-      scatter(N / 2, a0, a1);
+      // k = N/2: its own mirror
+      C a0, a1 = C{T(0), T(0)};
+      if (!trig) a0 = in_up.load(N / 2);
+      else {
+        a0 = in_up.load(rv ? N - 1 - N / 2 : N / 2);
+        a1 = in_up.load(rv ? N / 2 - 1 : N - N / 2);
+      }
+      C cs = C{T(1), T(0)};
+      if (trig) cs = cx_ldg(A.mak + N / 2);
+      C zk, zm;
+      combine(cs, a0, a1, zk, zm);
+      sm[Lay::at(c, Cfg::rev(N / 2))] = zk;
     }
   }
+  const RowsOut out_up = r2_rows<T, YMODE, false, FULL>(A.out, loc.oa, loc.ob, A.out_es, nullptr, loc, trig ? 2 * t : t);
+  const RowsOut out_dn = r2_rows<T, YMODE, false, FULL>(A.out, loc.oa, loc.ob, A.out_es, nullptr, loc, -2 * t);
   if (A.line_len > N && (SPLIT || A.in != A.out)) {
-    for (int i = N + t; i < A.line_len; i += TPL) {
-      const C x = get(i);
-      r2_store<T, YMODE, FULL>(A.out, loc, A.out_es, i, x.x, x.y, A.flags);
+    const RowsOut out_t = r2_rows<T, YMODE, false, FULL>(A.out, loc.oa, loc.ob, A.out_es, nullptr, loc, t);
+    for (int i = N; i + t < A.line_len; i += TPL) {
+      const C x = in_up.load(i);
+      out_t.store(i, x.x, x.y);
     }
   }
   r2_group_sync<Cfg, YMODE>(c);
@@ -609,11 +725,12 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
     for (int m = 0; m < E / R0; ++m)
 #pragma unroll
       for (int q = 0; q < R0; ++q) {
-        const int j = q * L0 + t + TPL * m;
-        const int i = r2_vperm(trig, N, j);
-        C x = v[m * R0 + q];
-        if (rv && (i & 1)) x = {-x.x, -x.y};
-        r2_store<T, YMODE, FULL>(A.out, loc, A.out_es, i, x.y, x.x, A.flags);
+        const int cj = q * L0 + TPL * m;
+        const C x = v[m * R0 + q];
+        if (!trig) out_up.store(cj, x.y, x.x);
+        else if (cj < N / 2) out_up.store(2 * cj, x.y, x.x);
+        else if (rv) out_dn.store(2 * N - 1 - 2 * cj, -x.y, -x.x);   // odd output rows change sign
+        else out_dn.store(2 * N - 1 - 2 * cj, x.y, x.x);
       }
   }
 }

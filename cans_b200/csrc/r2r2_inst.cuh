@@ -63,6 +63,7 @@ static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
   }
   if (grid < 1) return 0;
   if (grid > 0x7fffffffLL) return -2;
+  if (!YMODE && (long long)A.lines_per_group * A.ngroups > 0x7ffffff0LL) return -2;   // 32-bit line indices (r2_locate)
   const unsigned g = (unsigned)grid, b = Cfg::TPL * Cfg::G;
   // y mode: the unpredicated kernels need every column pair of every CTA to exist
   const bool full = !YMODE || (A.lines_per_group % (2 * Cfg::G)) == 0;
