@@ -1,6 +1,7 @@
 // C ABI of cans_b200 (include/cans_b200.h): context, plans, the solve.
 // Host-side orchestration only; all arithmetic lives in the kernels of
 // fft_kernels.cuh / thomas_kernels.cuh / aux_kernels.cuh.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -141,10 +142,16 @@ struct cansb200_plan {
   int q, periodic_z;
   cansb200_options opt;
   // thomas
-  int th_n, th_nn, th_m, th_variant, th_mmax, th_cols, nslots;
+  int th_n, th_nn, th_m, th_variant, th_mmax, th_cols, th_cl, nslots;
   long long slot_z, slot_den;
   DevBuf zcache, p2cache, dencache, state;
   unsigned long long solves = 0;
+  // TMA descriptors of the pipelined substitution: pivots (per plan) and right-hand sides (per field pointer / shape)
+  bool use_tma = true;
+  CUtensorMap map_z;
+  unsigned long long map_z_key[4] = {0, 0, 0, 0};
+  struct PMap { const void* p; long long sj, sk; int nx, ny, nn, box_rows; CUtensorMap m; };
+  std::vector<PMap> map_p;
 };
 
 template <class T> static std::map<int, FftTables<T>>& tabmap(cansb200_ctx* c);
@@ -368,30 +375,128 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   return D;
 }
 
-template <class T, int MMAX, bool EXACT, bool VEC, int COLS>
-static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, cudaStream_t st) {
-  auto kfn = thomas_pipe_kernel<T, MMAX, EXACT, VEC, COLS>;
+static bool thomas_is_pipelined(const cansb200_plan* pl) { return pl->th_variant == 1 || pl->th_variant == 3; }
+
+// ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point; no libcuda link) ----
+typedef CUresult (*cb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cb_encode_tiled_fn get_encode_tiled() {
+  static cb_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (cb_encode_tiled_fn)q;
+  }
+  return fn;
+}
+// tiles of {16 columns x box_rows rows}: rank 3 = (x, y, row), rank 4 adds the cache slot
+static bool encode_tile_map(CUtensorMap* m, const void* base, size_t esz, int rank, const cuuint64_t dims[4],
+                            const cuuint64_t strides_bytes[3], int box_rows) {
+  cb_encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint32_t box[4] = {16u, 1u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+  for (int d = 0; d + 1 < rank; ++d)
+    if (strides_bytes[d] % 16 != 0 || strides_bytes[d] >= (1ULL << 40)) return false;
+  if (((uintptr_t)base % 16) != 0) return false;
+  const CUtensorMapDataType dt = esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  return enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <class T>
+static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p, int box_rows, const CUtensorMap** mp,
+                            const CUtensorMap** mz) {
+  if (!pl->use_tma || D.nx < 16) return false;
+  const size_t esz = sizeof(T);
+  const unsigned long long zkey[4] = {(unsigned long long)(uintptr_t)pl->zcache.p, (unsigned long long)D.nx, (unsigned long long)D.ny,
+                                      ((unsigned long long)D.nn << 20) | (unsigned long long)box_rows};
+  if (memcmp(zkey, pl->map_z_key, sizeof(zkey)) != 0) {
+    const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nn, (cuuint64_t)pl->nslots};
+    const cuuint64_t st[3] = {(cuuint64_t)D.nx * esz, (cuuint64_t)D.nx * D.ny * esz, (cuuint64_t)pl->slot_z * esz};
+    if (!encode_tile_map(&pl->map_z, pl->zcache.p, esz, 4, dims, st, box_rows)) { pl->use_tma = false; return false; }
+    memcpy(pl->map_z_key, zkey, sizeof(zkey));
+  }
+  *mz = &pl->map_z;
+  for (auto& e : pl->map_p)
+    if (e.p == p && e.sj == D.sj && e.sk == D.sk && e.nx == D.nx && e.ny == D.ny && e.nn == D.nn && e.box_rows == box_rows) {
+      *mp = &e.m;
+      return true;
+    }
+  cansb200_plan::PMap e;
+  e.p = p; e.sj = D.sj; e.sk = D.sk; e.nx = D.nx; e.ny = D.ny; e.nn = D.nn; e.box_rows = box_rows;
+  const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nn, 1};
+  const cuuint64_t st[3] = {(cuuint64_t)D.sj * esz, (cuuint64_t)D.sk * esz, 0};
+  if (!encode_tile_map(&e.m, p, esz, 3, dims, st, box_rows)) return false;
+  if (pl->map_p.size() >= 16) pl->map_p.erase(pl->map_p.begin());
+  pl->map_p.push_back(e);
+  *mp = &pl->map_p.back().m;
+  return true;
+}
+
+template <class T, int MMAX, bool EXACT, int LDM, int COLS, int CL>
+static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, const CUtensorMap* mp,
+                       const CUtensorMap* mz, int box_rows, cudaStream_t st) {
+  auto kfn = thomas_pipe_kernel<T, MMAX, EXACT, LDM, COLS, CL>;
   const size_t smem = thomas_pipe_smem<T, MMAX, COLS>();
   static bool attr = false;
+  static int max_clusters = 0;
   if (!attr) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CL > 1) {
+      // how many CTA pairs can be resident at once (GPCs with an odd SM count leave one SM out)
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(CL * ctx->num_sms); q.blockDim = dim3(CB_TH_THREADS); q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      CK(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &q));
+      if (max_clusters < 1) return fail(CANSB200_ECUDA, "gaussel: no room for a CTA cluster");
+    }
     attr = true;
   }
   const long long tiles = (long long)((D.xn + COLS - 1) / COLS) * D.ny;
-  const unsigned grid = (unsigned)(tiles < ctx->num_sms ? tiles : ctx->num_sms);   // persistent: one CTA per SM
-  kfn<<<grid, CB_TH_THREADS, smem, st>>>(D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
-                                         (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute la[1];
+  if (CL > 1) {
+    const long long nc = tiles < max_clusters ? tiles : max_clusters;   // persistent: one cluster per SM pair
+    cfg.gridDim = dim3((unsigned)(nc * CL));
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    cfg.attrs = la; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3((unsigned)(tiles < ctx->num_sms ? tiles : ctx->num_sms));   // persistent: one CTA per SM
+  }
+  cfg.blockDim = dim3(CB_TH_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  static const CUtensorMap dummy = {};
+  CK(cudaLaunchKernelEx(&cfg, kfn, D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
+                        (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm, mp ? *mp : dummy, mz ? *mz : dummy, box_rows));
   ctx->launches++;
-  CK(cudaGetLastError());
   return 0;
 }
 
-template <class T, int MMAX, int COLS>
-static int launch_pipe_sel(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, bool exact, bool vec,
+template <class T, int MMAX, int COLS, int CL>
+static int launch_pipe_sel(cansb200_ctx* ctx, const ThomasDev<T>& D, cansb200_plan* pl, T* p, T norm, bool exact, bool vec,
                            cudaStream_t st) {
-  if (exact && vec) return launch_pipe<T, MMAX, true, true, COLS>(ctx, D, pl, p, norm, st);
-  if (vec) return launch_pipe<T, MMAX, false, true, COLS>(ctx, D, pl, p, norm, st);
-  return launch_pipe<T, MMAX, false, false, COLS>(ctx, D, pl, p, norm, st);
+  if (exact && vec && COLS == 16 && pl->th_variant != 3) {
+    // TMA boxes of 256 / 128 / 64 rows, whichever divides the rows of one CTA
+    const int rows = (CB_TH_THREADS / COLS) * MMAX;
+    const int box_rows = rows % 256 == 0 ? 256 : (rows % 128 == 0 ? 128 : 64);
+    const CUtensorMap *mp = nullptr, *mz = nullptr;
+    if (thomas_tma_maps<T>(pl, D, p, box_rows, &mp, &mz))
+      return launch_pipe<T, MMAX, true, CB_TH_LD_TMA, COLS, CL>(ctx, D, pl, p, norm, mp, mz, box_rows, st);
+  }
+  if (exact && vec) return launch_pipe<T, MMAX, true, CB_TH_LD_VEC, COLS, CL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
+  if (vec) return launch_pipe<T, MMAX, false, CB_TH_LD_VEC, COLS, CL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
+  return launch_pipe<T, MMAX, false, CB_TH_LD_ELEM, COLS, CL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
 }
 
 // pivot cache: content hash of (a, b, c, lambda) -> slot select -> factorisation on a miss
@@ -415,18 +520,21 @@ template <class T> static int gaussel_prepare(cansb200_plan* pl, const ThomasDev
 template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T>& D, T* p, T norm, cudaStream_t st) {
   cansb200_ctx* ctx = pl->ctx;
   CacheState* cs = (CacheState*)pl->state.p;
-  if (pl->th_variant == 1) {
+  if (thomas_is_pipelined(pl)) {
     // 16-byte tile copies need every row segment aligned: even (FP64) / multiple-of-4 (FP32) column counts and offsets
     const long long vw = 16 / (long long)sizeof(T);
     const bool vec = (D.nx % vw) == 0 && (D.xb % vw) == 0 && (D.sk % vw) == 0 && ((uintptr_t)p % 16) == 0 &&
                      ((uintptr_t)pl->zcache.p % 16) == 0 && (pl->slot_z % vw) == 0 && (D.xn % vw) == 0;
     const bool exact = D.m == pl->th_mmax;
-    if (pl->th_cols == 16) {
-      if (pl->th_mmax == 4) return launch_pipe_sel<T, 4, 16>(ctx, D, pl, p, norm, exact, vec, st);
-      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16>(ctx, D, pl, p, norm, exact, vec, st);
+    if (pl->th_cols == 16 && pl->th_cl == 1) {
+      if (pl->th_mmax == 4) return launch_pipe_sel<T, 4, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
+      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
+    } else if (pl->th_cols == 16 && pl->th_cl == 2) {
+      if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 16, 2>(ctx, D, pl, p, norm, exact, vec, st);
+      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16, 2>(ctx, D, pl, p, norm, exact, vec, st);
     } else if (pl->th_cols == 8) {
-      if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 8>(ctx, D, pl, p, norm, exact, vec, st);
-      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 8>(ctx, D, pl, p, norm, exact, vec, st);
+      if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 8, 1>(ctx, D, pl, p, norm, exact, vec, st);
+      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 8, 1>(ctx, D, pl, p, norm, exact, vec, st);
     }
     return fail(CANSB200_EUNSUPPORTED, "gaussel: no pipelined kernel for this chunk length");
   }
@@ -719,14 +827,22 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   pl->th_n = ctx->ng[2] - pl->q;
   pl->th_nn = pl->periodic_z ? pl->th_n - 1 : pl->th_n;
   if (pl->th_nn < 1) return fail(CANSB200_EINVAL, "plan_create: z system is empty");
-  // pipelined substitution: 16 columns x 64 chunks up to 512 rows, 8 columns x 128 chunks up to 1024 rows
-  pl->th_cols = pl->th_nn <= 512 ? 16 : 8;
-  const int chunks = CB_TH_THREADS / pl->th_cols;
-  pl->th_m = (pl->th_nn + chunks - 1) / chunks;
+  // pipelined substitution: 16 columns x 64 chunks up to 512 rows; up to 1024 rows a cluster of two CTAs shares
+  // the 16-column tile (variant 1) or one CTA takes 8 columns x 128 chunks (variant 2, and periodic z)
   int variant = o.thomas_variant >= 0 ? o.thomas_variant : 1;
+  pl->th_cols = 16;
+  pl->th_cl = 1;
+  if (pl->th_nn > 512) {
+    if (variant == 1 && !pl->periodic_z) pl->th_cl = 2;
+    else pl->th_cols = 8;
+  }
+  if (variant == 2) variant = 1;
+  if (variant > 3) variant = 1;   // 3 = as 1, tiles fetched with cp.async instead of TMA
+  const int chunks = CB_TH_THREADS / pl->th_cols * pl->th_cl;   // chunks per column over the whole cluster
+  pl->th_m = (pl->th_nn + chunks - 1) / chunks;
   if (pl->th_m > 8) variant = 0;   // nz > 1024: the sequential kernel
   pl->th_variant = variant;
-  pl->th_mmax = pl->th_cols == 16 ? (pl->th_m <= 4 ? 4 : 8) : (pl->th_m <= 6 ? 6 : 8);
+  pl->th_mmax = (pl->th_cols == 16 && pl->th_cl == 1) ? (pl->th_m <= 4 ? 4 : 8) : (pl->th_m <= 6 ? 6 : 8);
   pl->nslots = o.cache_slots >= 1 ? (o.cache_slots > CB_MAX_SLOTS ? CB_MAX_SLOTS : o.cache_slots) : 1;
   const long long ncol = (long long)ctx->n_z[0] * ctx->n_z[1];
   pl->slot_z = ncol * pl->th_nn;
@@ -844,7 +960,7 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
   rc = gaussel_prepare<T>(pl, D, st);
   if (rc) return rc;
   prof_mark(ctx, st);
-  if (pl->th_variant == 1) {
+  if (thomas_is_pipelined(pl)) {
     rc = gaussel_apply<T>(pl, D, Cz, (T)normfft, st);
     if (rc) return rc;
     if (pl->th_n < nz) {   // face-centred Dirichlet: the last plane is not part of the system but still travels back
@@ -921,7 +1037,7 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   prof_mark(ctx, st);
   R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nz, ny, 1};
   const int W = ctx->chain_cols;
-  if (W > 0 && W < nx && pl->th_variant == 1 && !ctx->profiling) {
+  if (W > 0 && W < nx && thomas_is_pipelined(pl) && !ctx->profiling) {
     // ---- L2-resident chain over x windows, round-robin on auxiliary streams
     ThomasDev<T> D = make_thomas<T>(pl, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, lam, a, b, c);
     rc = gaussel_prepare<T>(pl, D, st);

@@ -20,6 +20,7 @@
 //       scan of the affine maps, fix-up).  p' never leaves the chip: traffic
 //       is read p + read z + write p = 24 B/pt instead of 48.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -269,11 +270,68 @@ __device__ __forceinline__ float shfl_up_t(float v, int d) { return __shfl_up_sy
 __device__ __forceinline__ double shfl_down_t(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ float shfl_down_t(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers: one elected thread fetches a whole tile ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a byte-count mismatch must trap, not hang the device
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  for (unsigned it = 0;; ++it) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (it > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// ---- thread-block cluster helpers (two CTAs share one column tile when nz > 512) ----
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store v into the shared memory of CTA `rank` of the cluster, at the address that `local` has in this CTA
+template <class T> __device__ __forceinline__ void dsmem_store(T* local, unsigned rank, T v);
+template <> __device__ __forceinline__ void dsmem_store<double>(double* local, unsigned rank, double v) {
+  const unsigned la = (unsigned)__cvta_generic_to_shared(local);
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+template <> __device__ __forceinline__ void dsmem_store<float>(float* local, unsigned rank, float v) {
+  const unsigned la = (unsigned)__cvta_generic_to_shared(local);
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
 // Fold of the CHUNKS chunk maps v -> Y_g + P_g v of every column: warp w < COLS owns column w, lane l owns
 // the CPL = CHUNKS / 32 consecutive chunks l*CPL ..; Kogge-Stone scan of the lane aggregates with shuffles;
 // result = value entering each chunk, written over sY.  FWD: chunk 0 upward; otherwise the last chunk downward.
-template <class T, bool FWD, int COLS, int CHUNKS>
-__device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid) {
+// `cin` (indexed by column) is the value entering the first chunk in application order (nullptr = 0); the value
+// leaving the last one is handed to `agg(column, value)`.
+template <class T, bool FWD, int COLS, int CHUNKS, class Agg>
+__device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid, const T* cin, Agg agg) {
   constexpr int LD = CHUNKS + 1, CPL = CHUNKS / 32;
   static_assert(CHUNKS % 32 == 0, "chunks per column must be a multiple of the warp size");
   const int w = tid >> 5, lane = tid & 31;
@@ -299,8 +357,13 @@ __device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid) {
       const bool on = FWD ? (lane >= d) : (lane + d < 32);
       if (on) { Y = fma(P, Yp, Y); P *= Pp; }
     }
+    const T c0 = cin ? cin[w] : T(0);
+    const bool last = FWD ? (lane == 31) : (lane == 0);
+    if (last) agg(w, fma(P, c0, Y));
     T vin = FWD ? shfl_up_t(Y, 1) : shfl_down_t(Y, 1);
-    if (FWD ? (lane == 0) : (lane == 31)) vin = T(0);
+    const T pex = FWD ? shfl_up_t(P, 1) : shfl_down_t(P, 1);
+    if (FWD ? (lane == 0) : (lane == 31)) vin = c0;
+    else vin = fma(pex, c0, vin);
 #pragma unroll
     for (int s = 0; s < CPL; ++s) {
       const int q = FWD ? s : CPL - 1 - s;
@@ -312,22 +375,38 @@ __device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid) {
 
 // EXACT: the rows per chunk equal MMAX (no per-row predicates in the sweeps).
 // VEC: columns come in aligned 16-byte groups, so the tile copies use 16-byte cp.async.
-template <class T, int MMAX, bool EXACT, bool VEC, int COLS>
+// CL = 2: a cluster of two CTAs shares one tile of COLS columns; CTA `rank` owns the rows
+// [rank CHUNKS m, (rank + 1) CHUNKS m) and the two folds hand their carry across through distributed shared
+// memory (forward: rank 0 -> 1, backward: rank 1 -> 0), so 16-column (128-byte) rows reach nz = 1024.
+// LDM: how a tile reaches shared memory.  0 = element-wise cp.async (any alignment), 1 = 16-byte cp.async,
+// 2 = TMA: one thread issues cp.async.bulk.tensor boxes of {COLS columns x box_rows rows} of the right-hand side
+// (3-D map: x, y, row) and of the cached pivots (4-D map: x, y, row, cache slot), completion on an mbarrier;
+// out-of-range rows / columns arrive as zeros (the identity chunk maps the padding needs).
+#define CB_TH_LD_ELEM 0
+#define CB_TH_LD_VEC 1
+#define CB_TH_LD_TMA 2
+template <class T, int MMAX, bool EXACT, int LDM, int COLS, int CL>
 __global__ void __launch_bounds__(CB_TH_THREADS, 1)
 thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, const T* p2base, const T* denbase,
-                   long long slot_z, long long slot_den, T* p, T norm) {
+                   long long slot_z, long long slot_den, T* p, T norm, const __grid_constant__ CUtensorMap map_p,
+                   const __grid_constant__ CUtensorMap map_z, int box_rows) {
+  constexpr bool VEC = LDM == CB_TH_LD_VEC;
+  constexpr bool TMA = LDM == CB_TH_LD_TMA;
   constexpr int NT = CB_TH_THREADS;
   constexpr int CHUNKS = NT / COLS;
   constexpr int LD = CHUNKS + 1;
   constexpr int CSA = MMAX + 2;                     // chunk stride of the a/c tables (16-byte aligned, bank spread)
   constexpr int VW = 16 / sizeof(T);                // elements per 16-byte piece
-  extern __shared__ __align__(16) unsigned char cb_smem_raw[];
+  extern __shared__ __align__(128) unsigned char cb_smem_raw[];
   T* zs = reinterpret_cast<T*>(cb_smem_raw);        // [row][COLS] pivots of the tile in flight / being consumed
   T* ps = zs + (size_t)MMAX * NT;                   // [row][COLS] right-hand side
   T* sa = ps + (size_t)MMAX * NT;                   // a_k at [g][r]
   T* sc = sa + CHUNKS * CSA;                        // c_k
   T* sY = sc + CHUNKS * CSA;                        // [c][g] chunk value, row stride CHUNKS + 1
   T* sP = sY + COLS * LD;                           // [c][g] chunk product
+  __shared__ T xchg[2][COLS];                       // carries handed over by the other CTA of the cluster
+  __shared__ __align__(8) unsigned long long tile_bar;   // TMA: completion barrier of the tile in flight
+  const unsigned rank = CL > 1 ? cluster_ctarank() : 0u;
   const int tid = threadIdx.x, c = tid & (COLS - 1), g = tid / COLS;
   const int m = EXACT ? MMAX : D.m, nn = D.nn;
   const int nrows_tile = CHUNKS * m;
@@ -336,15 +415,25 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   const int tiles_x = (D.xn + COLS - 1) / COLS;
   const int ntiles = tiles_x * D.ny;
   const int sel = st->sel;
-  const int k0 = g * m;
+  const int rbase = (int)rank * nrows_tile;         // first row of this CTA
+  const int k0 = rbase + g * m;
   const int nrow_full = nn - k0 < 0 ? 0 : (nn - k0 < m ? nn - k0 : m);   // my rows inside the system
   const T* zsel = zbase + (long long)sel * slot_z;
 
   for (int e = tid; e < nrows_tile; e += NT) {
     const int ge = e / m, re = e - ge * m;
-    sa[ge * CSA + re] = (e < nn) ? D.a[e] : T(0);
-    sc[ge * CSA + re] = (e < nn) ? D.c[e] : T(0);
+    sa[ge * CSA + re] = (rbase + e < nn) ? D.a[rbase + e] : T(0);
+    sc[ge * CSA + re] = (rbase + e < nn) ? D.c[rbase + e] : T(0);
   }
+
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(&tile_bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+  }
+  unsigned tile_phase = 0;
 
   // tile -> (flat column of its first thread, live columns)
   auto tile_col0 = [&](int tile, int& ncols) -> long long {
@@ -355,16 +444,29 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   };
   // asynchronous copy of one tile of pivots and right-hand sides into [row][COLS]; rows >= nn and dead
   // columns are zero filled so that the chunk maps of padding rows are exact identities / zeros
-  auto prefetch = [&](long long col0, int ncols) {
+  auto prefetch = [&](int tile_i, long long col0, int ncols) {
+    if (TMA) {
+      if (tid == 0) {
+        const int tj = tile_i / tiles_x;
+        const int x0 = D.xb + (tile_i - tj * tiles_x) * COLS;
+        fence_proxy_async();   // the generic-proxy reads of the previous tile are ordered before the async writes
+        mbar_expect_tx(&tile_bar, (unsigned)(2u * nrows_tile * COLS * sizeof(T)));
+        for (int r0 = 0; r0 < nrows_tile; r0 += box_rows) {
+          tma_load_3d(ps + r0 * COLS, &map_p, &tile_bar, x0, tj, rbase + r0);
+          tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, x0, tj, rbase + r0, sel);
+        }
+      }
+      return;
+    }
     if (VEC) {
       constexpr int PPR = COLS / VW;                // pieces per row
       for (int q = tid; q < nrows_tile * PPR; q += NT) {
         const int row = q / PPR, pc = (q - row * PPR) * VW;
         T* zd = zs + row * COLS + pc;
         T* pd = ps + row * COLS + pc;
-        if (row < nn && pc < ncols) {
-          cp_async_16(zd, zsel + (long long)row * ncol + col0 + pc);
-          cp_async_16(pd, p + (long long)row * sk + col0 + pc);
+        if (rbase + row < nn && pc < ncols) {
+          cp_async_16(zd, zsel + (long long)(rbase + row) * ncol + col0 + pc);
+          cp_async_16(pd, p + (long long)(rbase + row) * sk + col0 + pc);
         } else {
 #pragma unroll
           for (int e = 0; e < VW; ++e) { zd[e] = T(0); pd[e] = T(0); }
@@ -373,9 +475,9 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     } else {
       for (int q = tid; q < nrows_tile * COLS; q += NT) {
         const int row = q / COLS, pc = q - row * COLS;
-        if (row < nn && pc < ncols) {
-          cp_async_elem(zs + q, zsel + (long long)row * ncol + col0 + pc);
-          cp_async_elem(ps + q, p + (long long)row * sk + col0 + pc);
+        if (rbase + row < nn && pc < ncols) {
+          cp_async_elem(zs + q, zsel + (long long)(rbase + row) * ncol + col0 + pc);
+          cp_async_elem(ps + q, p + (long long)(rbase + row) * sk + col0 + pc);
         } else {
           zs[q] = T(0);
           ps[q] = T(0);
@@ -385,20 +487,27 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     cp_async_commit();
   };
 
-  int tile = blockIdx.x;
-  if (tile >= ntiles) return;
+  const int tstride = (int)gridDim.x / CL;
+  int tile = (int)blockIdx.x / CL;
+  if (tile >= ntiles) return;   // both CTAs of a cluster leave together
   int ncols;
   long long col0 = tile_col0(tile, ncols);
-  prefetch(col0, ncols);
-  for (; tile < ntiles; tile += gridDim.x) {
-    cp_async_wait<0>();
+  prefetch(tile, col0, ncols);
+  auto no_agg = [](int, T) {};
+  for (; tile < ntiles; tile += tstride) {
+    if (TMA) {
+      mbar_wait(&tile_bar, tile_phase);
+      tile_phase ^= 1u;
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();   // this tile has landed (copies of all threads); also orders the previous tile's sY reads
     T y[MMAX], z[MMAX];
 #pragma unroll
     for (int r = 0; r < MMAX; ++r)
       if (EXACT || r < m) {
-        y[r] = ps[(k0 + r) * COLS + c];
-        z[r] = zs[(k0 + r) * COLS + c];
+        y[r] = ps[(g * m + r) * COLS + c];
+        z[r] = zs[(g * m + r) * COLS + c];
       }
     const bool live = c < ncols;
     const int nrow = live ? nrow_full : 0;
@@ -418,14 +527,21 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     sY[c * LD + g] = yy;
     sP[c * LD + g] = pi;
     __syncthreads();   // every thread holds its tile values in registers: the tile buffers are free again
-    const int tnext = tile + gridDim.x;
+    const int tnext = tile + tstride;
     int ncols_n = 0;
     long long col0_n = 0;
     if (tnext < ntiles) {
       col0_n = tile_col0(tnext, ncols_n);
-      prefetch(col0_n, ncols_n);
+      prefetch(tnext, col0_n, ncols_n);
     }
-    thomas_fold<T, true, COLS, CHUNKS>(sY, sP, tid);
+    if (CL == 1) {
+      thomas_fold<T, true, COLS, CHUNKS>(sY, sP, tid, (const T*)nullptr, no_agg);
+    } else {
+      // forward carry: rank 0 folds first and hands the value leaving its last row to rank 1
+      if (rank == 0) thomas_fold<T, true, COLS, CHUNKS>(sY, sP, tid, (const T*)nullptr, [&](int w, T v) { dsmem_store(&xchg[0][w], 1u, v); });
+      cluster_sync_all();
+      if (rank == 1) thomas_fold<T, true, COLS, CHUNKS>(sY, sP, tid, (const T*)xchg[0], no_agg);
+    }
     __syncthreads();
     T vin = sY[c * LD + g];
     pi = T(1);
@@ -450,7 +566,14 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     sY[c * LD + g] = xx;   // own slot: only this thread read it since the fold
     sP[c * LD + g] = rho;
     __syncthreads();
-    thomas_fold<T, false, COLS, CHUNKS>(sY, sP, tid);
+    if (CL == 1) {
+      thomas_fold<T, false, COLS, CHUNKS>(sY, sP, tid, (const T*)nullptr, no_agg);
+    } else {
+      // backward carry: rank 1 folds first and hands the value leaving its first row to rank 0
+      if (rank == 1) thomas_fold<T, false, COLS, CHUNKS>(sY, sP, tid, (const T*)nullptr, [&](int w, T v) { dsmem_store(&xchg[1][w], 0u, v); });
+      cluster_sync_all();
+      if (rank == 0) thomas_fold<T, false, COLS, CHUNKS>(sY, sP, tid, (const T*)xchg[1], no_agg);
+    }
     __syncthreads();
     vin = sY[c * LD + g];
     rho = T(1);
@@ -461,8 +584,8 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         y[r] = fma(rho, vin, y[r]);
       }
     }
-    if (D.periodic) {
-      // closure value and rank-one correction, src/solver.f90:272-306
+    if (CL == 1 && D.periodic) {
+      // closure value and rank-one correction (clusters: the host never pairs CTAs on a periodic system), src/solver.f90:272-306
       __syncthreads();
       const int kl = nn - 1;
       if (g == 0) sY[c] = y[0];                  // x_1

@@ -43,7 +43,9 @@ enum { CANSB200_MEM_HOST = 0, CANSB200_MEM_DEVICE = 1 };
 
 /* Tunables; negative = library default.  Read once by cansb200_plan_create. */
 typedef struct cansb200_options {
-  int thomas_variant;   /* 0 = sequential two-sweep (any nz), 1 = pipelined chunk-parallel on-chip (nz <= 1024) */
+  int thomas_variant;   /* 0 = sequential two-sweep (any nz); 1 = pipelined chunk-parallel on-chip (nz <= 1024; above 512 rows a cluster
+                           of two CTAs shares each 16-column tile); 2 = as 1 but 8-column tiles instead of clusters above 512 rows;
+                           3 = as 1 but the tiles are fetched with cp.async instead of TMA (cp.async.bulk.tensor) */
   int cache_slots;      /* factorisation cache entries per plan (1..8); Helmholtz plans want 3 */
   int fft_x_lines;      /* lines per tile of the contiguous transforms (0 = auto) */
   int fft_y_lines;      /* 8 or 16: x-width of the strided-transform tile (0 = auto) */

@@ -28,6 +28,12 @@ CASES = {
     "nz_1024": ([10, 8, 1024], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float64),
     "nz_1000_periodic": ([8, 6, 1000], [1.0, 1.0, 1.0], [P, P, P], C3, 0.0, np.float64),
     "nz_gt_1024": ([8, 8, 1100], [1.0, 1.0, 2.0], [P, P, D], C3, 1.0, np.float64),
+    # shapes that take the TMA tile path of the pipelined Thomas kernel (full chunks, >= 16 even columns);
+    # 40 columns = 2.5 tiles (out-of-range columns), 257 periodic rows = 256-row system + closure row
+    "nz_512_tma": ([48, 6, 512], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    "nz_257_periodic_tma": ([40, 4, 257], [1.0, 1.0, 1.0], [P, P, P], C3, 0.0, np.float64),
+    "nz_1024_tma_cluster": ([32, 4, 1024], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    "fp32_nz_512_tma": ([32, 4, 512], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float32),
     # implicit-diffusion (Helmholtz) operators: face-centred in one direction, Dirichlet walls
     "helm_u_face_x": ([16, 12, 20], [1.0, 1.0, 1.0], [D, D, D], ["f", "c", "c"], 1.0, np.float64),
     "helm_v_face_y": ([16, 12, 20], [1.0, 1.0, 1.0], [P, D, D], ["c", "f", "c"], 1.0, np.float64),

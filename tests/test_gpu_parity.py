@@ -107,9 +107,11 @@ def test_r2r_partial_length_leaves_tail(cb, S):
         assert np.abs(xd.cpu().numpy() - ref).max() < 1e-13
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("name", ["C1_ldc_2x64x64", "C2s_triperiodic", "C3s_channel", "periodic_z_odd", "tiny_z",
-                                  "nz_gt_512", "helm_w_face_z", "dirichlet_xyz"])
+                                  "nz_gt_512", "nz_768_duct", "nz_1024", "nz_1000_periodic", "nz_gt_1024",
+                                  "nz_512_tma", "nz_257_periodic_tma", "nz_1024_tma_cluster",
+                                  "helm_w_face_z", "dirichlet_xyz"])
 def test_gaussel_stage(cb, S, name, variant):
     """cansb200_gaussel == gaussel (src/solver.f90:114-307): pivot pin, periodic closure, q = 1."""
     cs = cases.build_case(name)
