@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--chain-streams", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-chunks", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -320,6 +321,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         nb = int(np.prod(shp)) * 8
+        if world == 1:
+            ctx.set_host_chunks(args.host_chunks)
+            if args.host_chunks > 1:   # chunked pipeline: only the interior z planes travel (halo planes are never read)
+                nb = nl[2] * shp[1] * shp[2] * 8
         ph = torch.empty(shp, dtype=torch.float64).pin_memory()
         ph.copy_(p)
         pn = ph.numpy()
@@ -338,7 +343,8 @@ def main():
             el = float(t.item())
         e2e = {"value": el / ne2e * 1e9 / total_pts, "unit": UNIT,
                "h2d_bytes_per_step": (nb + 8 * (3 * ng[2] + ctx.n_z[0] * ctx.n_z[1])) * world,
-               "d2h_bytes_per_step": nb * world, "steps": ne2e, "ms_per_step": el / ne2e * 1e3}
+               "d2h_bytes_per_step": nb * world, "steps": ne2e, "ms_per_step": el / ne2e * 1e3,
+               "host_chunks": args.host_chunks if world == 1 else 1}
         del ph
 
     cpu = None

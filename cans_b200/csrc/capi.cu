@@ -119,6 +119,11 @@ struct cansb200_ctx {
   std::vector<cudaEvent_t> aux_done;
   cudaEvent_t fork_ev = nullptr;
   unsigned long long launches = 0;
+  // host-memory mode: the z planes travel in chunks on two copy streams so that the x / y transforms of a chunk
+  // overlap the PCIe transfer of the others (only the tridiagonal stage needs the whole field)
+  int host_chunks = 16;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;   // 7 events per profiled solve
@@ -739,6 +744,9 @@ int cansb200_finalize(cansb200_ctx* c) {
   for (cudaStream_t q : c->aux) cudaStreamDestroy(q);
   for (cudaEvent_t q : c->aux_done) cudaEventDestroy(q);
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  for (cudaEvent_t q : c->chunk_ev) cudaEventDestroy(q);
   for (auto& kv : c->r2tabs64) { for (int q = 0; q < 4; ++q) cudaFree(kv.second.tw[q]); cudaFree(kv.second.mak); }
   for (auto& kv : c->r2tabs32) { for (int q = 0; q < 4; ++q) cudaFree(kv.second.tw[q]); cudaFree(kv.second.mak); }
   for (auto& kv : c->dtabs64) cudaFree(kv.second.cs);
@@ -774,6 +782,11 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
   if (what == CANSB200_CTX_X_VARIANT || what == CANSB200_CTX_Y_VARIANT) {
     if (value < 0 || value > 3) return fail(CANSB200_EINVAL, "ctx_set: variant must be 0..3");
     c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_HOST_CHUNKS) {
+    if (value < 1 || value > 64) return fail(CANSB200_EINVAL, "ctx_set: host_chunks must be 1..64");
+    c->host_chunks = value;
     return 0;
   }
   if (what == CANSB200_CTX_R2_FLAGS) {
@@ -1002,19 +1015,77 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   const size_t nh = (size_t)px * py * (nz + 2);
   T* p = (T*)p_any;
   const T *lam = (const T*)lam_any, *a = (const T*)a_any, *b = (const T*)b_any, *c = (const T*)c_any;
+  // host-memory mode, one rank: chunked copies overlapped with the transforms (see cansb200_ctx::host_chunks)
+  const bool chunked = mem_kind == CANSB200_MEM_HOST && ctx->nranks == 1 && ctx->host_chunks > 1 && nz >= 2 && !ctx->profiling &&
+                       !(ctx->chain_cols > 0 && ctx->chain_cols < nx);
+  const size_t plane = (size_t)px * py;
   if (mem_kind == CANSB200_MEM_HOST) {
     if (ctx->staging.ensure(nh * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: staging");
     const size_t nzg = (size_t)ctx->n_z[2], nlam = (size_t)ctx->n_z[0] * ctx->n_z[1];   // a, b, c(n_z(3)); lambdaxy(n_z(1), n_z(2))
     const size_t ncoef = 3 * nzg + nlam;
     if (ctx->coef.ensure(ncoef * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: coefficient staging");
     T* cf = (T*)ctx->coef.p;
-    CK(cudaMemcpyAsync(ctx->staging.p, p_any, nh * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (!chunked) CK(cudaMemcpyAsync(ctx->staging.p, p_any, nh * sizeof(T), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(cf, a_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(cf + nzg, b_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(cf + 2 * nzg, c_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(cf + 3 * nzg, lam_any, nlam * sizeof(T), cudaMemcpyHostToDevice, st));
     p = (T*)ctx->staging.p;
     a = cf; b = cf + nzg; c = cf + 2 * nzg; lam = cf + 3 * nzg;
+  }
+  if (chunked) {
+    const int nch = ctx->host_chunks < nz ? ctx->host_chunks : nz;
+    if (!ctx->h2d_stream) CK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    if (!ctx->d2h_stream) CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    while ((int)ctx->chunk_ev.size() < 2 * nch + 1) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->chunk_ev.push_back(e);
+    }
+    T* A = (T*)ctx->scratch.p;
+    T* hp = (T*)p_any;
+    // the copy stream starts after whatever the caller's stream has queued
+    CK(cudaEventRecord(ctx->chunk_ev[2 * nch], st));
+    CK(cudaStreamWaitEvent(ctx->h2d_stream, ctx->chunk_ev[2 * nch], 0));
+    int rc;
+    auto k_lo = [&](int q) { return (int)((long long)nz * q / nch); };
+    for (int q = 0; q < nch; ++q) {
+      const int k0 = k_lo(q), k1 = k_lo(q + 1), nk = k1 - k0;
+      // interior planes k0+1 .. k1 of the haloed array (whole xy planes, x / y halos included)
+      CK(cudaMemcpyAsync(p + (size_t)(k0 + 1) * plane, hp + (size_t)(k0 + 1) * plane, (size_t)nk * plane * sizeof(T),
+                         cudaMemcpyHostToDevice, ctx->h2d_stream));
+      CK(cudaEventRecord(ctx->chunk_ev[q], ctx->h2d_stream));
+      CK(cudaStreamWaitEvent(st, ctx->chunk_ev[q], 0));
+      T* pin = p + ((size_t)(k0 + 1) * plane + px + 1);
+      T* Aq = A + (size_t)k0 * nx * ny;
+      R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nk, nx, 0};
+      rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, Aq, gx, pl->opt.fft_x_lines, st);
+      if (rc) return rc;
+      R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nk, ny, 1};
+      rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], Aq, Aq, gy, pl->opt.fft_y_lines, st);
+      if (rc) return rc;
+    }
+    rc = run_gaussel<T>(pl, A, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, (T)normfft, lam, a, b, c, st);
+    if (rc) return rc;
+    for (int q = 0; q < nch; ++q) {
+      const int k0 = k_lo(q), k1 = k_lo(q + 1), nk = k1 - k0;
+      T* pin = p + ((size_t)(k0 + 1) * plane + px + 1);
+      T* Aq = A + (size_t)k0 * nx * ny;
+      R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nk, ny, 1};
+      rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], Aq, Aq, gy, pl->opt.fft_y_lines, st);
+      if (rc) return rc;
+      R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nk, nx, 0};
+      rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], Aq, pin, gxb, pl->opt.fft_x_lines, st);
+      if (rc) return rc;
+      CK(cudaEventRecord(ctx->chunk_ev[nch + q], st));
+      CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->chunk_ev[nch + q], 0));
+      CK(cudaMemcpyAsync(hp + (size_t)(k0 + 1) * plane, p + (size_t)(k0 + 1) * plane, (size_t)nk * plane * sizeof(T),
+                         cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    CK(cudaStreamSynchronize(ctx->d2h_stream));
+    CK(cudaStreamSynchronize(st));
+    pl->solves++;
+    return 0;
   }
   if (ctx->nranks > 1) {
     const int rcd = solve_dist<T>(pl, p, n, normfft, lam, a, b, c, st);

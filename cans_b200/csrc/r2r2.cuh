@@ -427,7 +427,9 @@ template <class T, class Cfg, bool YMODE, int S>
 __device__ __forceinline__ void r2_dif_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T>& A, int c, int t) {
   using Lay = R2Lay<T, Cfg, YMODE>;
   constexpr int Rs = Cfg::R(S), Ns = Cfg::Ns(S), L = Ns / Rs, NB = Cfg::E / Rs, TPL = Cfg::TPL;
-  constexpr bool POW2 = (Cfg::N & (Cfg::N - 1)) == 0;
+  // the slot splits into a per-thread and a compile-time part: always for power-of-two plans (disjoint bit
+  // fields), and in y mode (plain index, no swizzle) whenever L and TPL divide one another
+  constexpr bool POW2 = ((Cfg::N & (Cfg::N - 1)) == 0) || (YMODE && (L >= TPL ? L % TPL == 0 : TPL % L == 0));
   const int et = Lay::enc(r2_stage_tpos<Cfg, S>(t));
 #pragma unroll
   for (int m = 0; m < NB; ++m) {
@@ -458,7 +460,7 @@ template <class T, class Cfg, bool YMODE, int S>
 __device__ __forceinline__ void r2_dit_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T>& A, int c, int t) {
   using Lay = R2Lay<T, Cfg, YMODE>;
   constexpr int Rs = Cfg::R(S), Ns = Cfg::Ns(S), L = Ns / Rs, NB = Cfg::E / Rs, TPL = Cfg::TPL;
-  constexpr bool POW2 = (Cfg::N & (Cfg::N - 1)) == 0;
+  constexpr bool POW2 = ((Cfg::N & (Cfg::N - 1)) == 0) || (YMODE && (L >= TPL ? L % TPL == 0 : TPL % L == 0));
   const int et = Lay::enc(r2_stage_tpos<Cfg, S>(t));
 #pragma unroll
   for (int m = 0; m < NB; ++m) {

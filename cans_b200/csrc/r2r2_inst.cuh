@@ -33,7 +33,10 @@ namespace cb {
   X(1024, 1, 128, 4, 2, 8, 8, 4, 4)   \
   X(2048, 0, 128, 4, 1, 16, 16, 8, 1) \
   X(384, 0, 32, 8, 1, 12, 4, 4, 2)    \
-  X(768, 0, 64, 4, 3, 12, 4, 4, 4)
+  X(768, 0, 32, 8, 2, 12, 8, 8, 1)    \
+  X(768, 1, 64, 8, 2, 12, 4, 4, 4)    \
+  X(768, 2, 64, 4, 3, 12, 4, 4, 4)    \
+  X(768, 3, 32, 4, 4, 12, 8, 8, 1)
 
 extern int g_r2_default_carveout;
 

@@ -117,6 +117,10 @@ class Context:
         allocation, 2 = streaming stores, 4 = force the maximum shared-memory carveout."""
         check(lib.cansb200_ctx_set(self._h, 5, int(flags)), "ctx_set")
 
+    def set_host_chunks(self, n: int = 16):
+        """Host-memory solves: number of z-plane chunks whose copies overlap the transforms (1 = one copy each way)."""
+        check(lib.cansb200_ctx_set(self._h, 6, int(n)), "ctx_set")
+
     def set_chain(self, cols: int = 0, streams: int = 2):
         """L2-resident fft-y -> tridiagonal -> ifft-y chain over x windows of `cols` columns (0 = off)."""
         check(lib.cansb200_ctx_set(self._h, 3, int(cols)), "ctx_set")

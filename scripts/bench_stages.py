@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-thomas", action="store_true")
+    ap.add_argument("--check", action="store_true")
     args = ap.parse_args()
     ng = args.grid
     dev = torch.device("cuda:0")
@@ -62,6 +63,18 @@ def main():
         for kname in args.kinds.split(","):
             for var in range(args.variants):
                 ctx.set_variant(var if axis == 0 else 0, var if axis == 1 else 0)
+                if args.check:
+                    # every variant must reproduce variant 0 on the same input (a small slab is enough)
+                    small = [ng[0], ng[1], 4]
+                    cs = cb.Context(small, is_fp32=args.fp32)
+                    x0 = torch.rand((4, ng[1], ng[0]), dtype=dt, device=dev) - 0.5
+                    a0, a1 = x0.clone(), x0.clone()
+                    cs.set_variant(0, 0)
+                    S.r2r(cs, KINDS[kname], n, axis, a0)
+                    cs.set_variant(var if axis == 0 else 0, var if axis == 1 else 0)
+                    S.r2r(cs, KINDS[kname], n, axis, a1)
+                    err = float((a1 - a0).abs().max() / a0.abs().max())
+                    assert err < (1e-5 if args.fp32 else 1e-13), (kname, axis, var, err)
                 ms = timeit(lambda: S.r2r(ctx, KINDS[kname], n, axis, arr), args.reps)
                 rows.append((f"r2r axis={axis} n={n} {kname} var={var}", ms, 2 * esz * npts / ms / 1e6))
     ctx.set_variant(0, 0)
