@@ -43,6 +43,7 @@ SYMBOLS = {
     "cansb200_plan_create": (C.c_int, [_VP, C.POINTER(_VP), C.c_char_p, C.c_char_p, C.POINTER(Options), _D3]),
     "cansb200_plan_destroy": (C.c_int, [_VP]),
     "cansb200_solve": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, _VP, C.c_int, _VP]),
+    "cansb200_solve_z": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, C.c_int, _VP]),
     "cansb200_r2r": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _I3, _VP]),
     "cansb200_gaussel": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_int, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "cansb200_fillps": (C.c_int, [_VP, _I3, _D3, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP]),

@@ -92,6 +92,7 @@ struct cansb200_ctx {
   DevBuf scratch;   // haloless field buffer A (x pencil)
   DevBuf staging;   // haloed p when the caller's p is host memory
   DevBuf coef;      // a, b, c, lambdaxy staged from the host
+  DevBuf zero_lam;  // all-zero lambdaxy of the z-only solve (solver_gaussel_z)
   std::map<int, FftTables<double>> tabs64;
   std::map<int, FftTables<float>> tabs32;
   std::map<long long, DirectTables<double>> dtabs64;
@@ -376,7 +377,7 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   ThomasDev<T> D;
   D.nx = nx; D.ny = ny; D.n = n_rows; D.periodic = periodic; D.nn = periodic ? n_rows - 1 : n_rows;
   D.sj = sj; D.sk = sk; D.a = a; D.b = b; D.c = c; D.lam = lam; D.lam_sj = nx;
-  D.m = pl->th_m; D.chunk_layout = 0; D.xb = 0; D.xn = nx; D.out_rows = nullptr;
+  D.m = pl->th_m; D.chunk_layout = 0; D.xb = 0; D.xn = nx; D.out_rows = nullptr; D.nopin = 0;
   return D;
 }
 
@@ -528,7 +529,7 @@ template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T
   if (thomas_is_pipelined(pl)) {
     // 16-byte tile copies need every row segment aligned: even (FP64) / multiple-of-4 (FP32) column counts and offsets
     const long long vw = 16 / (long long)sizeof(T);
-    const bool vec = (D.nx % vw) == 0 && (D.xb % vw) == 0 && (D.sk % vw) == 0 && ((uintptr_t)p % 16) == 0 &&
+    const bool vec = (D.nx % vw) == 0 && (D.xb % vw) == 0 && (D.sk % vw) == 0 && (D.sj % vw) == 0 && ((uintptr_t)p % 16) == 0 &&
                      ((uintptr_t)pl->zcache.p % 16) == 0 && (pl->slot_z % vw) == 0 && (D.xn % vw) == 0;
     const bool exact = D.m == pl->th_mmax;
     if (pl->th_cols == 16 && pl->th_cl == 1) {
@@ -733,7 +734,7 @@ int cansb200_dist_status(cansb200_ctx* c, int* status) {
 
 int cansb200_finalize(cansb200_ctx* c) {
   if (!c) return 0;
-  c->scratch.release(); c->staging.release(); c->coef.release();
+  c->scratch.release(); c->staging.release(); c->coef.release(); c->zero_lam.release();
   for (auto& kv : c->tabs64) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (auto& kv : c->tabs32) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (int q = 0; q < (int)c->peer.size(); ++q)
@@ -1168,7 +1169,105 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// solver_gaussel_z (src/solver.f90:547-616): tridiagonal solve in z only, no transforms, lambda-less gaussel
+template <class T>
+static int solve_z_impl(cansb200_plan* pl, void* p_any, const int n[3], double norm, const void* a_any, const void* b_any,
+                        const void* c_any, int mem_kind, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  const int nx = n[0], ny = n[1], nzl = n[2];
+  const long long px = nx + 2, py = ny + 2;
+  const size_t nh = (size_t)px * py * (nzl + 2);
+  T* p = (T*)p_any;
+  const T *a = (const T*)a_any, *b = (const T*)b_any, *c = (const T*)c_any;
+  const size_t nlam = (size_t)ctx->n_z[0] * ctx->n_z[1];
+  if (!ctx->zero_lam.p) {
+    if (ctx->zero_lam.ensure(nlam * sizeof(T))) return fail(CANSB200_ENOMEM, "solve_z: lambda buffer");
+    CK(cudaMemsetAsync(ctx->zero_lam.p, 0, nlam * sizeof(T), st));
+  }
+  if (mem_kind == CANSB200_MEM_HOST) {
+    if (ctx->staging.ensure(nh * sizeof(T))) return fail(CANSB200_ENOMEM, "solve_z: staging");
+    const size_t nzg = (size_t)ctx->n_z[2];
+    if (ctx->coef.ensure((3 * nzg + nlam) * sizeof(T))) return fail(CANSB200_ENOMEM, "solve_z: coefficient staging");
+    T* cf = (T*)ctx->coef.p;
+    CK(cudaMemcpyAsync(ctx->staging.p, p_any, nh * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf, a_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf + nzg, b_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(cf + 2 * nzg, c_any, nzg * sizeof(T), cudaMemcpyHostToDevice, st));
+    p = (T*)ctx->staging.p;
+    a = cf; b = cf + nzg; c = cf + 2 * nzg;
+  }
+  const T* lam0 = (const T*)ctx->zero_lam.p;
+  T* pin = p + (px * py + px + 1);
+  int rc;
+  if (ctx->nranks == 1) {
+    // z is not decomposed: solve in place on the haloed array (row pitch px, plane pitch px * py)
+    if (nzl != ctx->ng[2]) return fail(CANSB200_EINVAL, "solve_z: extents");
+    ThomasDev<T> D = make_thomas<T>(pl, nx, ny, px, px * py, pl->th_n, pl->periodic_z, lam0, a, b, c);
+    D.nopin = 1;
+    rc = gaussel_prepare<T>(pl, D, st);
+    if (rc) return rc;
+    rc = gaussel_apply<T>(pl, D, pin, (T)norm, st);
+    if (rc) return rc;
+  } else {
+    if (!ctx->connected) return fail(CANSB200_ECOMM, "solve_z: cansb200_dist_connect has not been called");
+    const int nyl = ctx->n_z[1], nz = ctx->ng[2];
+    T* Cz = (T*)((char*)ctx->region + ctx->off_C);
+    const unsigned blocks = (unsigned)(ctx->num_sms * 8);
+    slab_rows_copy_kernel<T><<<blocks, 256, 0, st>>>(pin, px, px * py, (const DistRow<T>*)ctx->ytab_fwd.p, nx, ny, nzl, 1);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    rc = dist_barrier(ctx, st);
+    if (rc) return rc;
+    ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam0, a, b, c);
+    D.nopin = 1;
+    D.out_rows = (T* const*)ctx->ztab.p;
+    rc = gaussel_prepare<T>(pl, D, st);
+    if (rc) return rc;
+    if (thomas_is_pipelined(pl)) {
+      rc = gaussel_apply<T>(pl, D, Cz, (T)norm, st);
+      if (rc) return rc;
+      if (pl->th_n < nz) {
+        scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, D.out_rows, pl->th_n, nz, (long long)nx * nyl);
+        ctx->launches++;
+      }
+    } else {
+      ThomasDev<T> D2 = D;
+      D2.out_rows = nullptr;
+      rc = gaussel_apply<T>(pl, D2, Cz, (T)norm, st);
+      if (rc) return rc;
+      scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, D.out_rows, 0, nz, (long long)nx * nyl);
+      ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    rc = dist_barrier(ctx, st);
+    if (rc) return rc;
+    slab_rows_copy_kernel<T><<<blocks, 256, 0, st>>>(pin, px, px * py, (const DistRow<T>*)ctx->ytab_bwd.p, nx, ny, nzl, 0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  if (mem_kind == CANSB200_MEM_HOST) {
+    CK(cudaMemcpyAsync(p_any, ctx->staging.p, nh * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  pl->solves++;
+  return 0;
+}
+
 extern "C" {
+
+int cansb200_solve_z(cansb200_plan* pl, void* p, const int n[3], int nhalo, double norm, const void* a, const void* b,
+                     const void* c, int mem_kind, void* stream) {
+  if (!pl || !p || !n || !a || !b || !c) return fail(CANSB200_EINVAL, "solve_z: null argument");
+  if (nhalo != 1) return fail(CANSB200_EINVAL, "solve_z: nhalo must be 1");
+  cansb200_ctx* ctx = pl->ctx;
+  for (int d = 0; d < 3; ++d)
+    if (n[d] != ctx->n[d]) return fail(CANSB200_EINVAL, "solve_z: n differs from the context's local extents");
+  if (mem_kind != CANSB200_MEM_HOST && mem_kind != CANSB200_MEM_DEVICE) return fail(CANSB200_EINVAL, "solve_z: bad mem_kind");
+  cudaStream_t st = (cudaStream_t)stream;
+  return ctx->is_fp32 ? solve_z_impl<float>(pl, p, n, norm, a, b, c, mem_kind, st)
+                      : solve_z_impl<double>(pl, p, n, norm, a, b, c, mem_kind, st);
+}
 
 int cansb200_solve(cansb200_plan* pl, void* p, const int n[3], int nhalo, double normfft, const void* lambdaxy,
                    const void* a, const void* b, const void* c, int mem_kind, void* stream) {

@@ -64,4 +64,23 @@ __global__ void scatter_rows_kernel(const T* __restrict__ src, long long sk, T* 
   }
 }
 
+// z-only solve (solver_gaussel_z) on a decomposed grid: the x-pencil slab goes to the z pencils of its owners
+// and back without any transform in between.  Row (j, g) of my haloed slab <-> tab[j].ptr + g * tab[j].gs
+// (the same row tables the y transforms use for their peer-mapped stores / loads).
+template <class T> struct DistRow { T* ptr; long long gs; };
+template <class T>
+__global__ void slab_rows_copy_kernel(T* __restrict__ slab, long long px, long long pxy, const DistRow<T>* __restrict__ tab,
+                                      int nx, int ny, int nzl, int to_peers) {
+  const long long tot = (long long)nx * ny * nzl;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % nx);
+    const long long r = e / nx;
+    const int j = (int)(r % ny), g = (int)(r / ny);
+    T* mine = slab + (long long)g * pxy + (long long)j * px + i;
+    T* theirs = tab[j].ptr + (long long)g * tab[j].gs + i;
+    if (to_peers) *theirs = *mine;
+    else *mine = *theirs;
+  }
+}
+
 }  // namespace cb

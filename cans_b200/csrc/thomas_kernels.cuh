@@ -39,6 +39,8 @@ template <class T> struct ThomasDev {
   int xb, xn;         // column window of this launch: i in [xb, xb + xn) for every j (thomas_reg_kernel)
   int m;              // rows per chunk of the chunked substitution = ceil(nn/32)
   int chunk_layout;   // 0: z[k][j][i]   1: z[((j*nx+i)*m + r)*32 + lane], k = lane*m + r
+  int nopin;          // 1: the lambda-less variant of gaussel (src/solver.f90:168-188, :238-256; solver_gaussel_z):
+                      // no singular-pivot pin, no tolerance test on the periodic closure
 };
 
 // ---- exactly-rounded, never-contracted arithmetic ---------------------------
@@ -101,6 +103,7 @@ __global__ void thomas_hash_kernel(const ThomasDev<T> D, CacheState* st) {
     }
     h += mix64(mix64((unsigned long long)e) ^ bits_of(v));
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) h += mix64(0x5EEDULL + (unsigned long long)D.nopin);
   for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(&st->key_new, h);
 }
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(128) thomas_factor_kernel(const ThomasDev<T> D
     const T ad = mul_rn(D.a[k], d);
     const T den = sub_rn(bl, ad);
     bool pin = false;
-    if (k == nn - 1) {
+    if (k == nn - 1 && !D.nopin) {
       const T tol = mul_rn(eps_of<T>(), fmax(fabs(bl), fabs(ad)));
       pin = fabs(den) <= tol;
     }
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(128) thomas_factor_kernel(const ThomasDev<T> D
   const T bl = add_rn(D.b[nn], lam);
   const T den = add_rn(add_rn(bl, t1), t2);
   const T tol = mul_rn(eps_of<T>(), fmax(fabs(bl), fabs(add_rn(t1, t2))));
-  den_c[col] = (fabs(den) <= tol) ? T(0) : den;
+  den_c[col] = (!D.nopin && fabs(den) <= tol) ? T(0) : den;
 }
 
 // ---- sequential substitution, reference operation order ---------------------
@@ -435,13 +438,16 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   }
   unsigned tile_phase = 0;
 
-  // tile -> (flat column of its first thread, live columns)
+  // tile -> (flat column of its first thread, live columns); the field itself may have a row pitch sj != nx
+  // (the haloed array of solver_gaussel_z): its columns sit at pcol = col + tj (sj - nx)
+  const long long pitch_extra = D.sj - D.nx;
   auto tile_col0 = [&](int tile, int& ncols) -> long long {
     const int tj = tile / tiles_x;
     const int ti0 = (tile - tj * tiles_x) * COLS;
     ncols = D.xn - ti0 < COLS ? D.xn - ti0 : COLS;
     return (long long)tj * D.nx + D.xb + ti0;
   };
+  auto tile_pshift = [&](int tile) -> long long { return (long long)(tile / tiles_x) * pitch_extra; };
   // asynchronous copy of one tile of pivots and right-hand sides into [row][COLS]; rows >= nn and dead
   // columns are zero filled so that the chunk maps of padding rows are exact identities / zeros
   auto prefetch = [&](int tile_i, long long col0, int ncols) {
@@ -466,7 +472,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         T* pd = ps + row * COLS + pc;
         if (rbase + row < nn && pc < ncols) {
           cp_async_16(zd, zsel + (long long)(rbase + row) * ncol + col0 + pc);
-          cp_async_16(pd, p + (long long)(rbase + row) * sk + col0 + pc);
+          cp_async_16(pd, p + (long long)(rbase + row) * sk + col0 + tile_pshift(tile_i) + pc);
         } else {
 #pragma unroll
           for (int e = 0; e < VW; ++e) { zd[e] = T(0); pd[e] = T(0); }
@@ -477,7 +483,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         const int row = q / COLS, pc = q - row * COLS;
         if (rbase + row < nn && pc < ncols) {
           cp_async_elem(zs + q, zsel + (long long)(rbase + row) * ncol + col0 + pc);
-          cp_async_elem(ps + q, p + (long long)(rbase + row) * sk + col0 + pc);
+          cp_async_elem(ps + q, p + (long long)(rbase + row) * sk + col0 + tile_pshift(tile_i) + pc);
         } else {
           zs[q] = T(0);
           ps[q] = T(0);
@@ -512,6 +518,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     const bool live = c < ncols;
     const int nrow = live ? nrow_full : 0;
     const long long col = col0 + c;
+    const long long pcol = col + tile_pshift(tile);
 
     // forward: y_k = (p_k norm - a_k y_{k-1}) z_k, chunk-local with y_{k0-1} := 0
     T yy = T(0), pi = T(1);
@@ -599,11 +606,11 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         T pcl = T(0);
         if (live) {
           const T den = denbase[(long long)sel * slot_den + col];
-          const T pnn = p[(long long)nn * sk + col];
+          const T pnn = p[(long long)nn * sk + pcol];
           const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[COLS + c]));
           pcl = (den == T(0)) ? T(0) : div_rn(num, den);
           if (D.out_rows) D.out_rows[nn][col] = pcl;
-          else p[(long long)nn * sk + col] = pcl;
+          else p[(long long)nn * sk + pcol] = pcl;
         }
         sP[c] = pcl;
       }
@@ -620,7 +627,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       for (int r = 0; r < MMAX; ++r)
         if (r < nrow) rows[r][col] = y[r];
     } else {
-      T* pc = p + (long long)k0 * sk + col;
+      T* pc = p + (long long)k0 * sk + pcol;
       if (nrow == m) {
 #pragma unroll
         for (int r = 0; r < MMAX; ++r)

@@ -330,6 +330,27 @@ def solver(n, ng, arrplan: Plan, normfft, lambdaxy, a, b, c, bc, c_or_f, p, stre
     return p
 
 
+def solver_gaussel_z(n, ng, hi, a, b, c, bcz, c_or_f, norm, p, arrplan: Plan = None, stream=None):
+    """src/solver.f90:547-616 (`solver_gaussel_z`, the implicit-z-diffusion solve of `is_impdiff_1d`):
+    lambda-less tridiagonal solve in z on the interior of the haloed `p`, in place.  Argument order as in the
+    reference; `arrplan` is the plan of the solved variable (it carries the context and the z variant) -- the
+    reference needs none because this path uses no transforms."""
+    if arrplan is None:
+        raise ValueError("solver_gaussel_z: pass the variable's plan (arrplan=...)")
+    if list(bcz) != arrplan.cbc[2] or c_or_f[2] != arrplan.c_or_f[2]:
+        raise ValueError("solver_gaussel_z: bcz / c_or_f(3) differ from the ones the plan was created with")
+    dev = _is_torch(p) and p.is_cuda
+    for name, arr in (("a", a), ("b", b), ("c", c)):
+        if (_is_torch(arr) and arr.is_cuda) != dev:
+            raise ValueError(f"solver_gaussel_z: {name} must live where p lives (all device or all host)")
+    want = (n[2] + 2, n[1] + 2, n[0] + 2)
+    if tuple(p.shape) != want:
+        raise ValueError(f"solver_gaussel_z: p has shape {tuple(p.shape)}, expected {want}")
+    check(lib.cansb200_solve_z(arrplan.handle, _ptr(p), i3(n), 1, float(norm), _ptr(a), _ptr(b), _ptr(c),
+                               MEM_DEVICE if dev else MEM_HOST, _stream_ptr(stream)), "cansb200_solve_z")
+    return p
+
+
 def updt_rhs_b(c_or_f, cbc, n, rhsbx, rhsby, rhsbz, p, alpha=None):
     """src/bound.f90:514-598 on one rank: adds the wall contributions to the first / last planes."""
     norm = 1.0 if alpha is None else alpha

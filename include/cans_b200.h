@@ -92,6 +92,14 @@ int cansb200_solve(cansb200_plan* plan, void* p, const int n[3], int nhalo, doub
                    const void* lambdaxy, const void* a, const void* b, const void* c,
                    int mem_kind, void* stream);
 
+/* -- z-only solve: replaces solver_gaussel_z / solver_gaussel_z_gpu (src/solver.f90:547-616,
+ *    src/solver_gpu.f90:956-1105; implicit z diffusion, is_impdiff_1d): the lambda-less gaussel on the interior of
+ *    the haloed p, no transforms.  The plan supplies the z variant (periodic closure, q = 1 for a face-centred
+ *    Dirichlet top).  On a z-decomposed grid the slab travels to the z pencils and back over the same
+ *    peer-mapped row tables as the full solve.  norm as in the reference (1 for the diffusion solves). */
+int cansb200_solve_z(cansb200_plan* plan, void* p, const int n[3], int nhalo, double norm,
+                     const void* a, const void* b, const void* c, int mem_kind, void* stream);
+
 /* -- stage-level entry points (device pointers only), so that tests can compare every stage
  *    with the oracle the way the reference composes them:
  *    cansb200_r2r     == one `call fft(arrplan(idir_fb), arr)`            (src/fft.f90:247-258)

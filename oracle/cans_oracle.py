@@ -608,6 +608,17 @@ def gaussel_c(n, a, b, c, is_periodic, norm, p, lambdaxy):
     return p
 
 
+def solver_gaussel_z(n, ng, hi, a, b, c, bcz, c_or_f, norm, p):
+    """src/solver.f90:547-616 on one rank (z not decomposed): the lambda-less `gaussel` on the interior of the
+    haloed p[k,j,i], in place (`call gaussel(n(1),n(2),n(3)-q,1,a,b,c,is_periodic_z,norm,p)`, :598)."""
+    n1, n2, n3 = n
+    q = 1 if (c_or_f[2] == 'f' and bcz[1] == 'D' and hi[2] == ng[2]) else 0
+    pz = np.ascontiguousarray(p[1:n3 + 1, 1:n2 + 1, 1:n1 + 1])
+    gaussel(n3 - q, a, b, c, bcz[0] + bcz[1] == 'PP', norm, pz, None)
+    p[1:n3 + 1, 1:n2 + 1, 1:n1 + 1] = pz
+    return p
+
+
 def solver_fast(n, ng, arrplan, normfft, lambdaxy, a, b, c, bc, c_or_f, p, workers=-1):
     """`solver` with threaded pocketfft and the OpenMP C gaussel: the CPU baseline
     ("kind": "port").  FP64.  Same stages, same order as `solver`."""

@@ -27,6 +27,7 @@ DIST_CASES = {
     "duct_128x64x96": ([128, 64, 96], [6.0, 2.0, 2.0], [P, N, N], C3, 1.5, np.float64, False),
     "uneven_64x64x70": ([64, 64, 70], [1.0, 1.0, 1.0], [N, P, ["D", "D"]], C3, 1.0, np.float64, False),
     "helm_w_64x64x64": ([64, 64, 64], [1.0, 1.0, 1.0], [P, P, ["D", "D"]], ["c", "c", "f"], 1.0, np.float64, True),
+    "tma_32x64x256": ([32, 64, 256], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # full chunks: TMA tile path
     "fp32_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float32, False),
 }
 
@@ -80,6 +81,21 @@ def main():
         halo = np.ones(got.shape, bool)
         halo[1:-1, 1:-1, 1:-1] = False
         assert np.array_equal(got[halo], pl[halo]), "halo cells were modified"
+        # z-only solve (solver_gaussel_z) on the same decomposition: slab -> z pencils -> slab, no transforms
+        alphai = dt(1.0) / dt(cases.ALPHA)
+        bb = (cs["b"] + alphai).astype(dt)
+        refz = p.copy()
+        O.solver_gaussel_z(ng, ng, ng, cs["a"], bb, cs["c"], cbc[2], cf, alphai, refz)
+        pd.copy_(torch.from_numpy(pl))
+        cb.solver_gaussel_z(ctx.n, ng, ng, sd.a, torch.from_numpy(bb).to(dev), sd.c, cbc[2], cf, alphai, pd, arrplan=sd.arrplan)
+        torch.cuda.synchronize()
+        assert ctx.dist_status() == 0, "a device-side barrier timed out"
+        gotz = pd.cpu().numpy()
+        errz = cases.rel_l2(gotz[1:-1, 1:-1, 1:-1], refz[1 + z0:1 + z1, 1:-1, 1:-1])
+        if rank == 0:
+            print(f"{name}: solver_gaussel_z rel L2 = {errz:.3e}", flush=True)
+        assert errz < tol, f"{name}: gaussel_z {errz}"
+        assert np.array_equal(gotz[halo], pl[halo]), "halo cells were modified (gaussel_z)"
         dist.barrier()
         sd.arrplan.destroy()
         ctx.close()

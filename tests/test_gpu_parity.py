@@ -152,6 +152,43 @@ def test_solver_matches_oracle(cb, name):
     assert np.array_equal(got[halo], p[halo])
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", ["C3s_channel", "periodic_z_odd", "helm_w_face_z", "tiny_z", "nz_512_tma", "nz_gt_512",
+                                  "nz_257_periodic_tma", "fp32_channel"])
+def test_solver_gaussel_z_matches_oracle(cb, S, name, variant):
+    """cansb200_solve_z == solver_gaussel_z (src/solver.f90:547-616): z-only implicit-diffusion solve with the
+    Helmholtz-shifted diagonal b + 1/alpha (src/rk.f90 is_impdiff_1d branch), haloed array, halos untouched."""
+    cs = cases.build_case(name)
+    ng, dt = cs["ng"], cs["dtype"]
+    p = cases.make_rhs(cs, seed=321)
+    rng = np.random.default_rng(5)
+    p[0], p[-1] = rng.uniform(-1, 1, p[0].shape), rng.uniform(-1, 1, p[0].shape)   # halos carry junk that must survive
+    alphai = dt(1.0) / dt(cases.ALPHA)
+    bb = (cs["b"] + alphai).astype(dt)
+    norm = alphai
+    ref = p.copy()
+    O.solver_gaussel_z(ng, ng, ng, cs["a"], bb, cs["c"], cs["cbc"][2], cs["c_or_f"], norm, ref)
+    ctx = cb.Context(ng, is_fp32=(dt == np.float32))
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cs["cbc"], cs["bc"], cs["c_or_f"], device=_dev(),
+                       thomas_variant=variant)
+    pd = torch.from_numpy(p.copy()).to(_dev())
+    cb.solver_gaussel_z(ng, ng, ng, sd.a, torch.from_numpy(bb).to(_dev()), sd.c, cs["cbc"][2], cs["c_or_f"], norm, pd,
+                        arrplan=sd.arrplan)
+    got = pd.cpu().numpy()
+    I = (slice(1, -1),) * 3
+    err = cases.rel_l2(got[I], ref[I])
+    if variant == 0:
+        assert np.array_equal(got[I], ref[I]), f"sequential variant must be bit-identical (rel {err:.2e})"
+    assert err < TOL[dt], f"{name}: rel L2 {err:.3e}"
+    halo = np.ones(got.shape, bool)
+    halo[I] = False
+    assert np.array_equal(got[halo], p[halo])
+    # host-memory mode of the same call
+    ph = p.copy()
+    cb.solver_gaussel_z(ng, ng, ng, cs["a"], bb, cs["c"], cs["cbc"][2], cs["c_or_f"], norm, ph, arrplan=sd.arrplan)
+    assert cases.rel_l2(ph[I], ref[I]) < TOL[dt]
+
+
 @pytest.mark.parametrize("name", [f[:-4] for f in sorted(os.listdir(os.path.join(os.path.dirname(__file__), "golden")))
                                   if f.endswith(".npz")])
 def test_solver_matches_golden(cb, name):
