@@ -328,19 +328,50 @@ template <> __device__ __forceinline__ void dsmem_store<float>(float* local, uns
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 
+// one-way hand-over: store v into CTA `rank`'s copy of `local` and complete 8 / 4 bytes of the transaction count of
+// ITS copy of the mbarrier `bar` (st.async): the receiver waits on its own barrier, nobody fences global memory
+__device__ __forceinline__ void dsmem_send(double* local, unsigned long long* bar, unsigned rank, double v) {
+  const unsigned la = (unsigned)__cvta_generic_to_shared(local), lb = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(ra), "l"(__double_as_longlong(v)), "r"(rb) : "memory");
+}
+__device__ __forceinline__ void dsmem_send(float* local, unsigned long long* bar, unsigned rank, float v) {
+  const unsigned la = (unsigned)__cvta_generic_to_shared(local), lb = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  for (unsigned it = 0;; ++it) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (it > (1u << 26)) __trap();
+  }
+}
+
 // Fold of the CHUNKS chunk maps v -> Y_g + P_g v of every column: warp w < COLS owns column w, lane l owns
 // the CPL = CHUNKS / 32 consecutive chunks l*CPL ..; Kogge-Stone scan of the lane aggregates with shuffles;
 // result = value entering each chunk, written over sY.  FWD: chunk 0 upward; otherwise the last chunk downward.
 // `cin` (indexed by column) is the value entering the first chunk in application order (nullptr = 0); the value
 // leaving the last one is handed to `agg(column, value)`.
-template <class T, bool FWD, int COLS, int CHUNKS, class Agg>
+// PEX: also leave in sP the product of the maps before each chunk (the sensitivity of the value entering the chunk
+// to a carry entering the CTA), so that a carry that arrives later is applied as vin += pex * carry.
+template <class T, bool FWD, int COLS, int CHUNKS, bool PEX, class Agg>
 __device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid, const T* cin, Agg agg) {
   constexpr int LD = CHUNKS + 1, CPL = CHUNKS / 32;
   static_assert(CHUNKS % 32 == 0, "chunks per column must be a multiple of the warp size");
   const int w = tid >> 5, lane = tid & 31;
   if (w < COLS) {
     T* rowY = sY + w * LD + lane * CPL;
-    const T* rowP = sP + w * LD + lane * CPL;
+    T* rowP = sP + w * LD + lane * CPL;
     T y[CPL], p[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) { y[q] = rowY[q]; p[q] = rowP[q]; }
@@ -364,14 +395,16 @@ __device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid, const T* cin,
     const bool last = FWD ? (lane == 31) : (lane == 0);
     if (last) agg(w, fma(P, c0, Y));
     T vin = FWD ? shfl_up_t(Y, 1) : shfl_down_t(Y, 1);
-    const T pex = FWD ? shfl_up_t(P, 1) : shfl_down_t(P, 1);
-    if (FWD ? (lane == 0) : (lane == 31)) vin = c0;
+    T pex = FWD ? shfl_up_t(P, 1) : shfl_down_t(P, 1);
+    if (FWD ? (lane == 0) : (lane == 31)) { vin = c0; pex = T(1); }
     else vin = fma(pex, c0, vin);
 #pragma unroll
     for (int s = 0; s < CPL; ++s) {
       const int q = FWD ? s : CPL - 1 - s;
       rowY[q] = vin;
+      if (PEX) rowP[q] = pex;
       vin = fma(p[q], vin, y[q]);
+      pex *= p[q];
     }
   }
 }
@@ -408,6 +441,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   T* sY = sc + CHUNKS * CSA;                        // [c][g] chunk value, row stride CHUNKS + 1
   T* sP = sY + COLS * LD;                           // [c][g] chunk product
   __shared__ T xchg[2][COLS];                       // carries handed over by the other CTA of the cluster
+  __shared__ __align__(8) unsigned long long xbar[2];   // their arrival: [0] forward carry (rank 1 waits), [1] backward (rank 0)
   __shared__ __align__(8) unsigned long long tile_bar;   // TMA: completion barrier of the tile in flight
   const unsigned rank = CL > 1 ? cluster_ctarank() : 0u;
   const int tid = threadIdx.x, c = tid & (COLS - 1), g = tid / COLS;
@@ -500,6 +534,17 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   long long col0 = tile_col0(tile, ncols);
   prefetch(tile, col0, ncols);
   auto no_agg = [](int, T) {};
+  unsigned xphase = 0;
+  if (CL > 1) {
+    // hand-over barriers: armed by the receiver (one arrival + COLS values), completed by the sender's st.async
+    if (tid == 0) {
+      mbar_init(&xbar[0], 1);
+      mbar_init(&xbar[1], 1);
+      fence_mbar_init();
+      mbar_expect_tx(&xbar[rank == 1 ? 0 : 1], (unsigned)(COLS * sizeof(T)));
+    }
+    cluster_sync_all();   // both CTAs are armed before either one signals
+  }
   for (; tile < ntiles; tile += tstride) {
     if (TMA) {
       mbar_wait(&tile_bar, tile_phase);
@@ -541,16 +586,25 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       col0_n = tile_col0(tnext, ncols_n);
       prefetch(tnext, col0_n, ncols_n);
     }
+    T vin;
     if (CL == 1) {
-      thomas_fold<T, true, COLS, CHUNKS>(sY, sP, tid, (const T*)nullptr, no_agg);
+      thomas_fold<T, true, COLS, CHUNKS, false>(sY, sP, tid, (const T*)nullptr, no_agg);
+      __syncthreads();
+      vin = sY[c * LD + g];
     } else {
-      // forward carry: rank 0 folds first and hands the value leaving its last row to rank 1
-      if (rank == 0) thomas_fold<T, true, COLS, CHUNKS>(sY, sP, tid, (const T*)nullptr, [&](int w, T v) { dsmem_store(&xchg[0][w], 1u, v); });
-      cluster_sync_all();
-      if (rank == 1) thomas_fold<T, true, COLS, CHUNKS>(sY, sP, tid, (const T*)xchg[0], no_agg);
+      // both CTAs fold their halves at once with a zero carry; rank 0 hands the value leaving its last row to
+      // rank 1 (one-way st.async), which adds (product of the maps before the chunk) x carry
+      if (rank == 0) thomas_fold<T, true, COLS, CHUNKS, false>(sY, sP, tid, (const T*)nullptr, [&](int w, T v) { dsmem_send(&xchg[0][w], &xbar[0], 1u, v); });
+      else thomas_fold<T, true, COLS, CHUNKS, true>(sY, sP, tid, (const T*)nullptr, no_agg);
+      __syncthreads();
+      vin = sY[c * LD + g];
+      if (rank == 1) {
+        mbar_wait_cluster(&xbar[0], xphase);
+        vin = fma(sP[c * LD + g], xchg[0][c], vin);
+        // re-arm for the next tile: rank 0 cannot send again before it has received this tile's backward carry
+        if (tid == 0) mbar_expect_tx(&xbar[0], (unsigned)(COLS * sizeof(T)));
+      }
     }
-    __syncthreads();
-    T vin = sY[c * LD + g];
     pi = T(1);
 #pragma unroll
     for (int r = 0; r < MMAX; ++r) {
@@ -574,15 +628,22 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     sP[c * LD + g] = rho;
     __syncthreads();
     if (CL == 1) {
-      thomas_fold<T, false, COLS, CHUNKS>(sY, sP, tid, (const T*)nullptr, no_agg);
+      thomas_fold<T, false, COLS, CHUNKS, false>(sY, sP, tid, (const T*)nullptr, no_agg);
+      __syncthreads();
+      vin = sY[c * LD + g];
     } else {
-      // backward carry: rank 1 folds first and hands the value leaving its first row to rank 0
-      if (rank == 1) thomas_fold<T, false, COLS, CHUNKS>(sY, sP, tid, (const T*)nullptr, [&](int w, T v) { dsmem_store(&xchg[1][w], 0u, v); });
-      cluster_sync_all();
-      if (rank == 0) thomas_fold<T, false, COLS, CHUNKS>(sY, sP, tid, (const T*)xchg[1], no_agg);
+      // the same downward: rank 1 hands the value leaving its first row to rank 0
+      if (rank == 1) thomas_fold<T, false, COLS, CHUNKS, false>(sY, sP, tid, (const T*)nullptr, [&](int w, T v) { dsmem_send(&xchg[1][w], &xbar[1], 0u, v); });
+      else thomas_fold<T, false, COLS, CHUNKS, true>(sY, sP, tid, (const T*)nullptr, no_agg);
+      __syncthreads();
+      vin = sY[c * LD + g];
+      if (rank == 0) {
+        mbar_wait_cluster(&xbar[1], xphase);
+        vin = fma(sP[c * LD + g], xchg[1][c], vin);
+        if (tid == 0) mbar_expect_tx(&xbar[1], (unsigned)(COLS * sizeof(T)));
+      }
+      xphase ^= 1u;
     }
-    __syncthreads();
-    vin = sY[c * LD + g];
     rho = T(1);
 #pragma unroll
     for (int r = MMAX - 1; r >= 0; --r) {
@@ -641,6 +702,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     col0 = col0_n;
     ncols = ncols_n;
   }
+  if (CL > 1) cluster_sync_all();   // leave together: a CTA's shared memory must outlive the peer's last hand-over
 }
 
 }  // namespace cb
