@@ -32,6 +32,8 @@ WORKLOADS = {
     "C3_channel_1024x512x512": ([1024, 512, 512], [12.0, 6.0, 2.0], [["P", "P"], ["P", "P"], ["N", "N"]], 2.0),
     "C2_tgv_512x512x512": ([512, 512, 512], [6.283185307179586] * 3, [["P", "P"]] * 3, 0.0),
     "C4_duct_1024x768x768": ([1024, 768, 768], [12.0, 2.0, 2.0], [["P", "P"], ["N", "N"], ["N", "N"]], 1.5),
+    # configs[4]: 8 B200 (17.2 GB per field); the Poisson solve of the implicit-diffusion substep
+    "C5_channel_2048x1024x1024": ([2048, 1024, 1024], [12.0, 6.0, 2.0], [["P", "P"], ["P", "P"], ["N", "N"]], 2.0),
     "C1_ldc_2x64x64": ([2, 64, 64], [0.03125, 1.0, 1.0], [["P", "P"], ["N", "N"], ["N", "N"]], 0.0),
 }
 METRIC = "poisson_solve_ns_per_gridpoint"

@@ -18,7 +18,10 @@ namespace cb {
   X(1024, 0, 64, 2, 5, 16, 8, 8, 1)   \
   X(1024, 1, 128, 2, 4, 8, 8, 4, 4)   \
   X(1024, 2, 64, 4, 3, 16, 8, 8, 1)   \
-  X(2048, 0, 128, 2, 1, 16, 16, 8, 1) \
+  X(2048, 0, 128, 1, 4, 16, 16, 8, 1) \
+  X(2048, 1, 128, 2, 1, 16, 16, 8, 1) \
+  X(2048, 2, 128, 2, 2, 16, 16, 8, 1) \
+  X(2048, 3, 128, 1, 3, 16, 16, 8, 1) \
   X(384, 0, 32, 8, 1, 12, 4, 4, 2)    \
   X(768, 0, 64, 4, 1, 12, 4, 4, 4)
 // y mode: G = column pairs per CTA (8 pairs of FP64 = one 128-byte row).
@@ -31,6 +34,8 @@ namespace cb {
   X(512, 2, 64, 4, 4, 8, 8, 8, 1)     \
   X(1024, 0, 64, 8, 1, 16, 8, 8, 1)   \
   X(1024, 1, 128, 4, 2, 8, 8, 4, 4)   \
+  X(1024, 2, 32, 8, 1, 16, 16, 4, 1)  \
+  X(1024, 3, 32, 4, 2, 16, 16, 4, 1)  \
   X(2048, 0, 128, 4, 1, 16, 16, 8, 1) \
   X(384, 0, 32, 8, 1, 12, 4, 4, 2)    \
   X(768, 0, 32, 8, 2, 12, 8, 8, 1)    \
