@@ -34,6 +34,8 @@ WORKLOADS = {
     "C4_duct_1024x768x768": ([1024, 768, 768], [12.0, 2.0, 2.0], [["P", "P"], ["N", "N"], ["N", "N"]], 1.5),
     # configs[4]: 8 B200 (17.2 GB per field); the Poisson solve of the implicit-diffusion substep
     "C5_channel_2048x1024x1024": ([2048, 1024, 1024], [12.0, 6.0, 2.0], [["P", "P"], ["P", "P"], ["N", "N"]], 2.0),
+    # diagnostic shape: at N = 2 every GPU sees the z pencil of C5 at N = 8 (2048 x 128 x 1024)
+    "X_2048x256x1024": ([2048, 256, 1024], [12.0, 6.0, 2.0], [["P", "P"], ["P", "P"], ["N", "N"]], 2.0),
     "C1_ldc_2x64x64": ([2, 64, 64], [0.03125, 1.0, 1.0], [["P", "P"], ["N", "N"], ["N", "N"]], 0.0),
 }
 METRIC = "poisson_solve_ns_per_gridpoint"

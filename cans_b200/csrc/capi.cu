@@ -682,23 +682,26 @@ template <class T> static int build_dist_tables(cansb200_ctx* c) {
       // forward y output row j of my plane g: z pencil of rank s, plane zs[r] + g, row j - ys[s]
       yf[j].ptr = C_s + ((long long)c->zs[r] * nyl_s + (j - c->ys[s])) * nx;
       yf[j].gs = nyl_s * nx;
-      // backward y input row j of my plane g: block s of my way-back buffer [s][g][j - ys[s]][i]
-      yb[j].ptr = XB_r + (nzl_r * c->ys[s] + (j - c->ys[s])) * nx;
-      yb[j].gs = nyl_s * nx;
+      // backward y input row j of my plane g: block s of my way-back buffer [s][j - ys[s]][g][i]
+      yb[j].ptr = XB_r + (nzl_r * c->ys[s] + (long long)(j - c->ys[s]) * nzl_r) * nx;
+      yb[j].gs = nx;
     }
   }
-  std::vector<T*> zt(nz);
+  std::vector<OutRow<T>> zt(nz);
   for (int s = 0; s < P; ++s) {
     const long long nzl_s = c->zs[s + 1] - c->zs[s];
     T* XB_s = (T*)((char*)c->peer[s] + c->peer_off_XB[s]);
-    for (int k = c->zs[s]; k < c->zs[s + 1]; ++k)   // result row k of my columns: block r of rank s's way-back buffer
-      zt[k] = XB_s + nzl_s * c->ys[r] * nx + (long long)(k - c->zs[s]) * nyl_r * nx;
+    for (int k = c->zs[s]; k < c->zs[s + 1]; ++k) {   // result row k of my columns: block r of rank s's way-back buffer, [j][k][i]
+      zt[k].ptr = XB_s + nzl_s * c->ys[r] * nx + (long long)(k - c->zs[s]) * nx;
+      zt[k].sj = nzl_s * nx;
+    }
   }
-  if (c->ytab_fwd.ensure(sizeof(R2Row<T>) * ny) || c->ytab_bwd.ensure(sizeof(R2Row<T>) * ny) || c->ztab.ensure(sizeof(T*) * nz))
+  (void)nyl_r;
+  if (c->ytab_fwd.ensure(sizeof(R2Row<T>) * ny) || c->ytab_bwd.ensure(sizeof(R2Row<T>) * ny) || c->ztab.ensure(sizeof(OutRow<T>) * nz))
     return fail(CANSB200_ENOMEM, "dist_connect: tables");
   CK(cudaMemcpy(c->ytab_fwd.p, yf.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->ytab_bwd.p, yb.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->ztab.p, zt.data(), sizeof(T*) * nz, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->ztab.p, zt.data(), sizeof(OutRow<T>) * nz, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -970,7 +973,7 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
   // tridiagonal solve on my z pencil (nx, ny/P, nz); result rows go straight to the slabs of their owners
   if (pl->th_n != nz - pl->q) return fail(CANSB200_EINVAL, "solve: plan / grid mismatch");
   ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam, a, b, c);
-  D.out_rows = (T* const*)ctx->ztab.p;
+  D.out_rows = (const OutRow<T>*)ctx->ztab.p;
   rc = gaussel_prepare<T>(pl, D, st);
   if (rc) return rc;
   prof_mark(ctx, st);
@@ -978,7 +981,7 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     rc = gaussel_apply<T>(pl, D, Cz, (T)normfft, st);
     if (rc) return rc;
     if (pl->th_n < nz) {   // face-centred Dirichlet: the last plane is not part of the system but still travels back
-      scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, D.out_rows, pl->th_n, nz, (long long)nx * nyl);
+      scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, pl->th_n, nz, (long long)nx * nyl, nx);
       ctx->launches++;
     }
   } else {
@@ -986,7 +989,7 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     D2.out_rows = nullptr;
     rc = gaussel_apply<T>(pl, D2, Cz, (T)normfft, st);
     if (rc) return rc;
-    scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, D.out_rows, 0, nz, (long long)nx * nyl);
+    scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, 0, nz, (long long)nx * nyl, nx);
     ctx->launches++;
   }
   CK(cudaGetLastError());
@@ -1221,14 +1224,14 @@ static int solve_z_impl(cansb200_plan* pl, void* p_any, const int n[3], double n
     if (rc) return rc;
     ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam0, a, b, c);
     D.nopin = 1;
-    D.out_rows = (T* const*)ctx->ztab.p;
+    D.out_rows = (const OutRow<T>*)ctx->ztab.p;
     rc = gaussel_prepare<T>(pl, D, st);
     if (rc) return rc;
     if (thomas_is_pipelined(pl)) {
       rc = gaussel_apply<T>(pl, D, Cz, (T)norm, st);
       if (rc) return rc;
       if (pl->th_n < nz) {
-        scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, D.out_rows, pl->th_n, nz, (long long)nx * nyl);
+        scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, pl->th_n, nz, (long long)nx * nyl, nx);
         ctx->launches++;
       }
     } else {
@@ -1236,7 +1239,7 @@ static int solve_z_impl(cansb200_plan* pl, void* p_any, const int n[3], double n
       D2.out_rows = nullptr;
       rc = gaussel_apply<T>(pl, D2, Cz, (T)norm, st);
       if (rc) return rc;
-      scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, D.out_rows, 0, nz, (long long)nx * nyl);
+      scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, 0, nz, (long long)nx * nyl, nx);
       ctx->launches++;
     }
     CK(cudaGetLastError());

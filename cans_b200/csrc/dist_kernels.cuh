@@ -53,14 +53,17 @@ __global__ void dist_barrier_kernel(DistPeers peers, int rank, int nranks, unsig
 }
 
 // rows [k0, k1) of a (rows x ncol) array to their peer-mapped homes (used for rows the tridiagonal
-// kernel does not write: the face-centred Dirichlet plane, and the sequential fallback's result)
+// kernel does not write: the face-centred Dirichlet plane, and the sequential fallback's result);
+// rows[k] = {ptr, sj}: element (j, i) of row k goes to ptr[j * sj + i]
+template <class T> struct DistOutRow { T* ptr; long long sj; };
 template <class T>
-__global__ void scatter_rows_kernel(const T* __restrict__ src, long long sk, T* const* __restrict__ rows, int k0, int k1,
-                                    long long ncol) {
+__global__ void scatter_rows_kernel(const T* __restrict__ src, long long sk, const DistOutRow<T>* __restrict__ rows, int k0, int k1,
+                                    long long ncol, int nx) {
   const long long tot = (long long)(k1 - k0) * ncol;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
     const long long k = k0 + e / ncol, col = e - (e / ncol) * ncol;
-    rows[k][col] = src[k * sk + col];
+    const long long j = col / nx, i = col - j * nx;
+    rows[k].ptr[j * rows[k].sj + i] = src[k * sk + col];
   }
 }
 

@@ -26,6 +26,11 @@
 
 namespace cb {
 
+// where result row k of the distributed solve lives: element (j, i) of my z pencil goes to ptr[j * sj + i] on the
+// GPU that owns plane k.  The way-back buffer is ordered [j][k][i] per source rank, so that the rows one tile
+// writes to a peer are 16 KB apart (dense 2 MB windows over NVLink), not a whole pencil plane apart.
+template <class T> struct __align__(16) OutRow { T* ptr; long long sj; };
+
 template <class T> struct ThomasDev {
   int nx, ny;         // columns (x fastest)
   int n;              // rows handled: nz - q, incl. the periodic closure row
@@ -34,7 +39,7 @@ template <class T> struct ThomasDev {
   long long sj, sk;   // field strides: p[k*sk + j*sj + i]
   const T* a; const T* b; const T* c;  // device, length >= n
   const T* lam; long long lam_sj;      // lambdaxy[j*lam_sj + i]
-  T* const* out_rows; // distributed solve: row k of the result goes to out_rows[k][column] (a peer-mapped pointer);
+  const OutRow<T>* out_rows; // distributed solve: row k of the result goes to out_rows[k] (a peer-mapped pointer);
                       // nullptr = in place
   int xb, xn;         // column window of this launch: i in [xb, xb + xn) for every j (thomas_reg_kernel)
   int m;              // rows per chunk of the chunked substitution = ceil(nn/32)
@@ -670,7 +675,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
           const T pnn = p[(long long)nn * sk + pcol];
           const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[COLS + c]));
           pcl = (den == T(0)) ? T(0) : div_rn(num, den);
-          if (D.out_rows) D.out_rows[nn][col] = pcl;
+          if (D.out_rows) D.out_rows[nn].ptr[(long long)(tile / tiles_x) * D.out_rows[nn].sj + (col - (long long)(tile / tiles_x) * D.nx)] = pcl;
           else p[(long long)nn * sk + pcol] = pcl;
         }
         sP[c] = pcl;
@@ -683,10 +688,14 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         if (r < nrow) y[r] = fma(p2c[r * ncol], pcl, y[r]);
     }
     if (D.out_rows) {
-      T* const* rows = D.out_rows + k0;
+      const OutRow<T>* rows = D.out_rows + k0;
+      const long long tj = tile / tiles_x, xi = col - tj * D.nx;
 #pragma unroll
       for (int r = 0; r < MMAX; ++r)
-        if (r < nrow) rows[r][col] = y[r];
+        if (r < nrow) {
+          const longlong2 e = __ldg(reinterpret_cast<const longlong2*>(rows + r));
+          reinterpret_cast<T*>(e.x)[tj * e.y + xi] = y[r];
+        }
     } else {
       T* pc = p + (long long)k0 * sk + pcol;
       if (nrow == m) {

@@ -28,6 +28,7 @@ DIST_CASES = {
     "uneven_64x64x70": ([64, 64, 70], [1.0, 1.0, 1.0], [N, P, ["D", "D"]], C3, 1.0, np.float64, False),
     "helm_w_64x64x64": ([64, 64, 64], [1.0, 1.0, 1.0], [P, P, ["D", "D"]], ["c", "c", "f"], 1.0, np.float64, True),
     "tma_32x64x256": ([32, 64, 256], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # full chunks: TMA tile path
+    "cluster_32x64x1024": ([32, 64, 1024], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # CTA-pair Thomas + peer stores
     "fp32_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float32, False),
 }
 
