@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--r2-flags", type=int, default=-1)
     ap.add_argument("--x-variant", type=int, default=0)
     ap.add_argument("--y-variant", type=int, default=0)
-    ap.add_argument("--chain-cols", type=int, default=0)
+    ap.add_argument("--chain-cols", type=int, default=-1)
     ap.add_argument("--chain-streams", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

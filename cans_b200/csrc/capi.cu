@@ -114,7 +114,7 @@ struct cansb200_ctx {
   DevBuf ytab_fwd, ytab_bwd, ztab;
   // L2-resident chain: fft-y -> tridiagonal -> ifft-y run per window of `chain_cols` x columns, windows
   // round-robin on auxiliary streams, so that the two intermediate fields never leave the L2 cache
-  int chain_cols = 0;                          // 0 = off (three full-field passes)
+  int chain_cols = -1;                         // 0 = off (three full-field passes), -1 = auto (two half-width windows)
   int chain_nstreams = 2;
   std::vector<cudaStream_t> aux;
   std::vector<cudaEvent_t> aux_done;
@@ -774,7 +774,7 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
   if (!c) return fail(CANSB200_EINVAL, "null ctx");
   if (what == CANSB200_CTX_FORCE_GENERIC) { c->force_generic = value ? 1 : 0; return 0; }
   if (what == CANSB200_CTX_CHAIN_COLS) {
-    if (value < 0 || (value % 16) != 0) return fail(CANSB200_EINVAL, "ctx_set: chain_cols must be a non-negative multiple of 16");
+    if (value < -1 || (value > 0 && (value % 16) != 0)) return fail(CANSB200_EINVAL, "ctx_set: chain_cols must be -1 (auto), 0 (off) or a multiple of 16");
     c->chain_cols = value;
     return 0;
   }
@@ -1020,8 +1020,7 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   T* p = (T*)p_any;
   const T *lam = (const T*)lam_any, *a = (const T*)a_any, *b = (const T*)b_any, *c = (const T*)c_any;
   // host-memory mode, one rank: chunked copies overlapped with the transforms (see cansb200_ctx::host_chunks)
-  const bool chunked = mem_kind == CANSB200_MEM_HOST && ctx->nranks == 1 && ctx->host_chunks > 1 && nz >= 2 && !ctx->profiling &&
-                       !(ctx->chain_cols > 0 && ctx->chain_cols < nx);
+  const bool chunked = mem_kind == CANSB200_MEM_HOST && ctx->nranks == 1 && ctx->host_chunks > 1 && nz >= 2 && !ctx->profiling;
   const size_t plane = (size_t)px * py;
   if (mem_kind == CANSB200_MEM_HOST) {
     if (ctx->staging.ensure(nh * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: staging");
@@ -1111,7 +1110,9 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   if (rc) return rc;
   prof_mark(ctx, st);
   R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nz, ny, 1};
-  const int W = ctx->chain_cols;
+  // auto: two half-width windows on two streams; the windows' kernels overlap each other's ramp-up / ramp-down
+  // (measured -3 % on C3; windows small enough to stay in L2 lose more to launch tails than they gain)
+  const int W = ctx->chain_cols >= 0 ? ctx->chain_cols : ((nx >= 1024 && (nx / 2) % 16 == 0) ? nx / 2 : 0);
   if (W > 0 && W < nx && thomas_is_pipelined(pl) && !ctx->profiling) {
     // ---- L2-resident chain over x windows, round-robin on auxiliary streams
     ThomasDev<T> D = make_thomas<T>(pl, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, lam, a, b, c);

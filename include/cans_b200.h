@@ -143,7 +143,8 @@ enum {
   CANSB200_CTX_FORCE_GENERIC = 0,
   CANSB200_CTX_X_VARIANT = 1,   /* tuning variant (thread / radix split) of the contiguous transforms, 0 = default */
   CANSB200_CTX_Y_VARIANT = 2,   /* same for the strided transforms */
-  CANSB200_CTX_CHAIN_COLS = 3,  /* x-window (multiple of 16 columns) of the L2-resident fft-y -> tridiagonal -> ifft-y chain; 0 = off */
+  CANSB200_CTX_CHAIN_COLS = 3,  /* x-window (multiple of 16 columns) of the fft-y -> tridiagonal -> ifft-y chain run window by window on auxiliary streams;
+                                   0 = off, -1 = auto (default: two half-width windows, whose kernels overlap each other's tails) */
   CANSB200_CTX_CHAIN_STREAMS = 4, /* auxiliary streams the windows are issued on (1..8) */
   CANSB200_CTX_HOST_CHUNKS = 6,  /* host-memory solves: z-plane chunks whose PCIe copies overlap the x / y transforms (1 = off, default 16) */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
