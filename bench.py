@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--chain-streams", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fp32", action="store_true", help="the -D_SINGLE_PRECISION build of CaNS (not the headline; FP64 is)")
     ap.add_argument("--host-chunks", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -219,7 +220,9 @@ def main():
     dzc, dzf = gridgen.initgrid(1, ng[2], gr, l[2], per_z)
     dli = [ng[0] / l[0], ng[1] / l[1], ng[2] / l[2]]
     # N > 1: ONE global grid, z slabs over the N GPUs of the box (strong scaling, BASELINE.json "1/2/4/8 B200")
-    ctx = cb.Context(ng, rank=rank, nranks=world)
+    fp32 = bool(args.fp32)
+    tdt, ndt, esz = (torch.float32, np.float32, 4) if fp32 else (torch.float64, np.float64, 8)
+    ctx = cb.Context(ng, is_fp32=fp32, rank=rank, nranks=world)
     ctx.connect()
     ctx.set_variant(args.x_variant, args.y_variant)
     if args.r2_flags >= 0:
@@ -231,12 +234,12 @@ def main():
     shp = (nl[2] + 2, nl[1] + 2, nl[0] + 2)
     npts = ng[0] * ng[1] * ng[2]    # global points
     npts_local = nl[0] * nl[1] * nl[2]
-    p = torch.empty(shp, dtype=torch.float64, device=dev)
+    p = torch.empty(shp, dtype=tdt, device=dev)
     S.fill_hash(ctx, p, nl, ctx.lo, 1, 123)   # hash of the GLOBAL index: every decomposition sees the same field
     I = (slice(1, -1),) * 3
     if all(b[0] in "PN" for b in cbc):
         z0 = ctx.lo[2] - 1
-        wz = torch.from_numpy(dzf[1 + z0:1 + z0 + nl[2]]).to(dev)[:, None, None]
+        wz = torch.from_numpy(dzf[1 + z0:1 + z0 + nl[2]].astype(ndt)).to(dev)[:, None, None]
         num = (p[I] * wz).sum()
         den = wz.sum() * ng[0] * ng[1]
         if world > 1:
@@ -247,6 +250,15 @@ def main():
     def step():
         cb.solver(nl, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, p)
 
+    # FP32 only: the null-space mode of the singular operator is not pinned on a stretched grid, so
+    # feeding a solution back as the next right-hand side overflows single precision after a few solves.  The FP32
+    # line therefore restores the right-hand side before every solve (outside the per-solve CUDA events).
+    p0 = p.clone() if fp32 else None
+
+    def reset():
+        if fp32:
+            p.copy_(p0)
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -254,6 +266,7 @@ def main():
             torch.cuda.synchronize()
 
     for _ in range(max(3, args.warmup)):
+        reset()
         step()
     sync_all()
     l0 = sd.arrplan.stats()["launches"]
@@ -262,12 +275,24 @@ def main():
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync_all()
-    ms_total = ev0.elapsed_time(ev1)
+    if not fp32:
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        sync_all()
+        ms_total = ev0.elapsed_time(ev1)
+    else:
+        evs = []
+        for _ in range(args.steps):
+            reset()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            step()
+            a1.record()
+            evs.append((a0, a1))
+        sync_all()
+        ms_total = sum(a0.elapsed_time(a1) for a0, a1 in evs)
     clocks = sampler.stop() if rank == 0 else None
     launches = sd.arrplan.stats()["launches"] - l0
     if world > 1:
@@ -283,6 +308,7 @@ def main():
     # ---- per-stage device times (live, CUDA events on the solve's stream) -> roofline of the dominant kernel
     ctx.set_profiling(True)
     for _ in range(args.steps):
+        reset()
         step()
     prof, nprof = ctx.get_profile()
     ctx.set_profiling(False)
@@ -297,24 +323,24 @@ def main():
         stage_ms = {k: float(v) for k, v in zip(keys, t.tolist())}
         heavy = {k: v for k, v in stage_ms.items() if k != "pivot_cache"}
         dom = max(heavy, key=heavy.get)
-    stage_bytes = STAGE_BYTES_PER_POINT_FP64 * npts_local   # per GPU: each rank's launch covers its local points
+    stage_bytes = STAGE_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local   # per GPU: each rank's launch covers its local points
     achieved = stage_bytes / (stage_ms[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+            traffic = None if fp32 else json.load(open(tpath)).get(args.workload, {}).get(dom)
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes,
                 "stage_ms": stage_ms,
-                "solve": {"algorithmic_bytes_per_gpu": ALGO_BYTES_PER_POINT_FP64 * npts_local,
-                          "achieved": ALGO_BYTES_PER_POINT_FP64 * npts_local / (ms_per_step * 1e-3) / 1e9,
-                          "frac": ALGO_BYTES_PER_POINT_FP64 * npts_local / (ms_per_step * 1e-3) / 1e9 / peak}}
+                "solve": {"algorithmic_bytes_per_gpu": ALGO_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local,
+                          "achieved": ALGO_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local / (ms_per_step * 1e-3) / 1e9,
+                          "frac": ALGO_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local / (ms_per_step * 1e-3) / 1e9 / peak}}
     if world > 1:
         # two exchanges per solve, each sends (P-1)/P of the local field per GPU per direction
-        nvb = 2.0 * (world - 1) / world * npts_local * 8.0
+        nvb = 2.0 * (world - 1) / world * npts_local * float(esz)
         roofline["nvlink"] = {"bytes_per_gpu_per_direction_per_solve": nvb, "peak_GBs": 770.0,
                               "peak_source": "B200_PROFILING.md measured peer copy (900 nominal)",
                               "floor_ms": nvb / 770e9 * 1e3,
@@ -324,35 +350,39 @@ def main():
     # ---- e2e: the host-memory API (mode A of SURVEY 8b): pinned host p, H2D + solve + D2H per step
     e2e = None
     if not args.no_e2e:
-        nb = int(np.prod(shp)) * 8
+        nb = int(np.prod(shp)) * esz
         if world == 1:
             ctx.set_host_chunks(args.host_chunks)
             if args.host_chunks > 1:   # chunked pipeline: only the interior z planes travel (halo planes are never read)
-                nb = nl[2] * shp[1] * shp[2] * 8
-        ph = torch.empty(shp, dtype=torch.float64).pin_memory()
+                nb = nl[2] * shp[1] * shp[2] * esz
+        ph = torch.empty(shp, dtype=tdt).pin_memory()
         ph.copy_(p)
         pn = ph.numpy()
         hs = sd.host
         ne2e = max(1, min(args.steps, 5))
         cb.solver(nl, ng, sd.arrplan, sd.normfft, hs["lambdaxy"], hs["a"], hs["b"], hs["c"], cbc, cf, pn)  # warm-up
         sync_all()
-        t0 = time.perf_counter()
+        el = 0.0
+        ph0 = ph.clone() if fp32 else None
         for _ in range(ne2e):
+            if fp32:
+                ph.copy_(ph0)
+            t0 = time.perf_counter()
             cb.solver(nl, ng, sd.arrplan, sd.normfft, hs["lambdaxy"], hs["a"], hs["b"], hs["c"], cbc, cf, pn)
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            el += time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([el], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
         e2e = {"value": el / ne2e * 1e9 / total_pts, "unit": UNIT,
-               "h2d_bytes_per_step": (nb + 8 * (3 * ng[2] + ctx.n_z[0] * ctx.n_z[1])) * world,
+               "h2d_bytes_per_step": (nb + esz * (3 * ng[2] + ctx.n_z[0] * ctx.n_z[1])) * world,
                "d2h_bytes_per_step": nb * world, "steps": ne2e, "ms_per_step": el / ne2e * 1e3,
                "host_chunks": args.host_chunks if world == 1 else 1}
         del ph
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not fp32:
         r = cpu_solve_sample(args.workload, seconds_target=15.0)
         cpu = {"value": r["ns_per_point"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
@@ -360,7 +390,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if fp32 else "f64", "data": "synthetic",
             "config": {"workload": args.workload, "grid": ng, "bc": "".join(b[0] + b[1] for b in cbc), "gr": gr,
                        "decomposition": "single GPU" if world == 1 else f"z slabs over {world} GPUs (x pencils, dims=[1,{world}]), "
                                         "transposes = peer-mapped stores over NVLink",

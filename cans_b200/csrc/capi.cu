@@ -23,7 +23,7 @@ using namespace cb;
 namespace cb {
 // explicit instantiations live in r2r2_{x,y}{64,32}.cu
 template <class T, bool YMODE, bool SPLIT> int r2r2_run(const R2Args<T>& A, int n, int var, bool fwd, cudaStream_t st);
-template <bool YMODE> int r2r2_query(int n, int var, int radix[4]);
+template <bool YMODE, bool F32> int r2r2_query(int n, int var, int radix[4]);
 extern template int r2r2_run<double, false, false>(const R2Args<double>&, int, int, bool, cudaStream_t);
 extern template int r2r2_run<double, true, false>(const R2Args<double>&, int, int, bool, cudaStream_t);
 extern template int r2r2_run<float, false, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
@@ -31,8 +31,10 @@ extern template int r2r2_run<float, true, false>(const R2Args<float>&, int, int,
 extern template int r2r2_run<double, true, true>(const R2Args<double>&, int, int, bool, cudaStream_t);
 extern template int r2r2_run<float, true, true>(const R2Args<float>&, int, int, bool, cudaStream_t);
 extern int g_r2_default_carveout;   // 1: do not force the maximum shared-memory carveout (capi.cu owns it)
-extern template int r2r2_query<false>(int, int, int[4]);
-extern template int r2r2_query<true>(int, int, int[4]);
+extern template int r2r2_query<false, false>(int, int, int[4]);
+extern template int r2r2_query<true, false>(int, int, int[4]);
+extern template int r2r2_query<false, true>(int, int, int[4]);
+extern template int r2r2_query<true, true>(int, int, int[4]);
 }  // namespace cb
 
 namespace cb { int g_r2_default_carveout = 1; }
@@ -123,6 +125,8 @@ struct cansb200_ctx {
   // host-memory mode: the z planes travel in chunks on two copy streams so that the x / y transforms of a chunk
   // overlap the PCIe transfer of the others (only the tridiagonal stage needs the whole field)
   int host_chunks = 16;
+  int pin_host = 0;                             // 1: page-lock the caller's host array on first use (cudaHostRegister)
+  std::vector<std::pair<void*, size_t>> pinned; // what we registered (released in cansb200_finalize)
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
@@ -175,10 +179,11 @@ template <> std::map<int, R2Tables<float>>& r2tabmap<float>(cansb200_ctx* c) { r
 template <class T> static int get_r2_tables(cansb200_ctx* ctx, int n, int ymode, int& var, R2Tables<T>** out) {
   auto& mp = r2tabmap<T>(ctx);
   int radix[4];
-  int ns = ymode ? r2r2_query<true>(n, var, radix) : r2r2_query<false>(n, var, radix);
+  constexpr bool F32 = sizeof(T) == 4;
+  int ns = ymode ? r2r2_query<true, F32>(n, var, radix) : r2r2_query<false, F32>(n, var, radix);
   if (ns < 1 && var != 0) {
     var = 0;
-    ns = ymode ? r2r2_query<true>(n, var, radix) : r2r2_query<false>(n, var, radix);
+    ns = ymode ? r2r2_query<true, F32>(n, var, radix) : r2r2_query<false, F32>(n, var, radix);
   }
   const int key = (n * 4 + var) * 2 + (ymode ? 1 : 0);
   auto it = mp.find(key);
@@ -400,12 +405,12 @@ static cb_encode_tiled_fn get_encode_tiled() {
   }
   return fn;
 }
-// tiles of {16 columns x box_rows rows}: rank 3 = (x, y, row), rank 4 adds the cache slot
+// tiles of {box_cols columns (one 128-byte row segment) x box_rows rows}: rank 3 = (x, y, row), rank 4 adds the cache slot
 static bool encode_tile_map(CUtensorMap* m, const void* base, size_t esz, int rank, const cuuint64_t dims[4],
-                            const cuuint64_t strides_bytes[3], int box_rows) {
+                            const cuuint64_t strides_bytes[3], int box_rows, int box_cols) {
   cb_encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return false;
-  cuuint32_t box[4] = {16u, 1u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1u, (cuuint32_t)box_rows, 1u};
   cuuint32_t es[4] = {1u, 1u, 1u, 1u};
   for (int d = 0; d + 1 < rank; ++d)
     if (strides_bytes[d] % 16 != 0 || strides_bytes[d] >= (1ULL << 40)) return false;
@@ -416,16 +421,16 @@ static bool encode_tile_map(CUtensorMap* m, const void* base, size_t esz, int ra
 }
 
 template <class T>
-static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p, int box_rows, const CUtensorMap** mp,
-                            const CUtensorMap** mz) {
-  if (!pl->use_tma || D.nx < 16) return false;
+static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p, int box_rows, int box_cols,
+                            const CUtensorMap** mp, const CUtensorMap** mz) {
+  if (!pl->use_tma || D.nx < box_cols) return false;
   const size_t esz = sizeof(T);
   const unsigned long long zkey[4] = {(unsigned long long)(uintptr_t)pl->zcache.p, (unsigned long long)D.nx, (unsigned long long)D.ny,
                                       ((unsigned long long)D.nn << 20) | (unsigned long long)box_rows};
   if (memcmp(zkey, pl->map_z_key, sizeof(zkey)) != 0) {
     const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nn, (cuuint64_t)pl->nslots};
     const cuuint64_t st[3] = {(cuuint64_t)D.nx * esz, (cuuint64_t)D.nx * D.ny * esz, (cuuint64_t)pl->slot_z * esz};
-    if (!encode_tile_map(&pl->map_z, pl->zcache.p, esz, 4, dims, st, box_rows)) { pl->use_tma = false; return false; }
+    if (!encode_tile_map(&pl->map_z, pl->zcache.p, esz, 4, dims, st, box_rows, box_cols)) { pl->use_tma = false; return false; }
     memcpy(pl->map_z_key, zkey, sizeof(zkey));
   }
   *mz = &pl->map_z;
@@ -438,7 +443,7 @@ static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p
   e.p = p; e.sj = D.sj; e.sk = D.sk; e.nx = D.nx; e.ny = D.ny; e.nn = D.nn; e.box_rows = box_rows;
   const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nn, 1};
   const cuuint64_t st[3] = {(cuuint64_t)D.sj * esz, (cuuint64_t)D.sk * esz, 0};
-  if (!encode_tile_map(&e.m, p, esz, 3, dims, st, box_rows)) return false;
+  if (!encode_tile_map(&e.m, p, esz, 3, dims, st, box_rows, box_cols)) return false;
   if (pl->map_p.size() >= 16) pl->map_p.erase(pl->map_p.begin());
   pl->map_p.push_back(e);
   *mp = &pl->map_p.back().m;
@@ -492,12 +497,12 @@ static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_
 template <class T, int MMAX, int COLS, int CL>
 static int launch_pipe_sel(cansb200_ctx* ctx, const ThomasDev<T>& D, cansb200_plan* pl, T* p, T norm, bool exact, bool vec,
                            cudaStream_t st) {
-  if (exact && vec && COLS == 16 && pl->th_variant != 3) {
+  if (exact && vec && COLS * sizeof(T) == 128 && pl->th_variant != 3) {
     // TMA boxes of 256 / 128 / 64 rows, whichever divides the rows of one CTA
     const int rows = (CB_TH_THREADS / COLS) * MMAX;
     const int box_rows = rows % 256 == 0 ? 256 : (rows % 128 == 0 ? 128 : 64);
     const CUtensorMap *mp = nullptr, *mz = nullptr;
-    if (thomas_tma_maps<T>(pl, D, p, box_rows, &mp, &mz))
+    if (thomas_tma_maps<T>(pl, D, p, box_rows, COLS, &mp, &mz))
       return launch_pipe<T, MMAX, true, CB_TH_LD_TMA, COLS, CL>(ctx, D, pl, p, norm, mp, mz, box_rows, st);
   }
   if (exact && vec) return launch_pipe<T, MMAX, true, CB_TH_LD_VEC, COLS, CL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
@@ -532,15 +537,28 @@ template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T
     const bool vec = (D.nx % vw) == 0 && (D.xb % vw) == 0 && (D.sk % vw) == 0 && (D.sj % vw) == 0 && ((uintptr_t)p % 16) == 0 &&
                      ((uintptr_t)pl->zcache.p % 16) == 0 && (pl->slot_z % vw) == 0 && (D.xn % vw) == 0;
     const bool exact = D.m == pl->th_mmax;
-    if (pl->th_cols == 16 && pl->th_cl == 1) {
-      if (pl->th_mmax == 4) return launch_pipe_sel<T, 4, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
-      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
-    } else if (pl->th_cols == 16 && pl->th_cl == 2) {
-      if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 16, 2>(ctx, D, pl, p, norm, exact, vec, st);
-      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16, 2>(ctx, D, pl, p, norm, exact, vec, st);
-    } else if (pl->th_cols == 8) {
-      if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 8, 1>(ctx, D, pl, p, norm, exact, vec, st);
-      if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 8, 1>(ctx, D, pl, p, norm, exact, vec, st);
+    if constexpr (sizeof(T) == 8) {
+      if (pl->th_cols == 16 && pl->th_cl == 1) {
+        if (pl->th_mmax == 4) return launch_pipe_sel<T, 4, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
+        if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
+      } else if (pl->th_cols == 16 && pl->th_cl == 2) {
+        if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 16, 2>(ctx, D, pl, p, norm, exact, vec, st);
+        if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16, 2>(ctx, D, pl, p, norm, exact, vec, st);
+      } else if (pl->th_cols == 8) {
+        if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 8, 1>(ctx, D, pl, p, norm, exact, vec, st);
+        if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 8, 1>(ctx, D, pl, p, norm, exact, vec, st);
+      }
+    } else {
+      // FP32: 32 columns make the 128-byte row segment (32 chunks of up to 16 rows per column)
+      if (pl->th_cols == 32 && pl->th_cl == 1) {
+        if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 32, 1>(ctx, D, pl, p, norm, exact, vec, st);
+        if (pl->th_mmax == 16) return launch_pipe_sel<T, 16, 32, 1>(ctx, D, pl, p, norm, exact, vec, st);
+      } else if (pl->th_cols == 32 && pl->th_cl == 2) {
+        if (pl->th_mmax == 12) return launch_pipe_sel<T, 12, 32, 2>(ctx, D, pl, p, norm, exact, vec, st);
+        if (pl->th_mmax == 16) return launch_pipe_sel<T, 16, 32, 2>(ctx, D, pl, p, norm, exact, vec, st);
+      } else if (pl->th_cols == 16) {
+        if (pl->th_mmax == 16) return launch_pipe_sel<T, 16, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
+      }
     }
     return fail(CANSB200_EUNSUPPORTED, "gaussel: no pipelined kernel for this chunk length");
   }
@@ -748,6 +766,7 @@ int cansb200_finalize(cansb200_ctx* c) {
   for (cudaStream_t q : c->aux) cudaStreamDestroy(q);
   for (cudaEvent_t q : c->aux_done) cudaEventDestroy(q);
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+  for (auto& q : c->pinned) cudaHostUnregister(q.first);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   for (cudaEvent_t q : c->chunk_ev) cudaEventDestroy(q);
@@ -786,6 +805,10 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
   if (what == CANSB200_CTX_X_VARIANT || what == CANSB200_CTX_Y_VARIANT) {
     if (value < 0 || value > 3) return fail(CANSB200_EINVAL, "ctx_set: variant must be 0..3");
     c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_PIN_HOST) {
+    c->pin_host = value ? 1 : 0;
     return 0;
   }
   if (what == CANSB200_CTX_HOST_CHUNKS) {
@@ -847,19 +870,22 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   // pipelined substitution: 16 columns x 64 chunks up to 512 rows; up to 1024 rows a cluster of two CTAs shares
   // the 16-column tile (variant 1) or one CTA takes 8 columns x 128 chunks (variant 2, and periodic z)
   int variant = o.thomas_variant >= 0 ? o.thomas_variant : 1;
-  pl->th_cols = 16;
+  const int wide = ctx->is_fp32 ? 32 : 16;   // columns of a 128-byte row segment
+  pl->th_cols = wide;
   pl->th_cl = 1;
   if (pl->th_nn > 512) {
     if (variant == 1 && !pl->periodic_z) pl->th_cl = 2;
-    else pl->th_cols = 8;
+    else pl->th_cols = wide / 2;
   }
   if (variant == 2) variant = 1;
   if (variant > 3) variant = 1;   // 3 = as 1, tiles fetched with cp.async instead of TMA
   const int chunks = CB_TH_THREADS / pl->th_cols * pl->th_cl;   // chunks per column over the whole cluster
   pl->th_m = (pl->th_nn + chunks - 1) / chunks;
-  if (pl->th_m > 8) variant = 0;   // nz > 1024: the sequential kernel
+  const int m_cap = ctx->is_fp32 ? 16 : 8;
+  if (pl->th_m > m_cap) variant = 0;   // nz > 1024: the sequential kernel
   pl->th_variant = variant;
-  pl->th_mmax = (pl->th_cols == 16 && pl->th_cl == 1) ? (pl->th_m <= 4 ? 4 : 8) : (pl->th_m <= 6 ? 6 : 8);
+  if (!ctx->is_fp32) pl->th_mmax = (pl->th_cols == 16 && pl->th_cl == 1) ? (pl->th_m <= 4 ? 4 : 8) : (pl->th_m <= 6 ? 6 : 8);
+  else pl->th_mmax = pl->th_cols == 16 ? 16 : (pl->th_cl == 1 ? (pl->th_m <= 8 ? 8 : 16) : (pl->th_m <= 12 ? 12 : 16));
   pl->nslots = o.cache_slots >= 1 ? (o.cache_slots > CB_MAX_SLOTS ? CB_MAX_SLOTS : o.cache_slots) : 1;
   const long long ncol = (long long)ctx->n_z[0] * ctx->n_z[1];
   pl->slot_z = ncol * pl->th_nn;
@@ -1022,6 +1048,18 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   // host-memory mode, one rank: chunked copies overlapped with the transforms (see cansb200_ctx::host_chunks)
   const bool chunked = mem_kind == CANSB200_MEM_HOST && ctx->nranks == 1 && ctx->host_chunks > 1 && nz >= 2 && !ctx->profiling;
   const size_t plane = (size_t)px * py;
+  if (mem_kind == CANSB200_MEM_HOST && ctx->pin_host) {
+    // a pageable Fortran array copies at a fraction of the PCIe rate: page-lock it once (CaNS allocates p once per run)
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p_any) == cudaSuccess && at.type == cudaMemoryTypeUnregistered) {
+      if (cudaHostRegister(p_any, nh * sizeof(T), cudaHostRegisterDefault) == cudaSuccess)
+        ctx->pinned.emplace_back(p_any, nh * sizeof(T));
+      else
+        cudaGetLastError();   // not fatal: the copies just stay pageable
+    } else {
+      cudaGetLastError();
+    }
+  }
   if (mem_kind == CANSB200_MEM_HOST) {
     if (ctx->staging.ensure(nh * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: staging");
     const size_t nzg = (size_t)ctx->n_z[2], nlam = (size_t)ctx->n_z[0] * ctx->n_z[1];   // a, b, c(n_z(3)); lambdaxy(n_z(1), n_z(2))

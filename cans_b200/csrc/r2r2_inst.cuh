@@ -43,6 +43,21 @@ namespace cb {
   X(768, 2, 64, 4, 3, 12, 4, 4, 4)    \
   X(768, 3, 32, 4, 4, 12, 8, 8, 1)
 
+// y mode, FP32: 16 pairs of floats = one 128-byte row
+#define CB_R2_Y32_CONFIGS(X)          \
+  X(64, 0, 4, 16, 1, 16, 4, 1, 1)     \
+  X(128, 0, 8, 16, 1, 16, 8, 1, 1)    \
+  X(256, 0, 16, 16, 1, 16, 16, 1, 1)  \
+  X(512, 0, 32, 16, 2, 16, 8, 4, 1)   \
+  X(512, 1, 64, 16, 1, 8, 8, 8, 1)    \
+  X(512, 2, 64, 8, 2, 8, 8, 8, 1)     \
+  X(1024, 0, 64, 16, 1, 16, 8, 8, 1)  \
+  X(1024, 1, 128, 4, 2, 8, 8, 4, 4)   \
+  X(2048, 0, 128, 8, 1, 16, 16, 8, 1) \
+  X(384, 0, 32, 16, 1, 12, 4, 4, 2)   \
+  X(768, 0, 32, 16, 2, 12, 8, 8, 1)   \
+  X(768, 1, 64, 8, 2, 12, 4, 4, 4)
+
 extern int g_r2_default_carveout;
 
 template <class K>
@@ -98,7 +113,9 @@ static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
 template <class T, bool YMODE, bool SPLIT> int r2r2_run(const R2Args<T>& A, int n, int var, bool fwd, cudaStream_t st) {
 #define CB_R2_CASE(N_, V_, TPL_, G_, MB_, R0_, R1_, R2_, R3_) \
   case N_ * 4 + V_: return r2r2_launch<T, R2Cfg<N_, TPL_, G_, MB_, R0_, R1_, R2_, R3_>, YMODE, SPLIT>(A, fwd, st);
-  if constexpr (YMODE) {
+  if constexpr (YMODE && sizeof(T) == 4) {
+    switch (n * 4 + var) { CB_R2_Y32_CONFIGS(CB_R2_CASE) default: return 1; }
+  } else if constexpr (YMODE) {
     switch (n * 4 + var) { CB_R2_Y_CONFIGS(CB_R2_CASE) default: return 1; }
   } else {
     switch (n * 4 + var) { CB_R2_X_CONFIGS(CB_R2_CASE) default: return 1; }
@@ -107,10 +124,12 @@ template <class T, bool YMODE, bool SPLIT> int r2r2_run(const R2Args<T>& A, int 
 }
 
 // radices of variant `var` for length n (host-side table construction); returns the stage count or 0
-template <bool YMODE> int r2r2_query(int n, int var, int radix[4]) {
+template <bool YMODE, bool F32> int r2r2_query(int n, int var, int radix[4]) {
 #define CB_R2_CASE(N_, V_, TPL_, G_, MB_, R0_, R1_, R2_, R3_) \
   case N_ * 4 + V_: radix[0] = R0_; radix[1] = R1_; radix[2] = R2_; radix[3] = R3_; return R2Cfg<N_, TPL_, G_, MB_, R0_, R1_, R2_, R3_>::NS;
-  if constexpr (YMODE) {
+  if constexpr (YMODE && F32) {
+    switch (n * 4 + var) { CB_R2_Y32_CONFIGS(CB_R2_CASE) default: return 0; }
+  } else if constexpr (YMODE) {
     switch (n * 4 + var) { CB_R2_Y_CONFIGS(CB_R2_CASE) default: return 0; }
   } else {
     switch (n * 4 + var) { CB_R2_X_CONFIGS(CB_R2_CASE) default: return 0; }

@@ -2,4 +2,5 @@
 #include "r2r2_inst.cuh"
 namespace cb {
 template int r2r2_run<float, false, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
+template int r2r2_query<false, true>(int, int, int[4]);
 }  // namespace cb

@@ -2,5 +2,5 @@
 #include "r2r2_inst.cuh"
 namespace cb {
 template int r2r2_run<double, false, false>(const R2Args<double>&, int, int, bool, cudaStream_t);
-template int r2r2_query<false>(int, int, int[4]);
+template int r2r2_query<false, false>(int, int, int[4]);
 }  // namespace cb

@@ -219,6 +219,15 @@ def test_host_memory_mode(cb):
     ph = p.copy()
     cb.solver(cs["ng"], cs["ng"], sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cs["cbc"], cs["c_or_f"], ph)
     assert cases.rel_l2(ph, ref) < 1e-12
+    # one copy each way (no chunk pipeline), then with the caller's array page-locked on first use
+    for chunks, pin in ((1, False), (3, True), (16, True)):
+        ctx.set_host_chunks(chunks)
+        ctx.set_pin_host(pin)
+        ph = p.copy()
+        for _ in range(2):   # the second call finds the array already registered
+            ph[...] = p
+            cb.solver(cs["ng"], cs["ng"], sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cs["cbc"], cs["c_or_f"], ph)
+            assert cases.rel_l2(ph, ref) < 1e-12
 
 
 def test_factorisation_cache(cb):
