@@ -14,11 +14,14 @@
 //       keyed by a device-side content hash (no host sync).
 //   thomas_seq_kernel    : one thread per column, two sweeps through global
 //       memory using the cached pivots, reference operation order.  Any nz.
-//   thomas_warp_kernel   : one WARP per column; each lane keeps a chunk of m
-//       rows (values and pivots) in registers and the two first-order linear
-//       recurrences are evaluated chunk-parallel (local sweep, warp-shuffle
-//       scan of the affine maps, fix-up).  p' never leaves the chip: traffic
-//       is read p + read z + write p = 24 B/pt instead of 48.
+//   thomas_pipe_kernel   : persistent tiles of {one 128-byte row segment of
+//       columns x all rows}, fetched by TMA while the previous tile is solved;
+//       every thread keeps a chunk of m rows (values and pivots) in registers
+//       and the two first-order linear recurrences are evaluated chunk-parallel
+//       (local sweep, warp-shuffle scan of the affine chunk maps, fix-up).  p'
+//       never leaves the chip: traffic is read p + read z + write p = 24 B/pt
+//       instead of 48.  Above 512 rows a cluster of two CTAs shares the tile
+//       and hands the carries over through distributed shared memory.
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
