@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fp32", action="store_true", help="the -D_SINGLE_PRECISION build of CaNS (not the headline; FP64 is)")
     ap.add_argument("--host-chunks", type=int, default=16)
+    ap.add_argument("--zmajor", type=int, default=-1)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -228,6 +229,8 @@ def main():
     if args.r2_flags >= 0:
         ctx.set_r2_flags(args.r2_flags)
     ctx.set_chain(args.chain_cols, args.chain_streams)
+    if args.zmajor >= 0:
+        ctx.set_zmajor(bool(args.zmajor))
     sd = cb.initsolver(ctx, ng, dli, 1.0 / dzc, 1.0 / dzf, cbc, [[0.0, 0.0]] * 3, cf, device=dev,
                        thomas_variant=args.thomas, fft_x_lines=args.fft_x_lines, fft_y_lines=args.fft_y_lines)
     nl = ctx.n                      # local x pencil (nx, ny, nz / N)

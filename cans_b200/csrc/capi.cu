@@ -92,6 +92,8 @@ struct cansb200_ctx {
   size_t esz;
   int num_sms = 148;
   DevBuf scratch;   // haloless field buffer A (x pencil)
+  DevBuf scratch2;  // z-major copy B[j][k][i] of the middle stages (zmajor)
+  int zmajor = 1;   // 1: the y transforms write / read B, so that every row stream of the tridiagonal stage is 8 KB-strided
   DevBuf staging;   // haloed p when the caller's p is host memory
   DevBuf coef;      // a, b, c, lambdaxy staged from the host
   DevBuf zero_lam;  // all-zero lambdaxy of the z-only solve (solver_gaussel_z)
@@ -407,10 +409,11 @@ static cb_encode_tiled_fn get_encode_tiled() {
 }
 // tiles of {box_cols columns (one 128-byte row segment) x box_rows rows}: rank 3 = (x, y, row), rank 4 adds the cache slot
 static bool encode_tile_map(CUtensorMap* m, const void* base, size_t esz, int rank, const cuuint64_t dims[4],
-                            const cuuint64_t strides_bytes[3], int box_rows, int box_cols) {
+                            const cuuint64_t strides_bytes[3], int box_rows, int box_cols, bool rows_second) {
   cb_encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return false;
-  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, 1u, (cuuint32_t)box_rows, 1u};   // field: (x, y, row)
+  if (rows_second) { box[1] = (cuuint32_t)box_rows; box[2] = 1u; }             // pivot cache: (x, row, y, slot)
   cuuint32_t es[4] = {1u, 1u, 1u, 1u};
   for (int d = 0; d + 1 < rank; ++d)
     if (strides_bytes[d] % 16 != 0 || strides_bytes[d] >= (1ULL << 40)) return false;
@@ -428,9 +431,10 @@ static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p
   const unsigned long long zkey[4] = {(unsigned long long)(uintptr_t)pl->zcache.p, (unsigned long long)D.nx, (unsigned long long)D.ny,
                                       ((unsigned long long)D.nn << 20) | (unsigned long long)box_rows};
   if (memcmp(zkey, pl->map_z_key, sizeof(zkey)) != 0) {
-    const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nn, (cuuint64_t)pl->nslots};
-    const cuuint64_t st[3] = {(cuuint64_t)D.nx * esz, (cuuint64_t)D.nx * D.ny * esz, (cuuint64_t)pl->slot_z * esz};
-    if (!encode_tile_map(&pl->map_z, pl->zcache.p, esz, 4, dims, st, box_rows, box_cols)) { pl->use_tma = false; return false; }
+    // pivot cache z[slot][j][k][i]: tensor (x, row, y, slot)
+    const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.nn, (cuuint64_t)D.ny, (cuuint64_t)pl->nslots};
+    const cuuint64_t st[3] = {(cuuint64_t)D.nx * esz, (cuuint64_t)D.nx * D.nn * esz, (cuuint64_t)pl->slot_z * esz};
+    if (!encode_tile_map(&pl->map_z, pl->zcache.p, esz, 4, dims, st, box_rows, box_cols, true)) { pl->use_tma = false; return false; }
     memcpy(pl->map_z_key, zkey, sizeof(zkey));
   }
   *mz = &pl->map_z;
@@ -443,7 +447,7 @@ static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p
   e.p = p; e.sj = D.sj; e.sk = D.sk; e.nx = D.nx; e.ny = D.ny; e.nn = D.nn; e.box_rows = box_rows;
   const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nn, 1};
   const cuuint64_t st[3] = {(cuuint64_t)D.sj * esz, (cuuint64_t)D.sk * esz, 0};
-  if (!encode_tile_map(&e.m, p, esz, 3, dims, st, box_rows, box_cols)) return false;
+  if (!encode_tile_map(&e.m, p, esz, 3, dims, st, box_rows, box_cols, false)) return false;
   if (pl->map_p.size() >= 16) pl->map_p.erase(pl->map_p.begin());
   pl->map_p.push_back(e);
   *mp = &pl->map_p.back().m;
@@ -755,7 +759,7 @@ int cansb200_dist_status(cansb200_ctx* c, int* status) {
 
 int cansb200_finalize(cansb200_ctx* c) {
   if (!c) return 0;
-  c->scratch.release(); c->staging.release(); c->coef.release(); c->zero_lam.release();
+  c->scratch.release(); c->scratch2.release(); c->staging.release(); c->coef.release(); c->zero_lam.release();
   for (auto& kv : c->tabs64) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (auto& kv : c->tabs32) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (int q = 0; q < (int)c->peer.size(); ++q)
@@ -805,6 +809,10 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
   if (what == CANSB200_CTX_X_VARIANT || what == CANSB200_CTX_Y_VARIANT) {
     if (value < 0 || value > 3) return fail(CANSB200_EINVAL, "ctx_set: variant must be 0..3");
     c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_ZMAJOR) {
+    c->zmajor = value ? 1 : 0;
     return 0;
   }
   if (what == CANSB200_CTX_PIN_HOST) {
@@ -1148,12 +1156,27 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   if (rc) return rc;
   prof_mark(ctx, st);
   R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nz, ny, 1};
+  // z-major middle stages: B[j][k][i]; the y transforms go A -> B and B -> A, the tridiagonal stage works on B
+  bool zm = ctx->zmajor && kind_is_fast(pl->kind[1][0]) && kind_is_fast(pl->kind[1][1]) && pl->nt[1] == ny && !ctx->force_generic;
+  if (zm) {
+    R2Tables<T>* rt = nullptr;
+    int var = ctx->r2_variant[1];
+    if (get_r2_tables<T>(ctx, pl->nt[1], 1, var, &rt) || !rt) zm = false;
+  }
+  T* B = nullptr;
+  if (zm) {
+    if (ctx->scratch2.ensure((size_t)nx * ny * nz * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: z-major buffer");
+    B = (T*)ctx->scratch2.p;
+  }
+  const R2RGeom gyf{nx, (long long)nx * nz, 1, 1, (long long)nx * ny, nx, nx, nz, ny, 1};
+  const R2RGeom gyb{(long long)nx * nz, nx, 1, 1, nx, (long long)nx * ny, nx, nz, ny, 1};
   // auto: two half-width windows on two streams; the windows' kernels overlap each other's ramp-up / ramp-down
   // (measured -3 % on C3; windows small enough to stay in L2 lose more to launch tails than they gain)
   const int W = ctx->chain_cols >= 0 ? ctx->chain_cols : ((nx >= 1024 && (nx / 2) % 16 == 0) ? nx / 2 : 0);
   if (W > 0 && W < nx && thomas_is_pipelined(pl) && !ctx->profiling) {
     // ---- L2-resident chain over x windows, round-robin on auxiliary streams
-    ThomasDev<T> D = make_thomas<T>(pl, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, lam, a, b, c);
+    ThomasDev<T> D = make_thomas<T>(pl, nx, ny, zm ? (long long)nx * nz : (long long)nx, zm ? (long long)nx : (long long)nx * ny,
+                                    pl->th_n, pl->periodic_z, lam, a, b, c);
     rc = gaussel_prepare<T>(pl, D, st);
     if (rc) return rc;
     const int ns = ctx->chain_nstreams;
@@ -1170,14 +1193,15 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
     for (int x0 = 0; x0 < nx; x0 += W, ++iw) {
       cudaStream_t sq = ctx->aux[iw % ns];
       const int w = (nx - x0 < W) ? nx - x0 : W;
-      R2RGeom gw = gy;
+      R2RGeom gw = zm ? gyf : gy, gwb = zm ? gyb : gy;
       gw.lines_per_group = w;
-      rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + x0, A + x0, gw, pl->opt.fft_y_lines, sq);
+      gwb.lines_per_group = w;
+      rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + x0, (zm ? B : A) + x0, gw, pl->opt.fft_y_lines, sq);
       if (rc) return rc;
       D.xb = x0; D.xn = w;
-      rc = gaussel_apply<T>(pl, D, A, (T)normfft, sq);
+      rc = gaussel_apply<T>(pl, D, zm ? B : A, (T)normfft, sq);
       if (rc) return rc;
-      rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A + x0, A + x0, gw, pl->opt.fft_y_lines, sq);
+      rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], (zm ? B : A) + x0, A + x0, gwb, pl->opt.fft_y_lines, sq);
       if (rc) return rc;
     }
     for (int q = 0; q < ns; ++q) {
@@ -1185,16 +1209,15 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
       CK(cudaStreamWaitEvent(st, ctx->aux_done[q], 0));
     }
   } else {
-    // forward y, in place in A
-    rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
+    // forward y (in place in A, or A -> z-major B), tridiagonal solve in z, backward y
+    rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, zm ? B : A, zm ? gyf : gy, pl->opt.fft_y_lines, st);
     if (rc) return rc;
     prof_mark(ctx, st);
-    // tridiagonal solve in z
-    rc = run_gaussel<T>(pl, A, nx, ny, nx, (long long)nx * ny, pl->th_n, pl->periodic_z, (T)normfft, lam, a, b, c, st);
+    rc = run_gaussel<T>(pl, zm ? B : A, nx, ny, zm ? (long long)nx * nz : (long long)nx, zm ? (long long)nx : (long long)nx * ny,
+                        pl->th_n, pl->periodic_z, (T)normfft, lam, a, b, c, st);
     if (rc) return rc;
     prof_mark(ctx, st);
-    // backward y
-    rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
+    rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], zm ? B : A, A, zm ? gyb : gy, pl->opt.fft_y_lines, st);
     if (rc) return rc;
     prof_mark(ctx, st);
   }

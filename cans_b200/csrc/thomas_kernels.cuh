@@ -46,7 +46,7 @@ template <class T> struct ThomasDev {
                       // nullptr = in place
   int xb, xn;         // column window of this launch: i in [xb, xb + xn) for every j (thomas_reg_kernel)
   int m;              // rows per chunk of the chunked substitution = ceil(nn/32)
-  int chunk_layout;   // 0: z[k][j][i]   1: z[((j*nx+i)*m + r)*32 + lane], k = lane*m + r
+  int chunk_layout;   // unused (the pivot cache is always z[j][k][i], see zidx)
   int nopin;          // 1: the lambda-less variant of gaussel (src/solver.f90:168-188, :238-256; solver_gaussel_z):
                       // no singular-pivot pin, no tolerance test on the periodic closure
 };
@@ -64,12 +64,11 @@ template <class T> __device__ __forceinline__ T eps_of();
 template <> __device__ __forceinline__ double eps_of<double>() { return 2.220446049250313e-16; }
 template <> __device__ __forceinline__ float eps_of<float>() { return 1.1920929e-07f; }
 
+// Pivot-cache layout: z[j][k][i] (row pitch nx), so that the nn rows of one column tile sit in one window of
+// nn * nx elements (a 4 MB window on C3) instead of one row per field plane: the tile fetch then has the access
+// pattern of the y transforms for half of its bytes.
 template <class T> __device__ __forceinline__ long long zidx(const ThomasDev<T>& D, int i, int j, int k) {
-  if (D.chunk_layout) {
-    const int l = k / D.m, r = k - l * D.m;
-    return (((long long)j * D.nx + i) * D.m + r) * 32 + l;
-  }
-  return ((long long)k * D.ny + j) * D.nx + i;
+  return ((long long)j * D.nn + k) * D.nx + i;
 }
 
 // ---- factorisation cache bookkeeping (device resident) ----------------------
@@ -170,9 +169,6 @@ __global__ void __launch_bounds__(128) thomas_factor_kernel(const ThomasDev<T> D
     d = mul_rn(D.c[k], zz);
     z[zidx(D, i, j, k)] = zz;
   }
-  // pad the chunk layout so that lanes past nn see identity rows
-  if (D.chunk_layout)
-    for (int k = nn; k < 32 * D.m; ++k) z[zidx(D, i, j, k)] = T(0);
   if (!D.periodic) return;
   // auxiliary system of the periodic closure, src/solver.f90:201-260 (no pin in this sweep)
   zz = div_rn(one, add_rn(D.b[0], lam));
@@ -195,8 +191,6 @@ __global__ void __launch_bounds__(128) thomas_factor_kernel(const ThomasDev<T> D
     pv = sub_rn(p2[zidx(D, i, j, k)], mul_rn(dk, pv));
     p2[zidx(D, i, j, k)] = pv;
   }
-  if (D.chunk_layout)
-    for (int k = nn; k < 32 * D.m; ++k) p2[zidx(D, i, j, k)] = T(0);
   const T p2_first = p2[zidx(D, i, j, 0)], p2_last = p2[zidx(D, i, j, nn - 1)];
   const T t1 = mul_rn(D.c[nn], p2_first), t2 = mul_rn(D.a[nn], p2_last);
   const T bl = add_rn(D.b[nn], lam);
@@ -501,7 +495,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         mbar_expect_tx(&tile_bar, (unsigned)(2u * nrows_tile * COLS * sizeof(T)));
         for (int r0 = 0; r0 < nrows_tile; r0 += box_rows) {
           tma_load_3d(ps + r0 * COLS, &map_p, &tile_bar, x0, tj, rbase + r0);
-          tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, x0, tj, rbase + r0, sel);
+          tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, x0, rbase + r0, tj, sel);
         }
       }
       return;
@@ -513,7 +507,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         T* zd = zs + row * COLS + pc;
         T* pd = ps + row * COLS + pc;
         if (rbase + row < nn && pc < ncols) {
-          cp_async_16(zd, zsel + (long long)(rbase + row) * ncol + col0 + pc);
+          cp_async_16(zd, zsel + ((long long)(tile_i / tiles_x) * nn + rbase + row) * D.nx + (col0 - (long long)(tile_i / tiles_x) * D.nx) + pc);
           cp_async_16(pd, p + (long long)(rbase + row) * sk + col0 + tile_pshift(tile_i) + pc);
         } else {
 #pragma unroll
@@ -524,7 +518,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       for (int q = tid; q < nrows_tile * COLS; q += NT) {
         const int row = q / COLS, pc = q - row * COLS;
         if (rbase + row < nn && pc < ncols) {
-          cp_async_elem(zs + q, zsel + (long long)(rbase + row) * ncol + col0 + pc);
+          cp_async_elem(zs + q, zsel + ((long long)(tile_i / tiles_x) * nn + rbase + row) * D.nx + (col0 - (long long)(tile_i / tiles_x) * D.nx) + pc);
           cp_async_elem(ps + q, p + (long long)(rbase + row) * sk + col0 + tile_pshift(tile_i) + pc);
         } else {
           zs[q] = T(0);
@@ -685,10 +679,11 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       }
       __syncthreads();
       const T pcl = sP[c];
-      const T* p2c = p2base + (long long)sel * slot_z + col + (long long)k0 * ncol;
+      const long long tjp = tile / tiles_x;
+      const T* p2c = p2base + (long long)sel * slot_z + (tjp * nn + k0) * D.nx + (col - tjp * D.nx);
 #pragma unroll
       for (int r = 0; r < MMAX; ++r)
-        if (r < nrow) y[r] = fma(p2c[r * ncol], pcl, y[r]);
+        if (r < nrow) y[r] = fma(p2c[(long long)r * D.nx], pcl, y[r]);
     }
     if (D.out_rows) {
       const OutRow<T>* rows = D.out_rows + k0;

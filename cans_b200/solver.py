@@ -121,6 +121,10 @@ class Context:
         """Host-memory solves: number of z-plane chunks whose copies overlap the transforms (1 = one copy each way)."""
         check(lib.cansb200_ctx_set(self._h, 6, int(n)), "ctx_set")
 
+    def set_zmajor(self, on: bool = True):
+        """One-GPU solves: z-major intermediate between the y transforms and the tridiagonal stage."""
+        check(lib.cansb200_ctx_set(self._h, 8, int(on)), "ctx_set")
+
     def set_pin_host(self, on: bool = True):
         """Host-memory solves: page-lock the caller's array on first use (cudaHostRegister)."""
         check(lib.cansb200_ctx_set(self._h, 7, int(on)), "ctx_set")

@@ -149,6 +149,8 @@ enum {
   CANSB200_CTX_HOST_CHUNKS = 6,  /* host-memory solves: z-plane chunks whose PCIe copies overlap the x / y transforms (1 = off, default 16) */
   CANSB200_CTX_PIN_HOST = 7,     /* host-memory solves: 1 = page-lock the caller's p on first use (cudaHostRegister; released by
                                     cansb200_finalize) so that a pageable Fortran array copies at the full PCIe rate; default 0 */
+  CANSB200_CTX_ZMAJOR = 8,       /* one-GPU solves: the y transforms write / read a z-major copy B[j][k][i] of the field, so that the
+                                    tridiagonal stage streams 8 KB-strided rows instead of one row per field plane */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
                                     bit 2 = force the maximum shared-memory carveout (default: the driver picks, which leaves L1 to the twiddles) */
 };

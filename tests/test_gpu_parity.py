@@ -230,6 +230,27 @@ def test_host_memory_mode(cb):
             assert cases.rel_l2(ph, ref) < 1e-12
 
 
+@pytest.mark.parametrize("zmajor", [False, True])
+@pytest.mark.parametrize("ng,cbc,per", [([32, 64, 40], [cases.P, cases.N, cases.N], False),
+                                        ([16, 128, 24], [cases.P, cases.P, cases.P], True),
+                                        ([64, 256, 12], [cases.N, cases.D, cases.D], False)])
+def test_zmajor_intermediate(cb, ng, cbc, per, zmajor):
+    """The z-major copy B[j][k][i] between the y transforms and the tridiagonal stage (CANSB200_CTX_ZMAJOR) is a
+    pure re-addressing: same result as the in-place path and as the oracle."""
+    cs = O.make_case(ng, [1.0, 1.0, 1.0], cbc, gr=0.0 if per else 1.0)
+    p = cases.make_rhs(cs)
+    ref = p.copy()
+    O.solver(ng, ng, cs["arrplan"], cs["normfft"], cs["lambdaxy"], cs["a"], cs["b"], cs["c"], cbc, ["c"] * 3, ref)
+    ctx = cb.Context(ng)
+    ctx.set_zmajor(zmajor)
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], ["c"] * 3, device=_dev())
+    pd = torch.from_numpy(p.copy()).to(_dev())
+    cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, ["c"] * 3, pd)
+    I = (slice(1, -1),) * 3
+    err = cases.parity_error(cs, pd.cpu().numpy()[I], ref[I])
+    assert err < 1e-12, err
+
+
 def test_factorisation_cache(cb):
     """b and normfft change per Helmholtz call (src/solve_helmholtz.f90:63-71): the pivot cache must
     notice, refactor, and hit again when an earlier operator returns."""
