@@ -422,6 +422,21 @@ template <class Cfg, int S> __host__ __device__ constexpr int r2_stage_cpos(int 
   return ((Cfg::TPL * m) / L) * Ns + ((Cfg::TPL * m) % L) + q * L;
 }
 
+// a[r] *= w^(o r), r = 1 .. Rs-1, with w^(o r) at tab[(r-1) L].  The table is read for r = 1 and the even r only;
+// the odd ones are w^(o (r-1)) w^o (one extra rounding, ~1e-16): the twiddle loads were 16 % of all L1 wavefronts
+// of the x kernels (ncu, profiles/r1g_stage_kernels_ncu.md), this halves them at the cost of 4 flops each.
+template <class T, int Rs>
+__device__ __forceinline__ void r2_apply_twiddles(Cx<T>* a, const Cx<T>* tab, int L) {
+  const Cx<T> w1 = cx_ldg(tab);
+  a[1] = cx_mul(a[1], w1);
+#pragma unroll
+  for (int r = 2; r < Rs; r += 2) {
+    const Cx<T> we = cx_ldg(tab + (r - 1) * L);
+    a[r] = cx_mul(a[r], we);
+    if (r + 1 < Rs) a[r + 1] = cx_mul(a[r + 1], cx_mul(we, w1));
+  }
+}
+
 // one DIF stage on the shared tile (S > 0) or on registers already loaded (S == 0)
 template <class T, class Cfg, bool YMODE, int S>
 __device__ __forceinline__ void r2_dif_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T>& A, int c, int t) {
@@ -443,10 +458,7 @@ __device__ __forceinline__ void r2_dif_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T
         a[q] = POW2 ? sm[Lay::join(c, et, Lay::enc(r2_stage_cpos<Cfg, S>(m, q)))] : sm[Lay::at(c, base + q * L)];
     }
     bfR<T, Rs>(a);
-    if (L > 1) {
-#pragma unroll
-      for (int r = 1; r < Rs; ++r) a[r] = cx_mul(a[r], cx_ldg(A.tw[S] + (r - 1) * L + o));
-    }
+    if (L > 1) r2_apply_twiddles<T, Rs>(a, A.tw[S] + o, L);
 #pragma unroll
     for (int r = 0; r < Rs; ++r) {
       if (POW2) sm[Lay::join(c, et, Lay::enc(r2_stage_cpos<Cfg, S>(m, r)))] = a[r];
@@ -471,10 +483,7 @@ __device__ __forceinline__ void r2_dit_stage(Cx<T>* v, Cx<T>* sm, const R2Args<T
 #pragma unroll
     for (int q = 0; q < Rs; ++q)
       a[q] = POW2 ? sm[Lay::join(c, et, Lay::enc(r2_stage_cpos<Cfg, S>(m, q)))] : sm[Lay::at(c, base + q * L)];
-    if (L > 1) {
-#pragma unroll
-      for (int q = 1; q < Rs; ++q) a[q] = cx_mul(a[q], cx_ldg(A.tw[S] + (q - 1) * L + o));
-    }
+    if (L > 1) r2_apply_twiddles<T, Rs>(a, A.tw[S] + o, L);
     bfR<T, Rs>(a);
     if (S > 0) {
 #pragma unroll
