@@ -384,7 +384,7 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   ThomasDev<T> D;
   D.nx = nx; D.ny = ny; D.n = n_rows; D.periodic = periodic; D.nn = periodic ? n_rows - 1 : n_rows;
   D.sj = sj; D.sk = sk; D.a = a; D.b = b; D.c = c; D.lam = lam; D.lam_sj = nx;
-  D.m = pl->th_m; D.chunk_layout = 0; D.xb = 0; D.xn = nx; D.out_rows = nullptr; D.nopin = 0;
+  D.m = pl->th_m; D.chunk_layout = 2; D.xb = 0; D.xn = nx; D.out_rows = nullptr; D.nopin = 0;
   return D;
 }
 
@@ -875,8 +875,9 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   pl->th_n = ctx->ng[2] - pl->q;
   pl->th_nn = pl->periodic_z ? pl->th_n - 1 : pl->th_n;
   if (pl->th_nn < 1) return fail(CANSB200_EINVAL, "plan_create: z system is empty");
-  // pipelined substitution: 16 columns x 64 chunks up to 512 rows; up to 1024 rows a cluster of two CTAs shares
-  // the 16-column tile (variant 1) or one CTA takes 8 columns x 128 chunks (variant 2, and periodic z)
+  // pipelined substitution: tiles of one 128-byte row segment (16 FP64 / 32 FP32 columns) x all rows, 1024 threads;
+  // up to 512 rows one CTA per tile, up to 1024 rows a cluster of two CTAs shares the tile (variant 1) or one CTA
+  // takes half as many columns (variant 2, and periodic z)
   int variant = o.thomas_variant >= 0 ? o.thomas_variant : 1;
   const int wide = ctx->is_fp32 ? 32 : 16;   // columns of a 128-byte row segment
   pl->th_cols = wide;

@@ -46,7 +46,7 @@ template <class T> struct ThomasDev {
                       // nullptr = in place
   int xb, xn;         // column window of this launch: i in [xb, xb + xn) for every j (thomas_reg_kernel)
   int m;              // rows per chunk of the chunked substitution = ceil(nn/32)
-  int chunk_layout;   // unused (the pivot cache is always z[j][k][i], see zidx)
+  int chunk_layout;   // 2 = z[j][k][i] (the only layout, see zidx); kept for ABI stability of the struct
   int nopin;          // 1: the lambda-less variant of gaussel (src/solver.f90:168-188, :238-256; solver_gaussel_z):
                       // no singular-pivot pin, no tolerance test on the periodic closure
 };
