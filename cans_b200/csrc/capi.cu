@@ -631,7 +631,12 @@ int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ip
   (void)nccl_id;   // the exchange runs over CUDA IPC peer mappings (cansb200_dist_export / _connect), not NCCL
   if (!out || !ng || !dims) return fail(CANSB200_EINVAL, "init: null argument");
   if (ng[0] < 1 || ng[1] < 1 || ng[2] < 1) return fail(CANSB200_EINVAL, "init: ng must be positive");
-  if (ipencil_axis != 1) return fail(CANSB200_EUNSUPPORTED, "init: only ipencil_axis = 1 (x pencils) is implemented");
+  if (ipencil_axis < 1 || ipencil_axis > 3) return fail(CANSB200_EINVAL, "init: ipencil_axis must be 1, 2 or 3");
+  // The local array of `solver` is the pencil along ipencil_axis (src/initmpi.f90:198-260).  With dims = [1, P] the x and
+  // the y pencil are the same z slab (nx, ny, nz/P), and on one rank every pencil is the whole grid; z pencils of a
+  // decomposed grid (y split) would enter the solve at the tridiagonal stage's layout and are not implemented.
+  if (ipencil_axis == 3 && nranks > 1)
+    return fail(CANSB200_EUNSUPPORTED, "init: ipencil_axis = 3 on a decomposed grid is not implemented (use 1 or 2 with dims = [1, P])");
   if (nranks < 1 || nranks > CB_MAX_RANKS || rank < 0 || rank >= nranks) return fail(CANSB200_EINVAL, "init: bad rank / nranks");
   if (dims[0] != 1 || dims[1] != nranks)
     return fail(CANSB200_EUNSUPPORTED, "init: only dims = [1, nranks] (z slabs) is implemented");

@@ -55,7 +55,8 @@ typedef struct cansb200_options {
 
 /* -- context: replaces initmpi's cuDecomp setup (src/initmpi.f90:84-146), common_cudecomp.f90
  *    and workspaces.f90's init_wspace_arrays.  ng = global grid, dims = processor grid
- *    (only dims = [1, nranks], z slabs / x pencils, is implemented).  nccl_id is accepted for signature
+ *    (only dims = [1, nranks] is implemented: z slabs, which are both the x pencil and the y pencil of that processor
+ *    grid, so ipencil_axis may be 1 or 2; on one rank it may also be 3).  nccl_id is accepted for signature
  *    parity with cuDecomp's rendezvous (cudecomp.cc:65-69) and ignored: the exchange uses CUDA IPC peer
  *    mappings, see cansb200_dist_export / cansb200_dist_connect below. */
 int cansb200_init(cansb200_ctx** ctx, const int ng[3], const int dims[2], int ipencil_axis,

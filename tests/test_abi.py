@@ -31,7 +31,8 @@ def test_argument_errors_do_not_abort():
     assert b"null" in lib.cansb200_last_error()
     h = C.c_void_p()
     assert lib.cansb200_init(C.byref(h), _lib.i3([0, 4, 4]), _lib.i3([1, 1]), 1, 0, 1, None, 0) == -1
-    assert lib.cansb200_init(C.byref(h), _lib.i3([4, 4, 4]), _lib.i3([1, 1]), 2, 0, 1, None, 0) == -4  # unsupported pencil axis
+    assert lib.cansb200_init(C.byref(h), _lib.i3([4, 4, 4]), _lib.i3([1, 1]), 4, 0, 1, None, 0) == -1  # no such pencil axis
+    assert lib.cansb200_init(C.byref(h), _lib.i3([4, 4, 4]), _lib.i3([1, 2]), 3, 0, 2, None, 0) == -4  # z pencils of a decomposed grid
     assert lib.cansb200_solve(None, None, None, 1, 1.0, None, None, None, None, 1, None) == -1
     assert lib.cansb200_plan_destroy(None) == 0
     assert lib.cansb200_finalize(None) == 0

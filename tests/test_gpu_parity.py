@@ -251,6 +251,21 @@ def test_zmajor_intermediate(cb, ng, cbc, per, zmajor):
     assert err < 1e-12, err
 
 
+@pytest.mark.parametrize("axis", [1, 2, 3])
+def test_pencil_axis_entry_layouts(cb, axis):
+    """On one rank every pencil is the whole grid: ipencil_axis = 1, 2, 3 give the same solve (src/solver.f90:58-70)."""
+    name = "C4s_duct"
+    cs = cases.build_case(name)
+    p = cases.make_rhs(cs)
+    ref = cases.oracle_solve(name, cs, p)
+    ctx = cb.Context(cs["ng"], ipencil_axis=axis)
+    sd = cb.initsolver(ctx, cs["ng"], cs["dli"], cs["dzci"], cs["dzfi"], cs["cbc"], cs["bc"], cs["c_or_f"], device=_dev())
+    pd = torch.from_numpy(p.copy()).to(_dev())
+    cb.solver(cs["ng"], cs["ng"], sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cs["cbc"], cs["c_or_f"], pd)
+    I = (slice(1, -1),) * 3
+    assert cases.parity_error(cs, pd.cpu().numpy()[I], ref[I]) < 1e-12
+
+
 def test_factorisation_cache(cb):
     """b and normfft change per Helmholtz call (src/solve_helmholtz.f90:63-71): the pivot cache must
     notice, refactor, and hit again when an earlier operator returns."""
