@@ -15,9 +15,10 @@ namespace cb {
   X(256, 0, 16, 8, 1, 16, 16, 1, 1)   \
   X(512, 0, 64, 4, 4, 8, 8, 8, 1)     \
   X(512, 1, 32, 8, 2, 16, 8, 4, 1)    \
-  X(1024, 0, 64, 2, 5, 16, 8, 8, 1)   \
-  X(1024, 1, 128, 2, 4, 8, 8, 4, 4)   \
+  X(1024, 0, 64, 1, 10, 16, 8, 8, 1)  \
+  X(1024, 1, 64, 2, 5, 16, 8, 8, 1)   \
   X(1024, 2, 64, 4, 3, 16, 8, 8, 1)   \
+  X(1024, 3, 128, 2, 4, 8, 8, 4, 4)   \
   X(2048, 0, 128, 1, 4, 16, 16, 8, 1) \
   X(2048, 1, 128, 2, 1, 16, 16, 8, 1) \
   X(2048, 2, 128, 2, 2, 16, 16, 8, 1) \
