@@ -15,6 +15,8 @@ namespace cb {
   X(256, 0, 16, 8, 1, 16, 16, 1, 1)   \
   X(512, 0, 64, 4, 4, 8, 8, 8, 1)     \
   X(512, 1, 32, 8, 2, 16, 8, 4, 1)    \
+  X(512, 2, 64, 1, 12, 8, 8, 8, 1)    \
+  X(512, 3, 64, 2, 8, 8, 8, 8, 1)     \
   X(1024, 0, 64, 1, 10, 16, 8, 8, 1)  \
   X(1024, 1, 64, 2, 5, 16, 8, 8, 1)   \
   X(1024, 2, 64, 4, 3, 16, 8, 8, 1)   \
