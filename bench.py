@@ -183,8 +183,8 @@ def main():
     ap.add_argument("--fft-x-lines", type=int, default=-1)
     ap.add_argument("--fft-y-lines", type=int, default=-1)
     ap.add_argument("--r2-flags", type=int, default=-1)
-    ap.add_argument("--x-variant", type=int, default=0)
-    ap.add_argument("--y-variant", type=int, default=0)
+    ap.add_argument("--x-variant", type=int, default=-1)
+    ap.add_argument("--y-variant", type=int, default=-1)
     ap.add_argument("--chain-cols", type=int, default=-1)
     ap.add_argument("--chain-streams", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -104,7 +104,7 @@ struct cansb200_ctx {
   std::map<int, R2Tables<double>> r2tabs64;   // key = (n * 4 + variant) * 2 + ymode
   std::map<int, R2Tables<float>> r2tabs32;
   int force_generic = 0;                       // tests: route every transform through the generic engine
-  int r2_variant[2] = {0, 0};                  // tuning variant of the fast path, [x, y]
+  int r2_variant[2] = {-1, -1};                // tuning variant of the fast path, [x, y]; -1 = per-kind default (r2_auto_variant)
   int r2_flags = 0;                            // cache hints of the fast path (CANSB200_CTX_R2_FLAGS)
   // ---- z-slab decomposition over the GPUs of one box (dims = [1, P]); see dist_kernels.cuh
   std::vector<int> ys, zs;                     // split starts of y and z, size P + 1
@@ -272,6 +272,14 @@ struct R2RGeom {
   const void* row_tab = nullptr;   // distributed y transforms: peer-mapped output (forward) / input (backward) rows
 };
 
+// default plan per (length, mode, kind): variant 0 of r2r2_inst.cuh except where a sweep on B200 found better
+// (scripts/bench_stages.py; FP64 y-512: the 16-samples-per-thread plan wins for the forward kinds and the
+// cosine / sine inverses, the 8-samples-per-thread plan for HC2R)
+static int r2_auto_variant(int n, int ymode, int kind, bool fp32) {
+  if (!fp32 && ymode && n == 512 && kind != K_HC2R) return 3;
+  return 0;
+}
+
 template <class T>
 static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, const R2RGeom& g, int tile_hint,
                    cudaStream_t st) {
@@ -289,6 +297,7 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
     }
     R2Tables<T>* rt = nullptr;
     int var = ctx->r2_variant[g.ymode ? 1 : 0];
+    if (var < 0) var = r2_auto_variant(nt, g.ymode, kind, sizeof(T) == 4);
     if (ok) {
       int rc = get_r2_tables<T>(ctx, nt, g.ymode, var, &rt);
       if (rc) return rc;
@@ -812,7 +821,7 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
     return 0;
   }
   if (what == CANSB200_CTX_X_VARIANT || what == CANSB200_CTX_Y_VARIANT) {
-    if (value < 0 || value > 3) return fail(CANSB200_EINVAL, "ctx_set: variant must be 0..3");
+    if (value < -1 || value > 3) return fail(CANSB200_EINVAL, "ctx_set: variant must be -1 (per-kind default) or 0..3");
     c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
     return 0;
   }
@@ -1166,7 +1175,7 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   bool zm = ctx->zmajor && kind_is_fast(pl->kind[1][0]) && kind_is_fast(pl->kind[1][1]) && pl->nt[1] == ny && !ctx->force_generic;
   if (zm) {
     R2Tables<T>* rt = nullptr;
-    int var = ctx->r2_variant[1];
+    int var = ctx->r2_variant[1] < 0 ? 0 : ctx->r2_variant[1];
     if (get_r2_tables<T>(ctx, pl->nt[1], 1, var, &rt) || !rt) zm = false;
   }
   T* B = nullptr;

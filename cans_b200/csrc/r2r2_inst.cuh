@@ -35,6 +35,7 @@ namespace cb {
   X(512, 0, 64, 8, 2, 8, 8, 8, 1)     \
   X(512, 1, 32, 8, 3, 16, 8, 4, 1)    \
   X(512, 2, 64, 4, 4, 8, 8, 8, 1)     \
+  X(512, 3, 32, 8, 2, 16, 8, 4, 1)    \
   X(1024, 0, 64, 8, 1, 16, 8, 8, 1)   \
   X(1024, 1, 128, 4, 2, 8, 8, 4, 4)   \
   X(1024, 2, 32, 8, 1, 16, 16, 4, 1)  \

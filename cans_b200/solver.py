@@ -107,7 +107,7 @@ class Context:
         """Route every transform through the generic shared-memory engine (tests)."""
         check(lib.cansb200_ctx_set(self._h, 0, int(on)), "ctx_set")
 
-    def set_variant(self, x: int = 0, y: int = 0):
+    def set_variant(self, x: int = -1, y: int = -1):
         """Tuning variants of the fast transforms (thread / radix split), see r2r2_inst.cuh."""
         check(lib.cansb200_ctx_set(self._h, 1, int(x)), "ctx_set")
         check(lib.cansb200_ctx_set(self._h, 2, int(y)), "ctx_set")

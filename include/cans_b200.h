@@ -142,7 +142,7 @@ int cansb200_get_profile(cansb200_ctx* ctx, double ms[8], unsigned long long* ns
  * use it to cover the generic engine on lengths the fast path also serves). */
 enum {
   CANSB200_CTX_FORCE_GENERIC = 0,
-  CANSB200_CTX_X_VARIANT = 1,   /* tuning variant (thread / radix split) of the contiguous transforms, 0 = default */
+  CANSB200_CTX_X_VARIANT = 1,   /* tuning variant (thread / radix split) of the contiguous transforms: 0..3, -1 = per-kind default (initial state) */
   CANSB200_CTX_Y_VARIANT = 2,   /* same for the strided transforms */
   CANSB200_CTX_CHAIN_COLS = 3,  /* x-window (multiple of 16 columns) of the fft-y -> tridiagonal -> ifft-y chain run window by window on auxiliary streams;
                                    0 = off, -1 = auto (default: two half-width windows, whose kernels overlap each other's tails) */
