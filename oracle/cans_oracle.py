@@ -320,6 +320,98 @@ def gaussel(n, a, b, c, is_periodic, norm, p, lambdaxy=None):
 
 
 # --------------------------------------------------------------------------
+# gaussel_dtdma, src/solver.f90:309-517 -- distributed TDMA (is_poisson_dtdma), P ranks emulated in one process
+# --------------------------------------------------------------------------
+def gaussel_dtdma(starts, n, a, b, c, is_periodic, norm, p, lambdaxy=None):
+    """The reference's distributed tridiagonal solve, restated for a z decomposition with split starts `starts`
+    (len P + 1, rank r owns the global rows starts[r] .. starts[r+1]-1; rows >= n -- the face-centred Dirichlet
+    plane -- are dropped from the last rank, src/solver.f90:77,91).  `p[k, j, i]` holds rows 0..n-1 of the GLOBAL
+    system and is solved in place; `a, b, c` are the global coefficient arrays (every rank sees its own slice,
+    src/initsolver.f90:60-65).  Same expression order as the Fortran, every elementwise operation rounded
+    separately.  Steps per rank (:351-391): eliminate the inner rows so that they only couple to the rank's
+    first and last row; gather the 2 P boundary rows (transpose_y_to_z of aa_y, cc_y, pp_y, :429-440); solve the
+    reduced system (:449-461, periodic closure :462-490); hand the boundary values back and update the inner
+    rows (:499-510).  Used as the oracle of a future DTDMA kernel; pinned by the dense solve in tests/."""
+    dt = p.dtype.type
+    one = dt(1.0)
+    norm = dt(norm)
+    P = len(starts) - 1
+    lam = lambdaxy if lambdaxy is not None else np.zeros(p.shape[1:], dtype=p.dtype)
+    ranges = [(starts[r], min(starts[r + 1], n)) for r in range(P)]
+    if any(k1 - k0 < 3 for k0, k1 in ranges):
+        raise ValueError("gaussel_dtdma: every rank needs at least 3 rows")
+    AA, CC = [], []
+    red_a = np.empty((2 * P,) + p.shape[1:], dtype=p.dtype)
+    red_c = np.empty_like(red_a)
+    red_p = np.empty_like(red_a)
+    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+        for r, (k0, k1) in enumerate(ranges):
+            nl = k1 - k0
+            al, bl, cl = a[k0:k1], b[k0:k1], c[k0:k1]
+            pl = p[k0:k1]
+            aa = np.empty((nl,) + p.shape[1:], dtype=p.dtype)
+            cc = np.empty_like(aa)
+            for k in (0, 1):
+                zz = one / (bl[k] + lam)
+                aa[k] = al[k] * zz
+                cc[k] = cl[k] * zz
+                pl[k] = pl[k] * norm * zz
+            for k in range(2, nl):        # elimination of lower diagonals
+                z = one / ((bl[k] + lam) - al[k] * cc[k - 1])
+                pl[k] = (pl[k] * norm - al[k] * pl[k - 1]) * z
+                aa[k] = -al[k] * aa[k - 1] * z
+                cc[k] = cl[k] * z
+            for k in range(nl - 3, 0, -1):  # elimination of upper diagonals
+                pl[k] = pl[k] - cc[k] * pl[k + 1]
+                aa[k] = aa[k] - cc[k] * aa[k + 1]
+                cc[k] = -cc[k] * cc[k + 1]
+            z = one / (one - aa[1] * cc[0])
+            pl[0] = (pl[0] - cc[0] * pl[1]) * z
+            aa[0] = aa[0] * z
+            cc[0] = -cc[0] * cc[1] * z
+            AA.append(aa)
+            CC.append(cc)
+            red_a[2 * r], red_a[2 * r + 1] = aa[0], aa[nl - 1]
+            red_c[2 * r], red_c[2 * r + 1] = cc[0], cc[nl - 1]
+            red_p[2 * r], red_p[2 * r + 1] = pl[0], pl[nl - 1]
+        # reduced system: aa_z x_{k-1} + x_k + cc_z x_{k+1} = pp_z
+        nn = 2 * P
+        cc_z0 = red_c.copy()
+        if is_periodic:
+            nn -= 1
+        for k in range(1, nn):
+            z = one / (one - red_a[k] * red_c[k - 1])
+            red_p[k] = (red_p[k] - red_a[k] * red_p[k - 1]) * z
+            red_c[k] = red_c[k] * z
+        for k in range(nn - 2, -1, -1):
+            red_p[k] = red_p[k] - red_c[k] * red_p[k + 1]
+        if is_periodic:
+            cz = cc_z0
+            p2 = np.zeros((nn,) + p.shape[1:], dtype=p.dtype)
+            p2[0] = -red_a[0]
+            p2[nn - 1] = p2[nn - 1] - cz[nn - 1]
+            for k in range(1, nn):
+                z = one / (one - red_a[k] * cz[k - 1])
+                p2[k] = (p2[k] - red_a[k] * p2[k - 1]) * z
+                cz[k] = cz[k] * z
+            for k in range(nn - 2, -1, -1):
+                p2[k] = p2[k] - cz[k] * p2[k + 1]
+            red_p[nn] = (red_p[nn] - cz[nn] * red_p[0] - red_a[nn] * red_p[nn - 1]) / \
+                        (one + cz[nn] * p2[0] + red_a[nn] * p2[nn - 1])
+            for k in range(nn):
+                red_p[k] = red_p[k] + p2[k] * red_p[nn]
+        # back to the ranks: boundary values, then the inner rows
+        for r, (k0, k1) in enumerate(ranges):
+            nl = k1 - k0
+            pl = p[k0:k1]
+            pl[0] = red_p[2 * r]
+            pl[nl - 1] = red_p[2 * r + 1]
+            for k in range(1, nl - 1):
+                pl[k] = pl[k] - AA[r][k] * pl[0] - CC[r][k] * pl[nl - 1]
+    return p
+
+
+# --------------------------------------------------------------------------
 # solver / solve_helmholtz, src/solver.f90:17-112, src/solve_helmholtz.f90:28-75
 # --------------------------------------------------------------------------
 def solver(n, ng, arrplan, normfft, lambdaxy, a, b, c, bc, c_or_f, p, workers=1, stages=None):

@@ -166,3 +166,45 @@ def test_solver_gaussel_z_against_dense_solve(name):
     mask = np.ones(p.shape, bool)
     mask[1:n + 1, 1:-1, 1:-1] = False
     assert np.array_equal(ref[mask], p[mask])
+
+
+@pytest.mark.parametrize("name,nranks", [("C3s_channel", 2), ("C3s_channel", 4), ("C4s_duct", 3), ("periodic_z_odd", 3),
+                                         ("C2s_triperiodic", 4), ("helm_w_face_z", 2)])
+def test_gaussel_dtdma_oracle(name, nranks):
+    """The distributed-TDMA restatement (src/solver.f90:309-517, `is_poisson_dtdma`) solves the same tridiagonal
+    systems as `gaussel` and as a dense solve, for even and uneven z splits and for periodic z."""
+    from cans_b200.decomp import split_starts
+    cs = cases.build_case(name)
+    ng = cs["ng"]
+    helm = name in cases.HELMHOLTZ
+    a, c = cs["a"], cs["c"]
+    b = cs["b"] + (1.0 / cases.ALPHA if helm else 0.0)
+    lam = cs["lambdaxy"] - (0.0 if helm or not cases.is_singular(cs) else 0.37)   # keep every column regular
+    per = cs["cbc"][2] == P
+    q = 1 if (cs["c_or_f"][2] == "f" and cs["cbc"][2][1] == "D") else 0
+    n = ng[2] - q
+    rng = np.random.default_rng(23)
+    pz = rng.uniform(-1, 1, (ng[2], ng[1], ng[0]))
+    norm = 0.61
+    ref = pz.copy()
+    O.gaussel(n, a, b, c, per, norm, ref, lam)
+    got = pz.copy()
+    O.gaussel_dtdma(split_starts(ng[2], nranks), n, a, b, c, per, norm, got, lam)
+    assert per == (name in ("periodic_z_odd", "C2s_triperiodic"))
+    scale = np.abs(ref[:n]).max()
+    assert np.abs(got[:n] - ref[:n]).max() / scale < 1e-10
+    assert np.array_equal(got[n:], pz[n:])
+    # dense check of one column
+    j, i = ng[1] // 2, ng[0] // 3
+    M = np.zeros((n, n))
+    for k in range(n):
+        M[k, k] = b[k] + lam[j, i]
+        if k > 0:
+            M[k, k - 1] = a[k]
+        if k < n - 1:
+            M[k, k + 1] = c[k]
+    if per:
+        M[0, n - 1] += a[0]
+        M[n - 1, 0] += c[n - 1]
+    want = np.linalg.solve(M, pz[:n, j, i] * norm)
+    assert np.abs(got[:n, j, i] - want).max() / np.abs(want).max() < 1e-10
