@@ -66,6 +66,30 @@ def _worker(rank, world, port, name, q):
         O.fft(cs["arrplan"][1][1], slab)
         O.fft(cs["arrplan"][0][1], slab)
         err = cases.rel_l2(slab, ref[1 + z0:1 + z1, 1:-1, 1:-1])
+        # z-only solve (solver_gaussel_z) over the same exchange, no transforms (src/solver.f90:569-612)
+        alphai = 1.0 / cases.ALPHA
+        bb = cs["b"] + alphai
+        refz = p.copy()
+        O.solver_gaussel_z(ng, ng, ng, cs["a"], bb, cs["c"], cbc[2], cf, alphai, refz)
+        slab = np.ascontiguousarray(p[1 + z0:1 + z1, 1:-1, 1:-1])
+        send = [np.ascontiguousarray(b) for b in dec.forward_blocks(slab)]
+        dist.all_gather_object(allsend, send)
+        zp = dec.assemble_zpencil([allsend[s][rank] for s in range(world)])
+        O.gaussel(ng[2] - q3, cs["a"], bb, cs["c"], cbc[2] == ["P", "P"], alphai, zp, None)
+        send = [np.ascontiguousarray(b) for b in dec.backward_blocks(zp)]
+        dist.all_gather_object(allsend, send)
+        slab = dec.assemble_slab([allsend[s][rank] for s in range(world)])
+        err = max(err, cases.rel_l2(slab, refz[1 + z0:1 + z1, 1:-1, 1:-1]))
+        # distributed TDMA (is_poisson_dtdma): every rank keeps its slab; only the 2-rows-per-rank reduced system
+        # would travel.  The single-process oracle of it must agree with the transposed solve above.
+        full = np.ascontiguousarray(p[1:-1, 1:-1, 1:-1])
+        lam = cs["lambdaxy"] - 0.37   # regular columns (the pinned mode is the non-distributed solver's business)
+        want = full.copy()
+        O.gaussel(ng[2] - q3, cs["a"], cs["b"], cs["c"], cbc[2] == ["P", "P"], cs["normfft"], want, lam)
+        if all(e - s >= 3 for s, e in zip(dec.zs[:-1], [min(v, ng[2] - q3) for v in dec.zs[1:]])):
+            O.gaussel_dtdma(dec.zs, ng[2] - q3, cs["a"], cs["b"], cs["c"], cbc[2] == ["P", "P"], cs["normfft"], full, lam)
+            err_d = cases.rel_l2(full[z0:z1], want[z0:z1])
+            assert err_d < 1e-9, err_d
         q.put((rank, err))
     finally:
         dist.destroy_process_group()
