@@ -46,6 +46,7 @@ SYMBOLS = {
     "cansb200_solve_z": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, C.c_int, _VP]),
     "cansb200_r2r": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _I3, _VP]),
     "cansb200_gaussel": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_int, C.c_double, _VP, _VP, _VP, _VP, _VP]),
+    "cansb200_gaussel_dtdma": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_int, _I3, C.c_int, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "cansb200_fillps": (C.c_int, [_VP, _I3, _D3, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "cansb200_correc": (C.c_int, [_VP, _I3, _D3, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "cansb200_chkdiv": (C.c_int, [_VP, _I3, _D3, _VP, _VP, _VP, _VP, _D3, _D3, _VP]),

@@ -13,6 +13,7 @@
 #include "../../include/cans_b200.h"
 #include "aux_kernels.cuh"
 #include "dist_kernels.cuh"
+#include "dtdma_kernels.cuh"
 #include "fft_kernels.cuh"
 #include "fft_plan.hpp"
 #include "r2r2.cuh"
@@ -157,6 +158,7 @@ struct cansb200_plan {
   int th_n, th_nn, th_m, th_variant, th_mmax, th_cols, th_cl, nslots;
   long long slot_z, slot_den;
   DevBuf zcache, p2cache, dencache, state;
+  DevBuf dtdma_big, dtdma_small;   // distributed-TDMA coefficients (Z, AA, CC) and reduced system (cansb200_gaussel_dtdma)
   unsigned long long solves = 0;
   // TMA descriptors of the pipelined substitution: pivots (per plan) and right-hand sides (per field pointer / shape)
   bool use_tma = true;
@@ -937,6 +939,7 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
 int cansb200_plan_destroy(cansb200_plan* pl) {
   if (!pl) return 0;
   pl->zcache.release(); pl->p2cache.release(); pl->dencache.release(); pl->state.release();
+  pl->dtdma_big.release(); pl->dtdma_small.release();
   delete pl;
   return 0;
 }
@@ -1248,6 +1251,59 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   pl->solves++;
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// gaussel_dtdma (src/solver.f90:309-517) with the z slabs of `nsplit` ranks living on this GPU
+template <class T>
+static int gaussel_dtdma_impl(cansb200_plan* pl, T* pz, int nx, int ny, int n_rows, int nsplit, const int* starts, int periodic,
+                              T norm, const T* lam, const T* a, const T* b, const T* c, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  const size_t ncol = (size_t)nx * ny;
+  if (pl->dtdma_big.ensure(3 * ncol * (size_t)n_rows * sizeof(T))) return fail(CANSB200_ENOMEM, "gaussel_dtdma: coefficient arrays");
+  if (pl->dtdma_small.ensure((size_t)(11 * nsplit) * ncol * sizeof(T))) return fail(CANSB200_ENOMEM, "gaussel_dtdma: reduced system");
+  DtdmaDev<T> D;
+  D.nx = nx; D.ny = ny; D.n = n_rows; D.nranks = nsplit; D.periodic = periodic;
+  for (int r = 0; r <= nsplit; ++r) D.starts[r] = starts[r];
+  D.a = a; D.b = b; D.c = c; D.lam = lam;
+  T* big = (T*)pl->dtdma_big.p;
+  D.Z = big; D.AA = big + ncol * n_rows; D.CC = big + 2 * ncol * n_rows;
+  T* sm = (T*)pl->dtdma_small.p;
+  D.Z1 = sm;
+  D.ra = sm + ncol * nsplit; D.rc = D.ra + 2 * ncol * nsplit; D.rcw = D.rc + 2 * ncol * nsplit;
+  D.rp = D.rcw + 2 * ncol * nsplit; D.rp2 = D.rp + 2 * ncol * nsplit;
+  const unsigned cb = (unsigned)((ncol + 127) / 128);
+  dtdma_coef_kernel<T><<<cb, 128, 0, st>>>(D);
+  dtdma_phase1_kernel<T><<<cb, 128, 0, st>>>(D, pz, norm);
+  dtdma_reduced_kernel<T><<<cb, 128, 0, st>>>(D);
+  dtdma_phase3_kernel<T><<<ctx->num_sms * 8, 256, 0, st>>>(D, pz);
+  ctx->launches += 4;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int cansb200_gaussel_dtdma(cansb200_plan* pl, void* pz, const int d3[3], int n_rows, int nsplit, const int* starts,
+                           int is_periodic, double norm, const void* lam, const void* a, const void* b, const void* c,
+                           void* stream) {
+  if (!pl || !pz || !d3 || !starts || !a || !b || !c) return fail(CANSB200_EINVAL, "gaussel_dtdma: null argument");
+  if (nsplit < 1 || nsplit > CB_DTDMA_MAX_RANKS) return fail(CANSB200_EINVAL, "gaussel_dtdma: nsplit must be 1..16");
+  const int nx = d3[0], ny = d3[1], nz = d3[2];
+  if (nx < 1 || ny < 1 || n_rows < 1 || n_rows > nz) return fail(CANSB200_EINVAL, "gaussel_dtdma: bad extents");
+  if (starts[0] != 0 || starts[nsplit] < n_rows) return fail(CANSB200_EINVAL, "gaussel_dtdma: starts must cover rows 0 .. n_rows-1");
+  for (int r = 0; r < nsplit; ++r) {
+    const int k1 = starts[r + 1] < n_rows ? starts[r + 1] : n_rows;
+    if (k1 - starts[r] < 3) return fail(CANSB200_EINVAL, "gaussel_dtdma: every rank needs at least 3 rows");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return pl->ctx->is_fp32
+             ? gaussel_dtdma_impl<float>(pl, (float*)pz, nx, ny, n_rows, nsplit, starts, is_periodic, (float)norm, (const float*)lam,
+                                         (const float*)a, (const float*)b, (const float*)c, st)
+             : gaussel_dtdma_impl<double>(pl, (double*)pz, nx, ny, n_rows, nsplit, starts, is_periodic, norm, (const double*)lam,
+                                          (const double*)a, (const double*)b, (const double*)c, st);
+}
+
+}  // extern "C"
 
 // ---------------------------------------------------------------------------
 // solver_gaussel_z (src/solver.f90:547-616): tridiagonal solve in z only, no transforms, lambda-less gaussel

@@ -403,6 +403,17 @@ def gaussel(arrplan: Plan, n_rows, a, b, c, is_periodic, norm, pz, lambdaxy, str
     return pz
 
 
+def gaussel_dtdma(arrplan: Plan, starts, n_rows, a, b, c, is_periodic, norm, pz, lambdaxy=None, stream=None):
+    """`call gaussel_dtdma(nx,ny,n,0,a,b,c,is_periodic,norm,p,lambdaxy)` (src/solver.f90:309-517) with the z slabs of
+    len(starts) - 1 ranks on one GPU; `pz[k, j, i]` holds the rows of the global system."""
+    nz, ny, nx = pz.shape
+    st = (C.c_int * len(starts))(*[int(v) for v in starts])
+    check(lib.cansb200_gaussel_dtdma(arrplan.handle, _ptr(pz), i3([nx, ny, nz]), int(n_rows), len(starts) - 1, st,
+                                     int(is_periodic), float(norm), _ptr(lambdaxy) if lambdaxy is not None else None,
+                                     _ptr(a), _ptr(b), _ptr(c), _stream_ptr(stream)), "cansb200_gaussel_dtdma")
+    return pz
+
+
 def fillps(ctx, n, dli, dzfi, dti, u, v, w, p, stream=None):
     """src/fillps.f90:13-51."""
     check(lib.cansb200_fillps(ctx.handle, i3(n), d3(dli), _ptr(dzfi), float(dti), _ptr(u), _ptr(v), _ptr(w), _ptr(p),

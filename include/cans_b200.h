@@ -111,6 +111,15 @@ int cansb200_gaussel(cansb200_plan* plan, void* pz, const int dims3[3], int n_ro
                      double norm, const void* lambdaxy, const void* a, const void* b, const void* c,
                      void* stream);
 
+/* -- distributed TDMA, stage level (device pointers): the arithmetic of gaussel_dtdma / gaussel_dtdma_gpu
+ *    (src/solver.f90:309-517, src/solver_gpu.f90:430-695; is_poisson_dtdma) on a haloless field pz[k][j][i] whose
+ *    rows are split at `starts` (nsplit + 1 entries) into the z slabs of nsplit ranks, all living on this GPU:
+ *    inner-row elimination per slab, reduced 2-rows-per-rank system, update.  lambdaxy may be NULL (z-only
+ *    variant).  The reduced rows do not yet travel between GPUs. */
+int cansb200_gaussel_dtdma(cansb200_plan* plan, void* pz, const int dims3[3], int n_rows, int nsplit, const int* starts,
+                           int is_periodic, double norm, const void* lambdaxy, const void* a, const void* b,
+                           const void* c, void* stream);
+
 /* -- the steps either side of the path (device pointers, haloed arrays):
  *    fillps (src/fillps.f90:13-51), correc (src/correc.f90:13-60), chkdiv (src/chkdiv.f90:15-54) */
 int cansb200_fillps(cansb200_ctx* ctx, const int n[3], const double dli[3], const void* dzfi, double dti,

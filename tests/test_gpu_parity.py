@@ -135,6 +135,48 @@ def test_gaussel_stage(cb, S, name, variant):
     assert err < 1e-13, err
 
 
+@pytest.mark.parametrize("name,nsplit", [("C3s_channel", 2), ("C3s_channel", 4), ("C4s_duct", 3), ("periodic_z_odd", 3),
+                                         ("C2s_triperiodic", 4), ("helm_w_face_z", 2), ("nz_gt_512", 8), ("fp32_channel", 4),
+                                         ("C1_ldc_2x64x64", 1)])
+def test_gaussel_dtdma_stage(cb, S, name, nsplit):
+    """cansb200_gaussel_dtdma == gaussel_dtdma (src/solver.f90:309-517, is_poisson_dtdma): slab-wise elimination,
+    reduced 2-rows-per-rank system (periodic closure included), update -- bit for bit the reference's operation
+    order, for even and uneven z splits, and equal to the plain gaussel solve up to rounding."""
+    from cans_b200.decomp import split_starts
+    cs = cases.build_case(name)
+    ng, dt = cs["ng"], cs["dtype"]
+    helm = name in cases.HELMHOLTZ
+    a, c = cs["a"], cs["c"]
+    b = (cs["b"] + dt(1.0 / cases.ALPHA if helm else 0.0)).astype(dt)
+    lam = (cs["lambdaxy"] - dt(0.0 if helm or not cases.is_singular(cs) else 0.37)).astype(dt)   # regular columns
+    per = cs["cbc"][2] == cases.P
+    q = 1 if (cs["c_or_f"][2] == "f" and cs["cbc"][2][1] == "D") else 0
+    n = ng[2] - q
+    starts = split_starts(ng[2], nsplit)
+    rng = np.random.default_rng(29)
+    pz = rng.uniform(-1, 1, (ng[2], ng[1], ng[0])).astype(dt)
+    norm = 0.61
+    ref = pz.copy()
+    O.gaussel_dtdma(starts, n, a, b, c, per, norm, ref, lam)
+    plain = pz.copy()
+    O.gaussel(n, a, b, c, per, norm, plain, lam)
+    ctx = cb.Context(ng, is_fp32=(dt == np.float32))
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cs["cbc"], cs["bc"], cs["c_or_f"], device=_dev())
+    dev = _dev()
+    pd = torch.from_numpy(pz.copy()).to(dev)
+    S.gaussel_dtdma(sd.arrplan, starts, n, sd.a, torch.from_numpy(b).to(dev), sd.c, per, norm, pd, torch.from_numpy(lam).to(dev))
+    got = pd.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.array_equal(got, ref), f"not the reference's operation order (rel {cases.rel_l2(got, ref):.2e})"
+    assert cases.rel_l2(got[:n], plain[:n]) < (1e-9 if dt == np.float64 else 1e-3)
+    # lambda-less variant (z-only solve)
+    ref0 = pz.copy()
+    O.gaussel_dtdma(starts, n, a, b - dt(3.0), c, per, norm, ref0, None)
+    pd = torch.from_numpy(pz.copy()).to(dev)
+    S.gaussel_dtdma(sd.arrplan, starts, n, sd.a, torch.from_numpy((b - dt(3.0)).astype(dt)).to(dev), sd.c, per, norm, pd, None)
+    assert np.array_equal(pd.cpu().numpy(), ref0)
+
+
 # ------------------------------------------------------------- full solves ---
 @pytest.mark.parametrize("name", sorted(cases.CASES))
 def test_solver_matches_oracle(cb, name):
