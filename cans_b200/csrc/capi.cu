@@ -94,6 +94,7 @@ struct cansb200_ctx {
   int num_sms = 148;
   DevBuf scratch;   // haloless field buffer A (x pencil)
   DevBuf scratch2;  // z-major copy B[j][k][i] of the middle stages (zmajor)
+  int dtdma = 0;    // several ranks: keep z decomposed in the tridiagonal stage (gaussel_dtdma) instead of transposing to z pencils
   int zmajor = 1;   // 1: the y transforms write / read B, so that every row stream of the tridiagonal stage is 8 KB-strided
   DevBuf staging;   // haloed p when the caller's p is host memory
   DevBuf coef;      // a, b, c, lambdaxy staged from the host
@@ -827,6 +828,20 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
     c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
     return 0;
   }
+  if (what == CANSB200_CTX_DTDMA) {
+    // as in the reference (src/solver.f90:43-48, src/initsolver.f90 with is_poisson_dtdma): the "z pencil" extents that size
+    // lambdaxy and a, b, c become those of the y pencil = my slab: lambdaxy(nx, ny), a/b/c(nz_local)
+    c->dtdma = (value && c->nranks > 1) ? 1 : 0;
+    for (int d = 0; d < 3; ++d) { c->n_z[d] = c->ng[d]; c->lo_z[d] = 1; }
+    if (c->dtdma) {
+      c->n_z[2] = c->zs[c->rank + 1] - c->zs[c->rank];
+      c->lo_z[2] = c->zs[c->rank] + 1;
+    } else {
+      c->n_z[1] = c->ys[c->rank + 1] - c->ys[c->rank];
+      c->lo_z[1] = c->ys[c->rank] + 1;
+    }
+    return 0;
+  }
   if (what == CANSB200_CTX_ZMAJOR) {
     c->zmajor = value ? 1 : 0;
     return 0;
@@ -915,8 +930,8 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   const long long ncol = (long long)ctx->n_z[0] * ctx->n_z[1];
   pl->slot_z = ncol * pl->th_nn;
   pl->slot_den = ncol;
-  if (pl->zcache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: pivot cache");
-  if (pl->periodic_z) {
+  if (!ctx->dtdma && pl->zcache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: pivot cache");
+  if (pl->periodic_z && !ctx->dtdma) {
     if (pl->p2cache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: p2 cache");
     if (pl->dencache.ensure((size_t)pl->slot_den * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: den cache");
   }
@@ -1061,6 +1076,88 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
   return 0;
 }
 
+// the z-slab decomposed solve with the distributed TDMA (is_poisson_dtdma): no transposes; the only exchange is the
+// 2-rows-per-rank reduced system, gathered on every rank (peer stores into the otherwise unused z-pencil buffer) and
+// solved redundantly.  lam = lambdaxy(nx, ny) of the whole slab, a / b / c = my z slice (cansb200_ctx_set DTDMA).
+template <class T>
+static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double normfft, const T* lam, const T* a, const T* b,
+                            const T* c, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  if (!ctx->connected) return fail(CANSB200_ECOMM, "solve: cansb200_dist_connect has not been called");
+  const int nx = n[0], ny = n[1], nzl = n[2], P = ctx->nranks, r = ctx->rank;
+  const long long px = nx + 2, py = ny + 2;
+  const size_t ncol = (size_t)nx * ny;
+  const int nloc = nzl - (r == P - 1 ? pl->q : 0);
+  if (nloc < 3) return fail(CANSB200_EUNSUPPORTED, "solve (dtdma): every rank needs at least 3 z planes");
+  const size_t nel_z = (size_t)ctx->ng[0] * (ctx->ys[r + 1] - ctx->ys[r]) * ctx->ng[2];
+  // the gather buffer [3][2 P][ncol] lives in the z-pencil slot of the exchange region (same offset on every rank);
+  // the smallest slot of the box must hold it
+  size_t min_slot = nel_z;
+  for (int s = 0; s < P; ++s) {
+    const size_t e = (size_t)ctx->ng[0] * (ctx->ys[s + 1] - ctx->ys[s]) * ctx->ng[2];
+    if (e < min_slot) min_slot = e;
+  }
+  if ((size_t)6 * P * ncol > min_slot) return fail(CANSB200_EUNSUPPORTED, "solve (dtdma): nz too small for the reduced-system buffer (needs nz >= 6 P^2)");
+  if (pl->dtdma_big.ensure(3 * ncol * (size_t)nloc * sizeof(T))) return fail(CANSB200_ENOMEM, "solve (dtdma): coefficient arrays");
+  if (pl->dtdma_small.ensure((size_t)(7 + 4 * P) * ncol * sizeof(T))) return fail(CANSB200_ENOMEM, "solve (dtdma): reduced system");
+  T* A = (T*)ctx->scratch.p;
+  T* G = (T*)((char*)ctx->region + ctx->off_C);
+  T* pin = p + (px * py + px + 1);
+  int rc;
+  prof_mark(ctx, st);
+  R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nzl, nx, 0};
+  rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  R2RGeom gy{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nzl, ny, 1};
+  rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  // local elimination on my slab
+  DtdmaDev<T> D;
+  D.nx = nx; D.ny = ny; D.n = nloc; D.nranks = 1; D.periodic = 0;
+  D.starts[0] = 0; D.starts[1] = nloc;
+  D.a = a; D.b = b; D.c = c; D.lam = lam;
+  T* big = (T*)pl->dtdma_big.p;
+  D.Z = big; D.AA = big + ncol * nloc; D.CC = big + 2 * ncol * nloc;
+  T* sm = (T*)pl->dtdma_small.p;
+  D.Z1 = sm;
+  D.ra = sm + ncol; D.rc = D.ra + 2 * ncol; D.rp = D.rc + 2 * ncol;
+  D.rcw = D.rp + 2 * ncol; D.rp2 = D.rcw + 2 * ncol * P;
+  const unsigned cbk = (unsigned)((ncol + 127) / 128);
+  dtdma_coef_kernel<T><<<cbk, 128, 0, st>>>(D);
+  prof_mark(ctx, st);
+  dtdma_phase1_kernel<T><<<cbk, 128, 0, st>>>(D, A, (T)normfft);
+  DtdmaPeers pp;
+  for (int s = 0; s < CB_DTDMA_MAX_RANKS; ++s) pp.dst[s] = s < P ? (void*)((char*)ctx->peer[s] + ctx->off_C) : nullptr;
+  dtdma_gather_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(pp, r, P, (long long)ncol, D.ra, D.rc, D.rp);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  rc = dist_barrier(ctx, st);
+  if (rc) return rc;
+  // reduced system of all ranks, solved redundantly on every rank; then my inner rows
+  DtdmaDev<T> R = D;
+  R.nranks = P; R.periodic = pl->periodic_z;
+  R.ra = G; R.rc = G + 2 * (size_t)P * ncol; R.rp = G + 4 * (size_t)P * ncol;
+  dtdma_reduced_kernel<T><<<cbk, 128, 0, st>>>(R);
+  DtdmaDev<T> F = D;
+  F.rp = R.rp + 2 * (size_t)r * ncol;
+  dtdma_phase3_kernel<T><<<ctx->num_sms * 8, 256, 0, st>>>(F, A);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  rc = dist_barrier(ctx, st);   // nobody refills my gather buffer before I have read it
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nzl, nx, 0};
+  rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 template <class T>
 static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double normfft, const void* lam_any, const void* a_any,
@@ -1155,7 +1252,8 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
     return 0;
   }
   if (ctx->nranks > 1) {
-    const int rcd = solve_dist<T>(pl, p, n, normfft, lam, a, b, c, st);
+    const int rcd = ctx->dtdma ? solve_dist_dtdma<T>(pl, p, n, normfft, lam, a, b, c, st)
+                               : solve_dist<T>(pl, p, n, normfft, lam, a, b, c, st);
     if (rcd) return rcd;
     if (mem_kind == CANSB200_MEM_HOST) {
       CK(cudaMemcpyAsync(p_any, ctx->staging.p, nh * sizeof(T), cudaMemcpyDeviceToHost, st));

@@ -197,4 +197,23 @@ __global__ void dtdma_phase3_kernel(const DtdmaDev<T> D, T* p) {
   }
 }
 
+// ---- distributed: my two boundary rows of (aa, cc, p) into the gathered reduced system of EVERY rank ---------------
+// dst[s] = base of rank s's gather buffer [3][2 P][ncol] (peer mapped); my rows are 2 rank, 2 rank + 1
+struct DtdmaPeers { void* dst[CB_DTDMA_MAX_RANKS]; };
+template <class T>
+__global__ void dtdma_gather_kernel(DtdmaPeers peers, int rank, int nranks, long long ncol, const T* __restrict__ ra,
+                                    const T* __restrict__ rc, const T* __restrict__ rp) {
+  const long long per = 2 * ncol;                 // my two rows of one array
+  const long long tot = 3 * per * nranks;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(e / (3 * per));
+    const long long w = e - (long long)s * 3 * per;
+    const int arr = (int)(w / per);
+    const long long o = w - (long long)arr * per;   // h * ncol + col
+    const T v = arr == 0 ? ra[o] : (arr == 1 ? rc[o] : rp[o]);
+    T* g = reinterpret_cast<T*>(peers.dst[s]);
+    g[((long long)arr * 2 * nranks + 2 * rank) * ncol + o] = v;
+  }
+}
+
 }  // namespace cb

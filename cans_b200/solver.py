@@ -121,6 +121,14 @@ class Context:
         """Host-memory solves: number of z-plane chunks whose copies overlap the transforms (1 = one copy each way)."""
         check(lib.cansb200_ctx_set(self._h, 6, int(n)), "ctx_set")
 
+    def set_dtdma(self, on: bool = True):
+        """Several ranks: the reference's `is_poisson_dtdma` path (distributed TDMA, z stays decomposed).  Call it before
+        `initsolver`: `n_z` / `lo_z` become those of the slab, as in the reference (src/solver.f90:43-48)."""
+        check(lib.cansb200_ctx_set(self._h, 9, int(on)), "ctx_set")
+        n, lo, nz, loz = i3([0] * 3), i3([0] * 3), i3([0] * 3), i3([0] * 3)
+        check(lib.cansb200_get_extents(self._h, n, lo, nz, loz), "get_extents")
+        self.n, self.lo, self.n_z, self.lo_z = list(n), list(lo), list(nz), list(loz)
+
     def set_zmajor(self, on: bool = True):
         """One-GPU solves: z-major intermediate between the y transforms and the tridiagonal stage."""
         check(lib.cansb200_ctx_set(self._h, 8, int(on)), "ctx_set")
@@ -300,6 +308,9 @@ def initsolver(ctx: Context, ng, dli, dzci_g, dzfi_g, cbc, bc, c_or_f, device=No
     ly = ly[y0:y0 + ctx.n_z[1]]
     lambdaxy = np.ascontiguousarray((lx[None, :] + ly[:, None]).astype(dt))
     a, b, c = tridmatrix(cbc[2], ng[2], dzci_g, dzfi_g, c_or_f[2], dt)
+    # a, b, c(lo_z(3):hi_z(3)) (src/initsolver.f90:60-65): the whole z range except in distributed-TDMA mode
+    k0 = ctx.lo_z[2] - 1
+    a, b, c = (np.ascontiguousarray(v[k0:k0 + ctx.n_z[2]]) for v in (a, b, c))
     dl = [dt(1.0) / v for v in dli]
     dzc_g, dzf_g = dt(1.0) / dzci_g, dt(1.0) / dzfi_g
     n3 = ng[2]

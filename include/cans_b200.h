@@ -161,6 +161,10 @@ enum {
                                     cansb200_finalize) so that a pageable Fortran array copies at the full PCIe rate; default 0 */
   CANSB200_CTX_ZMAJOR = 8,       /* one-GPU solves: the y transforms write / read a z-major copy B[j][k][i] of the field, so that the
                                     tridiagonal stage streams 8 KB-strided rows instead of one row per field plane */
+  CANSB200_CTX_DTDMA = 9,        /* several ranks: 1 = the reference's is_poisson_dtdma path: z stays decomposed in the tridiagonal stage
+                                    (distributed TDMA), the only exchange is the 2-rows-per-rank reduced system.  Set it BEFORE creating
+                                    plans: cansb200_get_extents then reports n_z = (nx, ny, nz_local) as the reference does, i.e. the
+                                    caller passes lambdaxy(nx, ny) and its own z slice of a, b, c.  Needs nz >= 6 nranks^2.  Default 0 */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
                                     bit 2 = force the maximum shared-memory carveout (default: the driver picks, which leaves L1 to the twiddles) */
 };

@@ -41,6 +41,7 @@ def main():
     dist.init_process_group("gloo")
     from oracle import cans_oracle as O
     worst = 0.0
+    ndtdma = 0
     for name, (ng, l, cbc, cf, gr, dt, helm) in DIST_CASES.items():
         cs = O.make_case(ng, l, cbc, c_or_f=cf, gr=gr, dtype=dt)
         p = cases.make_rhs(cs)
@@ -100,8 +101,49 @@ def main():
         dist.barrier()
         sd.arrplan.destroy()
         ctx.close()
+        # distributed TDMA (is_poisson_dtdma, CANSB200_CTX_DTDMA): z stays decomposed, only the reduced system travels.
+        # Regular operators only (the reference's gaussel_dtdma has no singular-pivot pin) and nz >= 6 P^2.
+        singular = all(bb[0] in "PN" and bb[1] in "PN" for bb in cbc) and not helm
+        if not singular and ng[2] >= 6 * world * world and os.environ.get("CANSB200_TEST_DTDMA", "1") == "1":
+            ctx2 = cb.Context(ng, is_fp32=dt == np.float32, rank=rank, nranks=world)
+            ctx2.connect()
+            ctx2.set_dtdma(True)
+            assert ctx2.n_z == [ng[0], ng[1], z1 - z0] and ctx2.lo_z == [1, 1, z0 + 1], (ctx2.n_z, ctx2.lo_z)
+            sd2 = cb.initsolver(ctx2, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], cf, device=dev)
+            assert tuple(sd2.lambdaxy.shape) == (ng[1], ng[0]) and sd2.a.numel() == z1 - z0
+            # oracle: the same stages with the distributed elimination on the global field
+            ty = dt
+            alphai = ty(1.0) / ty(cases.ALPHA)
+            px = np.ascontiguousarray(p[1:-1, 1:-1, 1:-1])
+            O.fft(cs["arrplan"][0][0], px)
+            O.fft(cs["arrplan"][1][0], px)
+            q3 = 1 if (cf[2] == "f" and cbc[2][1] == "D") else 0
+            bq = (cs["b"] + alphai).astype(dt) if helm else cs["b"]
+            nq = ty(cs["normfft"]) * alphai if helm else cs["normfft"]
+            O.gaussel_dtdma(dec.zs, ng[2] - q3, cs["a"], bq, cs["c"], cbc[2] == P, nq, px, cs["lambdaxy"])
+            O.fft(cs["arrplan"][1][1], px)
+            O.fft(cs["arrplan"][0][1], px)
+            for rep in range(2):
+                pd.copy_(torch.from_numpy(pl))
+                if helm:
+                    cb.solve_helmholtz(ctx2.n, ng, sd2.arrplan, sd2.normfft, cases.ALPHA, sd2.lambdaxy, sd2.a, sd2.b, sd2.c, None,
+                                       None, None, cbc, cf, pd)
+                else:
+                    cb.solver(ctx2.n, ng, sd2.arrplan, sd2.normfft, sd2.lambdaxy, sd2.a, sd2.b, sd2.c, cbc, cf, pd)
+            torch.cuda.synchronize()
+            assert ctx2.dist_status() == 0, "a device-side barrier timed out (dtdma)"
+            gotd = pd.cpu().numpy()
+            errd = cases.rel_l2(gotd[1:-1, 1:-1, 1:-1], px[z0:z1])
+            if rank == 0:
+                print(f"{name}: distributed TDMA rel L2 = {errd:.3e}", flush=True)
+            assert errd < tol, f"{name}: dtdma {errd}"
+            ndtdma += 1
+            assert np.array_equal(gotd[halo], pl[halo]), "halo cells were modified (dtdma)"
+            dist.barrier()
+            sd2.arrplan.destroy()
+            ctx2.close()
     if rank == 0:
-        print(f"DIST_OK {worst:.3e}", flush=True)
+        print(f"DIST_OK {worst:.3e} dtdma_cases={ndtdma}", flush=True)
     dist.destroy_process_group()
 
 

@@ -21,3 +21,5 @@ def test_distributed_solve_matches_oracle(nproc):
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    if nproc == 2:   # the distributed-TDMA path needs nz >= 6 P^2: two of the cases qualify on 2 GPUs
+        assert "dtdma_cases=2" in r.stdout, r.stdout[-3000:]
