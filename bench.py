@@ -192,6 +192,10 @@ def main():
     ap.add_argument("--fp32", action="store_true", help="the -D_SINGLE_PRECISION build of CaNS (not the headline; FP64 is)")
     ap.add_argument("--host-chunks", type=int, default=16)
     ap.add_argument("--zmajor", type=int, default=-1)
+    ap.add_argument("--dtdma", action="store_true",
+                    help="N > 1: the distributed-TDMA path (CANSB200_CTX_DTDMA); use it with --helmholtz (it has no singular-pivot pin)")
+    ap.add_argument("--helmholtz", type=float, default=0.0,
+                    help="alpha != 0: time the implicit-diffusion Helmholtz solve p/alpha + lap p = rhs (regular operator) instead")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -225,6 +229,8 @@ def main():
     tdt, ndt, esz = (torch.float32, np.float32, 4) if fp32 else (torch.float64, np.float64, 8)
     ctx = cb.Context(ng, is_fp32=fp32, rank=rank, nranks=world)
     ctx.connect()
+    if args.dtdma and world > 1:
+        ctx.set_dtdma(True)
     ctx.set_variant(args.x_variant, args.y_variant)
     if args.r2_flags >= 0:
         ctx.set_r2_flags(args.r2_flags)
@@ -250,8 +256,15 @@ def main():
             dist.all_reduce(den)
         p[I] -= num / den
 
-    def step():
-        cb.solver(nl, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, p)
+    if args.helmholtz != 0.0:
+        alphai = 1.0 / args.helmholtz
+        b_h, norm_h = sd.b + alphai, float(sd.normfft) * alphai   # src/solve_helmholtz.f90:63-71
+
+        def step():
+            cb.solver(nl, ng, sd.arrplan, norm_h, sd.lambdaxy, sd.a, b_h, sd.c, cbc, cf, p)
+    else:
+        def step():
+            cb.solver(nl, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, p)
 
     # FP32 only: the null-space mode of the singular operator is not pinned on a stretched grid, so
     # feeding a solution back as the next right-hand side overflows single precision after a few solves.  The FP32
@@ -398,7 +411,9 @@ def main():
                        "decomposition": "single GPU" if world == 1 else f"z slabs over {world} GPUs (x pencils, dims=[1,{world}]), "
                                         "transposes = peer-mapped stores over NVLink",
                        "l2": "inputs (2.15 GB/field) larger than L2, no flush", "solves_per_s": 1e3 / ms_per_step,
-                       "thomas_variant": int(sd.arrplan.stats()["thomas_variant"])},
+                       "thomas_variant": int(sd.arrplan.stats()["thomas_variant"]),
+                       **({"dtdma": True} if (args.dtdma and world > 1) else {}),
+                       **({"helmholtz_alpha": args.helmholtz} if args.helmholtz != 0.0 else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(out), flush=True)
