@@ -49,7 +49,7 @@ typedef struct cansb200_options {
   int cache_slots;      /* factorisation cache entries per plan (1..8); Helmholtz plans want 3 */
   int fft_x_lines;      /* lines per tile of the contiguous transforms (0 = auto) */
   int fft_y_lines;      /* 8 or 16: x-width of the strided-transform tile (0 = auto) */
-  int exchange;         /* multi-GPU: 0 = NCCL all-to-all, 1 = fused peer stores */
+  int exchange;         /* reserved (multi-GPU exchange flavour): only the fused peer stores over CUDA IPC exist; the value is ignored */
   int reserved[11];
 } cansb200_options;
 
