@@ -39,6 +39,7 @@ SYMBOLS = {
     "cansb200_dist_export": (C.c_int, [_VP, _VP]),
     "cansb200_dist_connect": (C.c_int, [_VP, _VP]),
     "cansb200_dist_status": (C.c_int, [_VP, C.POINTER(C.c_int)]),
+    "cansb200_dist_connect_local": (C.c_int, [C.POINTER(_VP), C.c_int]),
     "cansb200_get_extents": (C.c_int, [_VP, _I3, _I3, _I3, _I3]),
     "cansb200_plan_create": (C.c_int, [_VP, C.POINTER(_VP), C.c_char_p, C.c_char_p, C.POINTER(Options), _D3]),
     "cansb200_plan_destroy": (C.c_int, [_VP]),

@@ -94,6 +94,7 @@ struct cansb200_ctx {
   int num_sms = 148;
   DevBuf scratch;   // haloless field buffer A (x pencil)
   DevBuf scratch2;  // z-major copy B[j][k][i] of the middle stages (zmajor)
+  DevBuf work2;     // third pencil-sized buffer lent to the host (cansb200_get_work)
   int dtdma = 0;    // several ranks: keep z decomposed in the tridiagonal stage (gaussel_dtdma) instead of transposing to z pencils
   int zmajor = 1;   // 1: the y transforms write / read B, so that every row stream of the tridiagonal stage is 8 KB-strided
   DevBuf staging;   // haloed p when the caller's p is host memory
@@ -115,8 +116,14 @@ struct cansb200_ctx {
   std::vector<void*> peer;                     // peer-mapped region bases (own rank: region)
   std::vector<size_t> peer_off_XB;             // offset of XB inside every rank's region
   bool connected = false;
-  unsigned long long epoch = 0;
-  int* dist_status = nullptr;
+  bool local_peers = false;                    // peers are contexts of this process on this device (cansb200_dist_connect_local)
+  unsigned long long seq = 0;                  // sequence number of the distributed solves = value of every flag of a solve
+  int* dist_status = nullptr;                  // host-mapped word set by a device-side wait that timed out
+  int* dist_status_dev = nullptr;              // its device-resident twin
+  int dist_windows = -1;                       // x windows of the pipelined exchange (-1 = auto: up to 4)
+  int dist_thomas_ctas = -1;                   // CTAs of the tridiagonal kernel while it shares the GPU with the y transforms (-1 = auto)
+  cudaStream_t dist_sT = nullptr, dist_sB = nullptr;   // pipeline stages: tridiagonal solve / backward y transform (forward = caller's stream)
+  std::vector<cudaEvent_t> dist_ev;            // [w] forward window done, [W + w] tridiagonal window done, [2 W] backward done
   DevBuf ytab_fwd, ytab_bwd, ztab;
   // L2-resident chain: fft-y -> tridiagonal -> ifft-y run per window of `chain_cols` x columns, windows
   // round-robin on auxiliary streams, so that the two intermediate fields never leave the L2 cache
@@ -126,6 +133,8 @@ struct cansb200_ctx {
   std::vector<cudaEvent_t> aux_done;
   cudaEvent_t fork_ev = nullptr;
   unsigned long long launches = 0;
+  int cta_cap = 0;                              // > 0: the persistent tridiagonal kernel uses at most this many CTAs (pipelined exchange)
+  int nplans = 0;                               // live plans (some switches are only legal before the first one)
   // host-memory mode: the z planes travel in chunks on two copy streams so that the x / y transforms of a chunk
   // overlap the PCIe transfer of the others (only the tridiagonal stage needs the whole field)
   int host_chunks = 16;
@@ -273,6 +282,7 @@ struct R2RGeom {
   long long in_es, out_es, in_ls, out_ls, in_gs, out_gs;
   int lines_per_group, ngroups, line_len, ymode;
   const void* row_tab = nullptr;   // distributed y transforms: peer-mapped output (forward) / input (backward) rows
+  int x0 = 0, g0 = 0;              // ... launched on a window of the slab: its first column / plane (the row table addresses whole rows)
 };
 
 // default plan per (length, mode, kind): variant 0 of r2r2_inst.cuh except where a sweep on B200 found better
@@ -313,6 +323,7 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
       for (int s = 0; s < 4; ++s) A.tw[s] = rt->tw[s];
       A.mak = rt->mak;
       A.row_tab = (const R2Row<T>*)g.row_tab;
+      A.x0 = g.x0; A.g0 = g.g0;
       A.flags = ctx->r2_flags & 3;
       cb::g_r2_default_carveout = (ctx->r2_flags & 4) ? 0 : 1;
       const int rc = !g.ymode ? r2r2_run<T, false, false>(A, nt, var, kind_is_forward(kind), st)
@@ -492,13 +503,16 @@ static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute la[1];
   if (CL > 1) {
-    const long long nc = tiles < max_clusters ? tiles : max_clusters;   // persistent: one cluster per SM pair
+    long long nc = tiles < max_clusters ? tiles : max_clusters;   // persistent: one cluster per SM pair
+    if (ctx->cta_cap > 0 && nc > ctx->cta_cap / CL) nc = ctx->cta_cap / CL > 0 ? ctx->cta_cap / CL : 1;
     cfg.gridDim = dim3((unsigned)(nc * CL));
     la[0].id = cudaLaunchAttributeClusterDimension;
     la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
     cfg.attrs = la; cfg.numAttrs = 1;
   } else {
-    cfg.gridDim = dim3((unsigned)(tiles < ctx->num_sms ? tiles : ctx->num_sms));   // persistent: one CTA per SM
+    long long nb = tiles < ctx->num_sms ? tiles : ctx->num_sms;   // persistent: one CTA per SM
+    if (ctx->cta_cap > 0 && nb > ctx->cta_cap) nb = ctx->cta_cap;
+    cfg.gridDim = dim3((unsigned)nb);
   }
   cfg.blockDim = dim3(CB_TH_THREADS);
   cfg.dynamicSmemBytes = smem;
@@ -680,8 +694,17 @@ int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ip
     c->region_bytes = c->off_XB + up(nel * c->esz);
     if (cudaMalloc(&c->region, c->region_bytes) != cudaSuccess) { c->scratch.release(); delete c; return fail(CANSB200_ENOMEM, "init: exchange region"); }
     cudaMemset(c->region, 0, 4096);
-    if (cudaMalloc((void**)&c->dist_status, sizeof(int)) != cudaSuccess) { delete c; return fail(CANSB200_ENOMEM, "init: status word"); }
-    cudaMemset(c->dist_status, 0, sizeof(int));
+    // host-mapped: the waiting kernels set it on a time-out, the host reads it without synchronising
+    if (cudaHostAlloc((void**)&c->dist_status, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+      cudaFree(c->region); c->scratch.release(); delete c;
+      return fail(CANSB200_ENOMEM, "init: status word");
+    }
+    *c->dist_status = 0;
+    if (cudaMalloc((void**)&c->dist_status_dev, sizeof(int)) != cudaSuccess) {
+      cudaFreeHost(c->dist_status); cudaFree(c->region); c->scratch.release(); delete c;
+      return fail(CANSB200_ENOMEM, "init: status word");
+    }
+    cudaMemset(c->dist_status_dev, 0, sizeof(int));
     c->peer.assign(nranks, nullptr);
     c->peer[rank] = c->region;
   }
@@ -767,22 +790,53 @@ int cansb200_dist_connect(cansb200_ctx* c, const void* blobs) {
   return 0;
 }
 
+int cansb200_dist_connect_local(cansb200_ctx* const* ctxs, int n) {
+  // all ranks of the decomposition live in THIS process on THIS device (one context each, solves issued on one
+  // stream per rank): the peers' regions are ordinary device pointers.  Same kernels, same row tables, same flags
+  // as the CUDA-IPC rendezvous -- what a single-GPU box can test of the multi-GPU path.
+  if (!ctxs || n < 2) return fail(CANSB200_EINVAL, "dist_connect_local: need at least two contexts");
+  for (int r = 0; r < n; ++r) {
+    cansb200_ctx* c = ctxs[r];
+    if (!c || c->nranks != n || c->rank != r) return fail(CANSB200_EINVAL, "dist_connect_local: contexts must be ordered by rank, nranks = n");
+    if (c->connected) return fail(CANSB200_EINVAL, "dist_connect_local: context already connected");
+    for (int d = 0; d < 3; ++d)
+      if (c->ng[d] != ctxs[0]->ng[d] || c->is_fp32 != ctxs[0]->is_fp32) return fail(CANSB200_EINVAL, "dist_connect_local: contexts differ");
+  }
+  for (int r = 0; r < n; ++r) {
+    cansb200_ctx* c = ctxs[r];
+    c->peer_off_XB.assign(n, 0);
+    for (int s = 0; s < n; ++s) {
+      c->peer_off_XB[s] = ctxs[s]->off_XB;
+      c->peer[s] = ctxs[s]->region;
+    }
+    c->local_peers = true;
+    const int rc = c->is_fp32 ? build_dist_tables<float>(c) : build_dist_tables<double>(c);
+    if (rc) return rc;
+    c->connected = true;
+  }
+  return 0;
+}
+
 int cansb200_dist_status(cansb200_ctx* c, int* status) {
   if (!c || !status) return fail(CANSB200_EINVAL, "dist_status: null argument");
-  *status = 0;
-  if (c->dist_status) CK(cudaMemcpy(status, c->dist_status, sizeof(int), cudaMemcpyDeviceToHost));
+  *status = c->dist_status ? *(volatile int*)c->dist_status : 0;
   return 0;
 }
 
 int cansb200_finalize(cansb200_ctx* c) {
   if (!c) return 0;
-  c->scratch.release(); c->scratch2.release(); c->staging.release(); c->coef.release(); c->zero_lam.release();
+  c->scratch.release(); c->scratch2.release(); c->work2.release(); c->staging.release(); c->coef.release(); c->zero_lam.release();
   for (auto& kv : c->tabs64) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (auto& kv : c->tabs32) { cudaFree(kv.second.tw); cudaFree(kv.second.twp); cudaFree(kv.second.mak); cudaFree(kv.second.rev); }
   for (int q = 0; q < (int)c->peer.size(); ++q)
-    if (q != c->rank && c->peer[q]) cudaIpcCloseMemHandle(c->peer[q]);
+    if (q != c->rank && c->peer[q] && !c->local_peers) cudaIpcCloseMemHandle(c->peer[q]);
   if (c->region) cudaFree(c->region);
-  if (c->dist_status) cudaFree(c->dist_status);
+  if (c->dist_status) cudaFreeHost(c->dist_status);
+  if (c->dist_status_dev) cudaFree(c->dist_status_dev);
+  if (c->dist_sT) cudaStreamDestroy(c->dist_sT);
+  if (c->dist_sB) cudaStreamDestroy(c->dist_sB);
+  for (cudaEvent_t q : c->dist_ev) cudaEventDestroy(q);
+  for (cudaEvent_t q : c->prof_events) cudaEventDestroy(q);
   c->ytab_fwd.release(); c->ytab_bwd.release(); c->ztab.release();
   for (cudaStream_t q : c->aux) cudaStreamDestroy(q);
   for (cudaEvent_t q : c->aux_done) cudaEventDestroy(q);
@@ -828,7 +882,18 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
     c->r2_variant[what == CANSB200_CTX_Y_VARIANT ? 1 : 0] = value;
     return 0;
   }
+  if (what == CANSB200_CTX_DIST_WINDOWS) {
+    if (value < -1 || value == 0 || value > CB_MAX_WINDOWS) return fail(CANSB200_EINVAL, "ctx_set: dist_windows must be -1 (auto) or 1..8");
+    c->dist_windows = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_DIST_THOMAS_CTAS) {
+    if (value < -1 || value == 0) return fail(CANSB200_EINVAL, "ctx_set: dist_thomas_ctas must be -1 (auto) or positive");
+    c->dist_thomas_ctas = value;
+    return 0;
+  }
   if (what == CANSB200_CTX_DTDMA) {
+    if (c->nplans > 0) return fail(CANSB200_EINVAL, "ctx_set: CANSB200_CTX_DTDMA must be set before any plan is created on the context");
     // as in the reference (src/solver.f90:43-48, src/initsolver.f90 with is_poisson_dtdma): the "z pencil" extents that size
     // lambdaxy and a, b, c become those of the y pencil = my slab: lambdaxy(nx, ny), a/b/c(nz_local)
     c->dtdma = (value && c->nranks > 1) ? 1 : 0;
@@ -864,10 +929,16 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
 }
 
 int cansb200_get_work(cansb200_ctx* c, int which, void** ptr, size_t* nelem) {
+  // src/rk.f90:27-29 aliases three pencil-sized device buffers (`work`, `solver_buf_0`, `solver_buf_1`) as scratch of
+  // the momentum step; they are only live between solver calls, so the library lends its own scratch:
+  // 0 = A (x pencil), 1 = B (z-major intermediate), 2 = a third pencil.  Any solve on the context clobbers them.
   if (!c || !ptr) return fail(CANSB200_EINVAL, "null argument");
-  if (which != 0) return fail(CANSB200_EINVAL, "get_work: only buffer 0 exists");
-  *ptr = c->scratch.p;
-  if (nelem) *nelem = c->scratch.bytes / c->esz;
+  if (which < 0 || which > 2) return fail(CANSB200_EINVAL, "get_work: which must be 0, 1 or 2");
+  const size_t nel = (size_t)c->n[0] * c->n[1] * c->n[2];
+  DevBuf* b = which == 0 ? &c->scratch : (which == 1 ? &c->scratch2 : &c->work2);
+  if (b->ensure(nel * c->esz)) return fail(CANSB200_ENOMEM, "get_work: allocation failed");
+  *ptr = b->p;
+  if (nelem) *nelem = b->bytes / c->esz;
   return 0;
 }
 
@@ -947,12 +1018,14 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
     else { FftTables<double>* t; rc = get_tables<double>(ctx, pl->nt[d], &t); }
     if (rc) return rc;
   }
+  ctx->nplans++;
   *out = pl.release();
   return 0;
 }
 
 int cansb200_plan_destroy(cansb200_plan* pl) {
   if (!pl) return 0;
+  pl->ctx->nplans--;
   pl->zcache.release(); pl->p2cache.release(); pl->dencache.release(); pl->state.release();
   pl->dtdma_big.release(); pl->dtdma_small.release();
   delete pl;
@@ -999,23 +1072,39 @@ int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
-// device-side barrier over the ranks of the box, stream ordered (dist_kernels.cuh)
-static int dist_barrier(cansb200_ctx* c, cudaStream_t st) {
+// device-side flags over the ranks of the box, stream ordered (dist_kernels.cuh): announce and / or wait for slot `slot`
+static int dist_flag(cansb200_ctx* c, int slot, unsigned long long seq, bool signal, bool wait, cudaStream_t st) {
   DistPeers pp;
   for (int s = 0; s < CB_MAX_RANKS; ++s) pp.flags[s] = s < c->nranks ? (unsigned long long*)c->peer[s] : nullptr;
-  c->epoch += 1;
-  dist_barrier_kernel<<<1, 32, 0, st>>>(pp, c->rank, c->nranks, c->epoch, c->dist_status, 20ULL * 1000000000ULL);
+  dist_flag_kernel<<<1, 32, 0, st>>>(pp, c->rank, c->nranks, slot, seq, signal ? 1 : 0, wait ? 1 : 0, c->dist_status,
+                                     c->dist_status_dev, 20ULL * 1000000000ULL);
   c->launches++;
   CK(cudaGetLastError());
   return 0;
 }
+// a wait that timed out in an earlier solve left partly written buffers behind: refuse to go on
+static int dist_check(cansb200_ctx* c, const char* who) {
+  if (!c->connected) return fail(CANSB200_ECOMM, std::string(who) + ": cansb200_dist_connect has not been called");
+  if (c->dist_status && *(volatile int*)c->dist_status)
+    return fail(CANSB200_ECOMM, std::string(who) + ": a device-side wait for a peer timed out (a rank is missing or failed); results are invalid");
+  return 0;
+}
 
-// the z-slab decomposed solve: x and y transforms on my slab, tridiagonal stage on my z pencil
+// the z-slab decomposed solve: x and y transforms on my slab, tridiagonal stage on my z pencil.
+//
+// The two exchanges are the stores of the producing kernels (forward y transform -> z pencils of the owners,
+// tridiagonal solve -> slabs of the owners).  The middle of the solve runs as a three-stage pipeline over W windows
+// of x columns: while window w + 1 is still being transformed and sent (stage F, the caller's stream), window w is
+// solved and sent back (stage T) and window w - 1 is transformed back (stage B).  The per-window flags replace the
+// two whole-field barriers of round 1: NVLink (stages F and T) and HBM-only work (stage B, and the parts of F and T
+// that read the local field) overlap instead of alternating.
 template <class T>
 static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, const T* lam, const T* a, const T* b,
                       const T* c, cudaStream_t st) {
   cansb200_ctx* ctx = pl->ctx;
-  if (!ctx->connected) return fail(CANSB200_ECOMM, "solve: cansb200_dist_connect has not been called");
+  const unsigned long long seq = ++ctx->seq;   // first: every rank counts every collective call, whatever happens next
+  int rc = dist_check(ctx, "solve");
+  if (rc) return rc;
   const int nx = n[0], ny = n[1], nzl = n[2];
   const int nyl = ctx->n_z[1], nz = ctx->ng[2];
   const long long px = nx + 2, py = ny + 2;
@@ -1023,51 +1112,112 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
   T* Cz = (T*)((char*)ctx->region + ctx->off_C);
   T* XB = (T*)((char*)ctx->region + ctx->off_XB);
   T* pin = p + (px * py + px + 1);
-  int rc;
+  if (pl->th_n != nz - pl->q) return fail(CANSB200_EINVAL, "solve: plan / grid mismatch");
+  const bool pipelined = thomas_is_pipelined(pl);
+  // windows: whole 128-byte row segments, as many as asked for (auto: 4) that divide nx
+  const int wide = (int)(128 / sizeof(T));
+  int W = 1;
+  if (pipelined && !ctx->profiling) {
+    const int want = ctx->dist_windows > 0 ? ctx->dist_windows : 4;
+    for (W = want < CB_MAX_WINDOWS ? want : CB_MAX_WINDOWS; W > 1; --W)
+      if (nx % (W * wide) == 0) break;
+  }
+  cudaStream_t sF = st, sT = st, sB = st;
+  if (W > 1) {
+    if (!ctx->dist_sT) {
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // later stages first: the pipeline drains instead of piling up
+      CK(cudaStreamCreateWithPriority(&ctx->dist_sT, cudaStreamNonBlocking, hi));
+      CK(cudaStreamCreateWithPriority(&ctx->dist_sB, cudaStreamNonBlocking, hi));
+    }
+    while ((int)ctx->dist_ev.size() < 2 * CB_MAX_WINDOWS + 1) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->dist_ev.push_back(e);
+    }
+    sT = ctx->dist_sT; sB = ctx->dist_sB;
+  }
   prof_mark(ctx, st);
   R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nzl, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
   if (rc) return rc;
   prof_mark(ctx, st);
-  // forward y: rows go straight to the z pencils of their owners (pack + wire + unpack = one peer store)
-  R2RGeom gyf{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nzl, ny, 1};
-  gyf.row_tab = ctx->ytab_fwd.p;
-  rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A, A, gyf, pl->opt.fft_y_lines, st);
-  if (rc) return rc;
-  rc = dist_barrier(ctx, st);
-  if (rc) return rc;
-  prof_mark(ctx, st);
-  // tridiagonal solve on my z pencil (nx, ny/P, nz); result rows go straight to the slabs of their owners
-  if (pl->th_n != nz - pl->q) return fail(CANSB200_EINVAL, "solve: plan / grid mismatch");
   ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam, a, b, c);
   D.out_rows = (const OutRow<T>*)ctx->ztab.p;
-  rc = gaussel_prepare<T>(pl, D, st);
-  if (rc) return rc;
-  prof_mark(ctx, st);
-  if (thomas_is_pipelined(pl)) {
-    rc = gaussel_apply<T>(pl, D, Cz, (T)normfft, st);
+  if (W > 1) {
+    rc = gaussel_prepare<T>(pl, D, st);   // pivot-cache lookup (and factorisation on a miss) ahead of the pipeline
     if (rc) return rc;
-    if (pl->th_n < nz) {   // face-centred Dirichlet: the last plane is not part of the system but still travels back
-      scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, pl->th_n, nz, (long long)nx * nyl, nx);
+  }
+  const int ww = nx / W;
+  // while the tridiagonal kernel shares the GPU with the y transforms of the neighbouring windows it must not take every
+  // SM (one of its CTAs fills a whole SM): leave part of the machine to stages F and B
+  const int cap = ctx->dist_thomas_ctas > 0 ? ctx->dist_thomas_ctas : (ctx->num_sms * 5) / 8;
+  for (int w = 0; w < W; ++w) {
+    const int xb = w * ww;
+    // ---- stage F: forward y transform of the window; rows go straight to the z pencils of their owners
+    R2RGeom gyf{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, ww, nzl, ny, 1};
+    gyf.row_tab = ctx->ytab_fwd.p;
+    gyf.x0 = xb;
+    rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + xb, A + xb, gyf, pl->opt.fft_y_lines, sF);
+    if (rc) return rc;
+    if (W > 1) {
+      rc = dist_flag(ctx, CB_SLOT_FWD + w, seq, true, false, sF);
+      if (rc) return rc;
+      CK(cudaEventRecord(ctx->dist_ev[w], sF));
+      CK(cudaStreamWaitEvent(sT, ctx->dist_ev[w], 0));
+      rc = dist_flag(ctx, CB_SLOT_FWD + w, seq, false, true, sT);
+    } else {
+      rc = dist_flag(ctx, CB_SLOT_FWD, seq, true, true, sT);
+    }
+    if (rc) return rc;
+    // ---- stage T: tridiagonal solve on the window of my z pencil (nx, ny/P, nz); result rows go to the slabs
+    if (W == 1) {
+      prof_mark(ctx, st);
+      rc = gaussel_prepare<T>(pl, D, st);
+      if (rc) return rc;
+      prof_mark(ctx, st);
+    }
+    if (pipelined) {
+      D.xb = xb; D.xn = ww;
+      ctx->cta_cap = W > 1 ? cap : 0;
+      rc = gaussel_apply<T>(pl, D, Cz, (T)normfft, sT);
+      ctx->cta_cap = 0;
+      if (rc) return rc;
+      if (pl->th_n < nz) {   // face-centred Dirichlet: the last plane is not part of the system but still travels back
+        scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, sT>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, pl->th_n, nz, nyl, nx, xb, ww);
+        ctx->launches++;
+      }
+    } else {
+      ThomasDev<T> D2 = D;
+      D2.out_rows = nullptr;
+      rc = gaussel_apply<T>(pl, D2, Cz, (T)normfft, sT);
+      if (rc) return rc;
+      scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, sT>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, 0, nz, nyl, nx, 0, nx);
       ctx->launches++;
     }
-  } else {
-    ThomasDev<T> D2 = D;
-    D2.out_rows = nullptr;
-    rc = gaussel_apply<T>(pl, D2, Cz, (T)normfft, st);
+    CK(cudaGetLastError());
+    if (W > 1) {
+      rc = dist_flag(ctx, CB_SLOT_BWD + w, seq, true, false, sT);
+      if (rc) return rc;
+      CK(cudaEventRecord(ctx->dist_ev[CB_MAX_WINDOWS + w], sT));
+      CK(cudaStreamWaitEvent(sB, ctx->dist_ev[CB_MAX_WINDOWS + w], 0));
+      rc = dist_flag(ctx, CB_SLOT_BWD + w, seq, false, true, sB);
+    } else {
+      rc = dist_flag(ctx, CB_SLOT_BWD, seq, true, true, sB);
+    }
     if (rc) return rc;
-    scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, 0, nz, (long long)nx * nyl, nx);
-    ctx->launches++;
+    if (W == 1) prof_mark(ctx, st);
+    // ---- stage B: backward y transform of the window; gathers its rows from the way-back buffer
+    R2RGeom gyb{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, ww, nzl, ny, 1};
+    gyb.row_tab = ctx->ytab_bwd.p;
+    gyb.x0 = xb;
+    rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], XB, A + xb, gyb, pl->opt.fft_y_lines, sB);
+    if (rc) return rc;
   }
-  CK(cudaGetLastError());
-  rc = dist_barrier(ctx, st);
-  if (rc) return rc;
-  prof_mark(ctx, st);
-  // backward y: gathers its rows from the way-back buffer, writes the natural slab
-  R2RGeom gyb{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, nzl, ny, 1};
-  gyb.row_tab = ctx->ytab_bwd.p;
-  rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], XB, A, gyb, pl->opt.fft_y_lines, st);
-  if (rc) return rc;
+  if (W > 1) {
+    CK(cudaEventRecord(ctx->dist_ev[2 * CB_MAX_WINDOWS], sB));
+    CK(cudaStreamWaitEvent(st, ctx->dist_ev[2 * CB_MAX_WINDOWS], 0));
+  }
   prof_mark(ctx, st);
   R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nzl, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
@@ -1083,7 +1233,9 @@ template <class T>
 static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double normfft, const T* lam, const T* a, const T* b,
                             const T* c, cudaStream_t st) {
   cansb200_ctx* ctx = pl->ctx;
-  if (!ctx->connected) return fail(CANSB200_ECOMM, "solve: cansb200_dist_connect has not been called");
+  const unsigned long long seq = ++ctx->seq;
+  int rc = dist_check(ctx, "solve (dtdma)");
+  if (rc) return rc;
   const int nx = n[0], ny = n[1], nzl = n[2], P = ctx->nranks, r = ctx->rank;
   const long long px = nx + 2, py = ny + 2;
   const size_t ncol = (size_t)nx * ny;
@@ -1103,7 +1255,6 @@ static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double norm
   T* A = (T*)ctx->scratch.p;
   T* G = (T*)((char*)ctx->region + ctx->off_C);
   T* pin = p + (px * py + px + 1);
-  int rc;
   prof_mark(ctx, st);
   R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nzl, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
@@ -1133,7 +1284,7 @@ static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double norm
   dtdma_gather_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(pp, r, P, (long long)ncol, D.ra, D.rc, D.rp);
   ctx->launches += 3;
   CK(cudaGetLastError());
-  rc = dist_barrier(ctx, st);
+  rc = dist_flag(ctx, CB_SLOT_BAR, seq, true, true, st);
   if (rc) return rc;
   // reduced system of all ranks, solved redundantly on every rank; then my inner rows
   DtdmaDev<T> R = D;
@@ -1145,7 +1296,7 @@ static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double norm
   dtdma_phase3_kernel<T><<<ctx->num_sms * 8, 256, 0, st>>>(F, A);
   ctx->launches += 2;
   CK(cudaGetLastError());
-  rc = dist_barrier(ctx, st);   // nobody refills my gather buffer before I have read it
+  rc = dist_flag(ctx, CB_SLOT_BAR + 1, seq, true, true, st);   // nobody refills my gather buffer before I have read it
   if (rc) return rc;
   prof_mark(ctx, st);
   rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A, A, gy, pl->opt.fft_y_lines, st);
@@ -1258,6 +1409,8 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
     if (mem_kind == CANSB200_MEM_HOST) {
       CK(cudaMemcpyAsync(p_any, ctx->staging.p, nh * sizeof(T), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
+      const int rcs = dist_check(ctx, "solve");
+      if (rcs) return rcs;
     }
     pl->solves++;
     return 0;
@@ -1434,6 +1587,7 @@ static int solve_z_impl(cansb200_plan* pl, void* p_any, const int n[3], double n
   const T* lam0 = (const T*)ctx->zero_lam.p;
   T* pin = p + (px * py + px + 1);
   int rc;
+  const unsigned long long seq = ++ctx->seq;
   if (ctx->nranks == 1) {
     // z is not decomposed: solve in place on the haloed array (row pitch px, plane pitch px * py)
     if (nzl != ctx->ng[2]) return fail(CANSB200_EINVAL, "solve_z: extents");
@@ -1444,14 +1598,15 @@ static int solve_z_impl(cansb200_plan* pl, void* p_any, const int n[3], double n
     rc = gaussel_apply<T>(pl, D, pin, (T)norm, st);
     if (rc) return rc;
   } else {
-    if (!ctx->connected) return fail(CANSB200_ECOMM, "solve_z: cansb200_dist_connect has not been called");
+    rc = dist_check(ctx, "solve_z");
+    if (rc) return rc;
     const int nyl = ctx->n_z[1], nz = ctx->ng[2];
     T* Cz = (T*)((char*)ctx->region + ctx->off_C);
     const unsigned blocks = (unsigned)(ctx->num_sms * 8);
     slab_rows_copy_kernel<T><<<blocks, 256, 0, st>>>(pin, px, px * py, (const DistRow<T>*)ctx->ytab_fwd.p, nx, ny, nzl, 1);
     ctx->launches++;
     CK(cudaGetLastError());
-    rc = dist_barrier(ctx, st);
+    rc = dist_flag(ctx, CB_SLOT_BAR, seq, true, true, st);
     if (rc) return rc;
     ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam0, a, b, c);
     D.nopin = 1;
@@ -1462,7 +1617,7 @@ static int solve_z_impl(cansb200_plan* pl, void* p_any, const int n[3], double n
       rc = gaussel_apply<T>(pl, D, Cz, (T)norm, st);
       if (rc) return rc;
       if (pl->th_n < nz) {
-        scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, pl->th_n, nz, (long long)nx * nyl, nx);
+        scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, pl->th_n, nz, nyl, nx, 0, nx);
         ctx->launches++;
       }
     } else {
@@ -1470,11 +1625,11 @@ static int solve_z_impl(cansb200_plan* pl, void* p_any, const int n[3], double n
       D2.out_rows = nullptr;
       rc = gaussel_apply<T>(pl, D2, Cz, (T)norm, st);
       if (rc) return rc;
-      scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, 0, nz, (long long)nx * nyl, nx);
+      scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, 0, nz, nyl, nx, 0, nx);
       ctx->launches++;
     }
     CK(cudaGetLastError());
-    rc = dist_barrier(ctx, st);
+    rc = dist_flag(ctx, CB_SLOT_BAR + 1, seq, true, true, st);
     if (rc) return rc;
     slab_rows_copy_kernel<T><<<blocks, 256, 0, st>>>(pin, px, px * py, (const DistRow<T>*)ctx->ytab_bwd.p, nx, ny, nzl, 0);
     ctx->launches++;
@@ -1495,6 +1650,9 @@ int cansb200_solve_z(cansb200_plan* pl, void* p, const int n[3], int nhalo, doub
   if (!pl || !p || !n || !a || !b || !c) return fail(CANSB200_EINVAL, "solve_z: null argument");
   if (nhalo != 1) return fail(CANSB200_EINVAL, "solve_z: nhalo must be 1");
   cansb200_ctx* ctx = pl->ctx;
+  if (ctx->dtdma)
+    return fail(CANSB200_EUNSUPPORTED, "solve_z: not available on a CANSB200_CTX_DTDMA context (the reference routes it through gaussel_dtdma, "
+                                       "src/solver.f90:592-596; use cansb200_gaussel_dtdma with lambdaxy = NULL on the slab)");
   for (int d = 0; d < 3; ++d)
     if (n[d] != ctx->n[d]) return fail(CANSB200_EINVAL, "solve_z: n differs from the context's local extents");
   if (mem_kind != CANSB200_MEM_HOST && mem_kind != CANSB200_MEM_DEVICE) return fail(CANSB200_EINVAL, "solve_z: bad mem_kind");
@@ -1534,6 +1692,7 @@ int cansb200_gaussel(cansb200_plan* pl, void* pz, const int d3[3], int n_rows, i
                      const void* lam, const void* a, const void* b, const void* c, void* stream) {
   if (!pl || !pz || !d3 || !lam || !a || !b || !c) return fail(CANSB200_EINVAL, "gaussel: null argument");
   const int nx = d3[0], ny = d3[1];
+  if (pl->ctx->dtdma) return fail(CANSB200_EUNSUPPORTED, "gaussel: a CANSB200_CTX_DTDMA context keeps no pivot cache (use cansb200_gaussel_dtdma)");
   if (nx != pl->ctx->n_z[0] || ny != pl->ctx->n_z[1]) return fail(CANSB200_EINVAL, "gaussel: extents differ from the plan's");
   cudaStream_t st = (cudaStream_t)stream;
   return pl->ctx->is_fp32

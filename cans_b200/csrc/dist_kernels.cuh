@@ -31,23 +31,42 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-// One CTA, thread s talks to rank s: announce "everything I enqueued before this kernel is done"
-// (kernel boundary + system fence order the earlier peer stores before the flag), then wait for the same
-// announcement of every rank.  A rank that never shows up trips the timeout instead of hanging the GPU.
-__global__ void dist_barrier_kernel(DistPeers peers, int rank, int nranks, unsigned long long epoch, int* status,
-                                    unsigned long long timeout_ns) {
+// Flag words: every rank owns CB_FLAG_SLOTS x CB_MAX_RANKS words at the start of its exchange region; word
+// [slot][r] is written by rank r only.  The value is the sequence number of the distributed solve (one per
+// cansb200_solve / _solve_z call, the same on every rank because the calls are collective), so flags never
+// need a reset and a rank that fails half-way through a solve cannot shift the meaning of later flags.
+// Slots: 0..7 "my forward y transform of x window w has landed on every z pencil", 8..15 "my tridiagonal
+// solve of x window w has landed on every slab", 16 / 17 whole-field barriers (solve_z, distributed TDMA).
+#define CB_FLAG_SLOTS 32
+#define CB_SLOT_FWD 0
+#define CB_SLOT_BWD 8
+#define CB_SLOT_BAR 16
+#define CB_MAX_WINDOWS 8
+
+// One CTA, thread s talks to rank s.  SIGNAL: announce "everything enqueued on this stream before this kernel
+// is done" (kernel boundary + system fence order the earlier peer stores before the flag).  WAIT: spin until
+// every rank has announced the same.  A rank that never shows up trips the timeout instead of hanging the GPU;
+// `status` is a host-mapped word the library checks before the next solve (CANSB200_ECOMM), `status_dev` its
+// device-resident twin (what later waits look at).
+__global__ void dist_flag_kernel(DistPeers peers, int rank, int nranks, int slot, unsigned long long seq, int do_signal,
+                                 int do_wait, volatile int* status, volatile int* status_dev, unsigned long long timeout_ns) {
   const int s = threadIdx.x;
   if (s >= nranks) return;
-  __threadfence_system();
-  st_release_sys(peers.flags[s] + rank, epoch);
-  const unsigned long long* mine = peers.flags[rank] + s;
+  if (do_signal) {
+    __threadfence_system();
+    st_release_sys(peers.flags[s] + slot * CB_MAX_RANKS + rank, seq);
+  }
+  if (!do_wait || *status_dev) return;   // after one time-out the solve is lost anyway: later waits do not add 20 s each
+  const unsigned long long* mine = peers.flags[rank] + slot * CB_MAX_RANKS + s;
   const unsigned long long t0 = global_timer_ns();
-  while (ld_acquire_sys(mine) < epoch) {
+  while (ld_acquire_sys(mine) < seq) {
     if (global_timer_ns() - t0 > timeout_ns) {
-      atomicExch(status, 1);
+      *status_dev = 1;
+      *status = 1;
+      __threadfence_system();
       break;
     }
-    __nanosleep(200);
+    __nanosleep(100);
   }
   __threadfence_system();
 }
@@ -58,12 +77,13 @@ __global__ void dist_barrier_kernel(DistPeers peers, int rank, int nranks, unsig
 template <class T> struct DistOutRow { T* ptr; long long sj; };
 template <class T>
 __global__ void scatter_rows_kernel(const T* __restrict__ src, long long sk, const DistOutRow<T>* __restrict__ rows, int k0, int k1,
-                                    long long ncol, int nx) {
-  const long long tot = (long long)(k1 - k0) * ncol;
+                                    int ny, int nx, int xb, int xn) {
+  const long long ncolw = (long long)ny * xn;   // columns of the window [xb, xb + xn) of every j
+  const long long tot = (long long)(k1 - k0) * ncolw;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
-    const long long k = k0 + e / ncol, col = e - (e / ncol) * ncol;
-    const long long j = col / nx, i = col - j * nx;
-    rows[k].ptr[j * rows[k].sj + i] = src[k * sk + col];
+    const long long k = k0 + e / ncolw, cw = e - (e / ncolw) * ncolw;
+    const long long j = cw / xn, i = xb + (cw - j * xn);
+    rows[k].ptr[j * rows[k].sj + i] = src[k * sk + j * nx + i];
   }
 }
 

@@ -3,11 +3,12 @@
 // stays decomposed, every rank eliminates its inner rows so that they only couple to its first and last row,
 // the 2 P boundary rows form a reduced tridiagonal system, and the inner rows are updated from its solution.
 //
-// State of this file: the four kernels below are the complete arithmetic, in the reference's operation order
-// (exactly rounded, never contracted; the tests compare them with the CPU restatement of the same routine).  They are
-// exercised through the stage-level entry point cansb200_gaussel_dtdma with the P slabs living on ONE GPU
-// ("virtual ranks"); moving the reduced rows between GPUs over the peer row tables of dist_kernels.cuh is the
-// remaining step.  One thread per (i, j) column, i fastest: every access is coalesced.
+// The four kernels below are the complete arithmetic, in the reference's operation order (exactly rounded, never
+// contracted; the tests compare them with the CPU restatement of the same routine).  Two callers (capi.cu):
+// cansb200_gaussel_dtdma keeps the P slabs on ONE GPU ("virtual ranks", stage-level parity), and solve_dist_dtdma
+// (CANSB200_CTX_DTDMA) runs the elimination per rank and gathers the two boundary rows of every rank on all peers
+// with dtdma_gather_kernel (peer-mapped stores) before the redundant reduced solve.
+// One thread per (i, j) column, i fastest: every access is coalesced.
 #pragma once
 #include <cuda_runtime.h>
 #include "thomas_kernels.cuh"   // exactly rounded arithmetic helpers

@@ -240,6 +240,8 @@ template <class T> struct R2Args {
   const Cx<T>* mak;          // (cos, sin)(pi k / (2N)), k = 0..N/2
   const R2Row<T>* row_tab;   // SPLIT kernels: where each output (forward) / input (backward) row lives
   int flags;                 // CB_R2_LD_NA | CB_R2_ST_CS
+  int x0 = 0, g0 = 0;        // SPLIT kernels launched on a window of the slab: first column / first plane of the window
+                             // (the row table addresses whole slab rows; in / out already point at the window)
 };
 
 template <class T, class Cfg, bool YMODE> struct R2Lay {
@@ -308,8 +310,8 @@ __device__ __forceinline__ R2Loc<T> r2_locate(const R2Args<T>& A, int c) {
     L.ob = L.oa + A.out_ls;
     L.has_a = x < A.lines_per_group;
     L.has_b = x + 1 < A.lines_per_group;
-    L.g = g;
-    L.x = x;
+    L.g = g + A.g0;
+    L.x = x + A.x0;
   } else {
     // 32-bit index arithmetic (the launcher checks that the line count fits)
     const unsigned lpg = (unsigned)A.lines_per_group;

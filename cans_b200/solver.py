@@ -94,6 +94,28 @@ class Context:
         check(lib.cansb200_dist_connect(self._h, buf), "dist_connect")
         dist.barrier(group=group)
 
+    @staticmethod
+    def connect_local(ctxs):
+        """All ranks in THIS process on THIS device (ctxs[r] = context of rank r): wires the exchange regions directly
+        (`cansb200_dist_connect_local`).  Each rank's solve must be enqueued on its own stream before any host sync."""
+        arr = (C.c_void_p * len(ctxs))(*[c.handle for c in ctxs])
+        check(lib.cansb200_dist_connect_local(arr, len(ctxs)), "dist_connect_local")
+
+    def is_bound(self):
+        """`is_bound(0:1,3)` of initmpi (src/initmpi.f90:193-250) as [idir][ibound]: does this rank own the physical
+        boundary?  z slabs: x and y always, z only on the first / last rank."""
+        return [[True, True], [True, True],
+                [self.lo[2] == 1, self.lo[2] + self.n[2] - 1 == self.ng[2]]]
+
+    def hi(self):
+        return [self.lo[d] + self.n[d] - 1 for d in range(3)]
+
+    def set_dist_windows(self, windows: int = -1, thomas_ctas: int = -1):
+        """Several ranks: x windows of the pipelined exchange (-1 = auto, 1 = two whole-field barriers) and the CTAs the
+        tridiagonal kernel may take while it shares the GPU with the y transforms."""
+        check(lib.cansb200_ctx_set(self._h, 10, int(windows)), "ctx_set")
+        check(lib.cansb200_ctx_set(self._h, 11, int(thomas_ctas)), "ctx_set")
+
     def dist_status(self) -> int:
         st = C.c_int()
         check(lib.cansb200_dist_status(self._h, C.byref(st)), "dist_status")
@@ -370,29 +392,40 @@ def solver_gaussel_z(n, ng, hi, a, b, c, bcz, c_or_f, norm, p, arrplan: Plan = N
     return p
 
 
-def updt_rhs_b(c_or_f, cbc, n, rhsbx, rhsby, rhsbz, p, alpha=None):
-    """src/bound.f90:514-598 on one rank: adds the wall contributions to the first / last planes."""
+def updt_rhs_b(c_or_f, cbc, n, is_bound, rhsbx, rhsby, rhsbz, p, alpha=None):
+    """src/bound.f90:514-598: adds the wall contributions to the first / last interior planes of the ranks that own
+    the wall (`is_bound[idir][ibound]`, as `Context.is_bound()` returns it)."""
     norm = 1.0 if alpha is None else alpha
     q = [1 if (c_or_f[d] == "f" and cbc[d][1] == "D") else 0 for d in range(3)]
     n1, n2, n3 = n
     K, J, I = slice(1, n3 + 1), slice(1, n2 + 1), slice(1, n1 + 1)
     if rhsbx is not None:
-        p[K, J, 1] += rhsbx[0] * norm
-        p[K, J, n1 - q[0]] += rhsbx[1] * norm
+        if is_bound[0][0]:
+            p[K, J, 1] += rhsbx[0] * norm
+        if is_bound[0][1]:
+            p[K, J, n1 - q[0]] += rhsbx[1] * norm
     if rhsby is not None:
-        p[K, 1, I] += rhsby[0] * norm
-        p[K, n2 - q[1], I] += rhsby[1] * norm
+        if is_bound[1][0]:
+            p[K, 1, I] += rhsby[0] * norm
+        if is_bound[1][1]:
+            p[K, n2 - q[1], I] += rhsby[1] * norm
     if rhsbz is not None:
-        p[1, J, I] += rhsbz[0] * norm
-        p[n3 - q[2], J, I] += rhsbz[1] * norm
+        if is_bound[2][0]:
+            p[1, J, I] += rhsbz[0] * norm
+        if is_bound[2][1]:
+            p[n3 - q[2], J, I] += rhsbz[1] * norm
 
 
-def solve_helmholtz(n, ng, arrplan, normfft, alpha, lambdaxy, a, b, c, rhsbx, rhsby, rhsbz, cbc, c_or_f, p, stream=None):
-    """src/solve_helmholtz.f90:28-75: p/alpha + lap(p) = rhs."""
-    updt_rhs_b(c_or_f, cbc, n, rhsbx, rhsby, rhsbz, p, alpha)
+def solve_helmholtz(n, ng, hi, arrplan, normfft, alpha, lambdaxy, a, b, c, rhsbx, rhsby, rhsbz, is_bound, cbc, c_or_f, p,
+                    stream=None, is_impdiff_1d=False):
+    """src/solve_helmholtz.f90:28-75 (same argument order): p/alpha + lap(p) = rhs.  `is_impdiff_1d` is a module
+    parameter in the reference (`mod_param`); here a keyword."""
+    updt_rhs_b(c_or_f, cbc, n, is_bound, rhsbx, rhsby, rhsbz, p, alpha)
     ty = p.dtype.type if isinstance(p, np.ndarray) else (np.float32 if p.dtype == torch.float32 else np.float64)
     alphai = ty(1.0) / ty(alpha)
     bb = b + alphai if not _is_torch(b) else b + float(alphai)
+    if is_impdiff_1d:
+        return solver_gaussel_z(n, ng, hi, a, bb, c, cbc[2], c_or_f, alphai, p, arrplan=arrplan, stream=stream)
     return solver(n, ng, arrplan, ty(normfft) * alphai, lambdaxy, a, bb, c, cbc, c_or_f, p, stream)
 
 

@@ -69,11 +69,19 @@ int cansb200_finalize(cansb200_ctx* ctx);
  *      1. every rank calls cansb200_dist_export into a blob of cansb200_dist_blob_size() bytes,
  *      2. the host gathers the blobs of all ranks in rank order (MPI_Allgather / torch.distributed),
  *      3. every rank calls cansb200_dist_connect with the gathered array.
- *    cansb200_dist_status returns non-zero if a device-side barrier ever timed out (a rank went missing). */
+ *    A device-side wait for a peer that does not show up within 20 s gives up instead of hanging the GPU and sets a
+ *    sticky status word: every later cansb200_solve / _solve_z on the context (and the host-memory solve that saw it)
+ *    returns CANSB200_ECOMM; cansb200_dist_status reads the word. */
 int cansb200_dist_blob_size(void);
 int cansb200_dist_export(cansb200_ctx* ctx, void* blob);
 int cansb200_dist_connect(cansb200_ctx* ctx, const void* blobs);
 int cansb200_dist_status(cansb200_ctx* ctx, int* status);
+/* The same rendezvous when all ranks are contexts of ONE process on ONE device (ctxs[r] = the context of rank r):
+ * the peers' regions are plain device pointers.  Every rank's solve must then be enqueued on its own stream before
+ * the host synchronises (the device-side waits of one rank need the kernels of the others to run; for the same reason
+ * the process must load its kernels eagerly, CUDA_MODULE_LOADING=EAGER, or have run every kernel once).  It exists so that
+ * a single-GPU box exercises the kernels, row tables and flags of the multi-GPU path (tests/test_gpu_parity.py). */
+int cansb200_dist_connect_local(cansb200_ctx* const* ctxs, int n);
 
 /* local extents of this rank: n = x-pencil (nx, ny, nz/P) as main.f90 sees it, lo_z / n_z =
  * z-pencil (nx, ny/P, nz) that lambdaxy is indexed by (src/initsolver.f90:54-58). 1-based lo. */
@@ -115,7 +123,8 @@ int cansb200_gaussel(cansb200_plan* plan, void* pz, const int dims3[3], int n_ro
  *    (src/solver.f90:309-517, src/solver_gpu.f90:430-695; is_poisson_dtdma) on a haloless field pz[k][j][i] whose
  *    rows are split at `starts` (nsplit + 1 entries) into the z slabs of nsplit ranks, all living on this GPU:
  *    inner-row elimination per slab, reduced 2-rows-per-rank system, update.  lambdaxy may be NULL (z-only
- *    variant).  The reduced rows do not yet travel between GPUs. */
+ *    variant).  This entry point keeps all slabs on one GPU (stage-level parity with the oracle); on a CANSB200_CTX_DTDMA
+ *    context cansb200_solve runs the same elimination per rank and gathers the reduced rows over the peer mappings. */
 int cansb200_gaussel_dtdma(cansb200_plan* plan, void* pz, const int dims3[3], int n_rows, int nsplit, const int* starts,
                            int is_periodic, double norm, const void* lambdaxy, const void* a, const void* b,
                            const void* c, void* stream);
@@ -165,11 +174,17 @@ enum {
                                     (distributed TDMA), the only exchange is the 2-rows-per-rank reduced system.  Set it BEFORE creating
                                     plans: cansb200_get_extents then reports n_z = (nx, ny, nz_local) as the reference does, i.e. the
                                     caller passes lambdaxy(nx, ny) and its own z slice of a, b, c.  Needs nz >= 6 nranks^2.  Default 0 */
+  CANSB200_CTX_DIST_WINDOWS = 10, /* several ranks: x windows of the pipelined exchange (forward y transform of window w + 1, tridiagonal
+                                    solve of window w and backward y transform of window w - 1 run concurrently, ordered by
+                                    per-window flags); -1 = auto (4 when nx allows), 1 = one window (two whole-field barriers) */
+  CANSB200_CTX_DIST_THOMAS_CTAS = 11, /* CTAs of the persistent tridiagonal kernel while it shares the GPU with the y transforms of the
+                                    neighbouring windows (one CTA fills an SM); -1 = auto (5/8 of the SMs) */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
                                     bit 2 = force the maximum shared-memory carveout (default: the driver picks, which leaves L1 to the twiddles) */
 };
 int cansb200_ctx_set(cansb200_ctx* ctx, int what, int value);
-/* workspace the OpenACC host may alias as `work` / `solver_buf_0` (src/rk.f90:26-30) */
+/* pencil-sized device buffers the OpenACC host may alias as `work` / `solver_buf_0` / `solver_buf_1` (src/rk.f90:27-29):
+ * which = 0, 1, 2.  They are the library's own scratch: any solve on the context overwrites them. */
 int cansb200_get_work(cansb200_ctx* ctx, int which, void** ptr, size_t* nelem);
 
 #ifdef __cplusplus

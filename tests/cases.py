@@ -43,6 +43,18 @@ CASES = {
     "fp32_channel": ([32, 16, 40], [12.0, 6.0, 2.0], [P, P, N], C3, 2.0, np.float32),
     "fp32_ldc": ([2, 64, 64], [0.03125, 1.0, 1.0], [P, N, N], C3, 0.0, np.float32),
 }
+# cases of the distributed (z-slab) solve: name -> (ng, l, cbc, c_or_f, gr, dtype, helmholtz)
+DIST_CASES = {
+    "chan_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),
+    "tgv_64x128x64": ([64, 128, 64], [6.2832] * 3, [P, P, P], C3, 0.0, np.float64, False),
+    "duct_128x64x96": ([128, 64, 96], [6.0, 2.0, 2.0], [P, N, N], C3, 1.5, np.float64, False),
+    "uneven_64x64x70": ([64, 64, 70], [1.0, 1.0, 1.0], [N, P, ["D", "D"]], C3, 1.0, np.float64, False),
+    "helm_w_64x64x64": ([64, 64, 64], [1.0, 1.0, 1.0], [P, P, ["D", "D"]], ["c", "c", "f"], 1.0, np.float64, True),
+    "tma_32x64x256": ([32, 64, 256], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # full chunks: TMA tile path
+    "cluster_32x64x1024": ([32, 64, 1024], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # CTA-pair Thomas + peer stores
+    "fp32_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float32, False),
+}
+
 HELMHOLTZ = {"helm_u_face_x", "helm_v_face_y", "helm_w_face_z", "helm_w_face_z_nn"}
 ALPHA = -0.0123  # alpha = -0.5 * visc * dt_rk < 0 (src/main.f90:456)
 

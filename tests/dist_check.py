@@ -18,19 +18,8 @@ import cases  # noqa: E402
 import cans_b200 as cb  # noqa: E402
 from cans_b200.decomp import SlabDecomp  # noqa: E402
 
-P, N = ["P", "P"], ["N", "N"]
-C3 = ["c"] * 3
-# name -> (ng, l, cbc, c_or_f, gr, dtype, helmholtz)
-DIST_CASES = {
-    "chan_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),
-    "tgv_64x128x64": ([64, 128, 64], [6.2832] * 3, [P, P, P], C3, 0.0, np.float64, False),
-    "duct_128x64x96": ([128, 64, 96], [6.0, 2.0, 2.0], [P, N, N], C3, 1.5, np.float64, False),
-    "uneven_64x64x70": ([64, 64, 70], [1.0, 1.0, 1.0], [N, P, ["D", "D"]], C3, 1.0, np.float64, False),
-    "helm_w_64x64x64": ([64, 64, 64], [1.0, 1.0, 1.0], [P, P, ["D", "D"]], ["c", "c", "f"], 1.0, np.float64, True),
-    "tma_32x64x256": ([32, 64, 256], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # full chunks: TMA tile path
-    "cluster_32x64x1024": ([32, 64, 1024], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # CTA-pair Thomas + peer stores
-    "fp32_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float32, False),
-}
+DIST_CASES = cases.DIST_CASES
+P = cases.P
 
 
 def main():
@@ -63,8 +52,8 @@ def main():
         for rep in range(3):   # repeated solves exercise buffer reuse across the device-side barriers
             pd.copy_(torch.from_numpy(pl))
             if helm:
-                cb.solve_helmholtz(ctx.n, ng, sd.arrplan, sd.normfft, cases.ALPHA, sd.lambdaxy, sd.a, sd.b, sd.c, None, None,
-                                   None, cbc, cf, pd)
+                cb.solve_helmholtz(ctx.n, ng, ctx.hi(), sd.arrplan, sd.normfft, cases.ALPHA, sd.lambdaxy, sd.a, sd.b, sd.c, None, None,
+                                   None, ctx.is_bound(), cbc, cf, pd)
             else:
                 cb.solver(ctx.n, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, pd)
         torch.cuda.synchronize()
@@ -126,8 +115,8 @@ def main():
             for rep in range(2):
                 pd.copy_(torch.from_numpy(pl))
                 if helm:
-                    cb.solve_helmholtz(ctx2.n, ng, sd2.arrplan, sd2.normfft, cases.ALPHA, sd2.lambdaxy, sd2.a, sd2.b, sd2.c, None,
-                                       None, None, cbc, cf, pd)
+                    cb.solve_helmholtz(ctx2.n, ng, ctx2.hi(), sd2.arrplan, sd2.normfft, cases.ALPHA, sd2.lambdaxy, sd2.a, sd2.b, sd2.c, None,
+                                       None, None, ctx2.is_bound(), cbc, cf, pd)
                 else:
                     cb.solver(ctx2.n, ng, sd2.arrplan, sd2.normfft, sd2.lambdaxy, sd2.a, sd2.b, sd2.c, cbc, cf, pd)
             torch.cuda.synchronize()

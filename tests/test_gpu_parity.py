@@ -42,8 +42,8 @@ def _gpu_solve(cb, cs, p, helmholtz=False, **options):
     assert float(sd.normfft) == pytest.approx(float(cs["normfft"]), rel=1e-15 if cs["dtype"] == np.float64 else 1e-6)
     pd = torch.from_numpy(p.copy()).to(_dev())
     if helmholtz:
-        cb.solve_helmholtz(ng, ng, sd.arrplan, sd.normfft, cases.ALPHA, sd.lambdaxy, sd.a, sd.b, sd.c, None, None, None,
-                           cs["cbc"], cs["c_or_f"], pd)
+        cb.solve_helmholtz(ng, ng, ng, sd.arrplan, sd.normfft, cases.ALPHA, sd.lambdaxy, sd.a, sd.b, sd.c, None, None, None,
+                           ctx.is_bound(), cs["cbc"], cs["c_or_f"], pd)
     else:
         cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cs["cbc"], cs["c_or_f"], pd)
     torch.cuda.synchronize()
@@ -324,8 +324,8 @@ def test_factorisation_cache(cb):
         O.solve_helmholtz(ng, ng, cs["arrplan"], cs["normfft"], al, cs["lambdaxy"], cs["a"], cs["b"], cs["c"], None, None,
                           None, cs["cbc"], cs["c_or_f"], ref)
         pd = torch.from_numpy(p0.copy()).to(_dev())
-        cb.solve_helmholtz(ng, ng, sd.arrplan, sd.normfft, al, sd.lambdaxy, sd.a, sd.b, sd.c, None, None, None,
-                           cs["cbc"], cs["c_or_f"], pd)
+        cb.solve_helmholtz(ng, ng, ng, sd.arrplan, sd.normfft, al, sd.lambdaxy, sd.a, sd.b, sd.c, None, None, None,
+                           ctx.is_bound(), cs["cbc"], cs["c_or_f"], pd)
         assert cases.rel_l2(pd.cpu().numpy(), ref) < 1e-12
     st = sd.arrplan.stats()
     assert st["solves"] == len(alphas)
