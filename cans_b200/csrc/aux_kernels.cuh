@@ -98,4 +98,51 @@ __global__ void chkdiv_kernel(int n1, int n2, int n3, T dxi, T dyi, const T* __r
   }
 }
 
+// ---- eigenvalue order of an _OPENACC-built `initsolver` ------------------------------------------------------------
+// The CUDA build of the reference stores the spectrum of a periodic direction as cuFFT leaves it after its own
+// post-processing, (r0, r[n/2], r1, i1, r2, i2, ...), and permutes the eigenvalues to match
+// (/root/reference/src/initsolver.f90:98-117, `iswap`).  The kernels here keep FFTW's halfcomplex order
+// (r0, r1, ..., r[n/2], i[n/2-1], ..., i1), which is what the CPU build's `initsolver` produces.  pack_index maps a
+// halfcomplex position h to the position of the same mode in the packed order, so that
+//     lambda_halfcomplex[h] = lambda_packed[pack_index(h, n)].
+__host__ __device__ inline int pack_index(int h, int n) {
+  if (h == 0) return 0;
+  if (2 * h <= n) return (2 * h == n) ? 1 : 2 * h;   // real part of mode h (r[n/2] sits at 1 when n is even)
+  const int k = n - h;                                 // imaginary part of mode k
+  return (2 * k + 1 < n) ? 2 * k + 1 : 1;              // odd n: i[(n-1)/2] takes the slot r[n/2] has for even n
+}
+// out[j][i] = in[qy(j)][qx(i)] with q = pack_index in the directions flagged periodic-and-packed
+template <class T>
+__global__ void lambda_unpack_kernel(const T* __restrict__ in, T* __restrict__ out, int nx, int ny, int px, int py) {
+  const long long tot = (long long)nx * ny;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e / nx), i = (int)(e - (long long)j * nx);
+    const int qi = px ? pack_index(i, nx) : i, qj = py ? pack_index(j, ny) : j;
+    out[e] = in[(long long)qj * nx + qi];
+  }
+}
+
+// updt_rhs_b (src/bound.f90:514-598): p(plane) += value * norm on up to six boundary planes of the interior.
+// plane[d][s] = interior index (1-based) of the plane of direction d, side s, or 0 when this rank does not own that wall
+// or no value was passed.
+struct RhsbPlanes { int idx[3][2]; double val[3][2]; };
+template <class T>
+__global__ void updt_rhs_b_kernel(T* __restrict__ p, int n1, int n2, int n3, RhsbPlanes B, int dir) {
+  // one launch per direction (edge points belong to planes of two directions: the reference adds them one loop after
+  // the other, so must we); one thread per face point adds the lower then the upper plane (they coincide when n = 1)
+  const long long p1 = n1 + 2, p2 = n2 + 2;
+  const long long tot = dir == 0 ? (long long)n2 * n3 : (dir == 1 ? (long long)n1 * n3 : (long long)n1 * n2);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int q = B.idx[dir][s];
+      if (!q) continue;
+      const T v = (T)B.val[dir][s];
+      if (dir == 0) { const long long k = e / n2 + 1, j = e % n2 + 1; p[(k * p2 + j) * p1 + q] += v; }
+      else if (dir == 1) { const long long k = e / n1 + 1, i = e % n1 + 1; p[(k * p2 + q) * p1 + i] += v; }
+      else { const long long j = e / n1 + 1, i = e % n1 + 1; p[((long long)q * p2 + j) * p1 + i] += v; }
+    }
+  }
+}
+
 }  // namespace cb

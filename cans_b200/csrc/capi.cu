@@ -6,9 +6,12 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/cans_b200.h"
 #include "aux_kernels.cuh"
@@ -44,6 +47,16 @@ static int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+// integer names of the live plans (arrplan is `integer, dimension(2,2)` on the reference's CUDA build)
+static std::mutex g_plan_mu;
+static std::vector<cansb200_plan*> g_plan_ids;   // id - 1 -> plan (nullptr = free)
+
+// NVTX ranges around the solve and its stages (the reference brackets its steps with nvtxStartRange / nvtxEndRange through
+// timer_tic / timer_toc, src/timer.f90:113-216, src/nvtx.f90:48-64).  NVTX3 is header-only and costs a few ns without a tool.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -100,6 +113,10 @@ struct cansb200_ctx {
   DevBuf staging;   // haloed p when the caller's p is host memory
   DevBuf coef;      // a, b, c, lambdaxy staged from the host
   DevBuf zero_lam;  // all-zero lambdaxy of the z-only solve (solver_gaussel_z)
+  DevBuf lam_perm;  // lambdaxy brought from the _OPENACC (packed) order to halfcomplex order (CANSB200 option lambda_order = 1)
+  DevBuf ytab_fwd_pk, ytab_bwd_pk;   // row tables of the distributed y transforms when the y rows are dealt out in packed order
+  bool tabs_pk = false;
+  std::map<std::string, cansb200_plan*> zplans;   // z-only plans created on demand by cansb200_solve_z_bc, keyed by bcz + c_or_f(3)
   std::map<int, FftTables<double>> tabs64;
   std::map<int, FftTables<float>> tabs32;
   std::map<long long, DirectTables<double>> dtabs64;
@@ -122,6 +139,11 @@ struct cansb200_ctx {
   int* dist_status_dev = nullptr;              // its device-resident twin
   int dist_windows = -1;                       // x windows of the pipelined exchange (-1 = auto: up to 4)
   int dist_thomas_ctas = -1;                   // CTAs of the tridiagonal kernel while it shares the GPU with the y transforms (-1 = auto)
+  int dist_mode = -1;                          // exchange flavour: 0 = stores of the producing kernels, 1 = copy engines, -1 = auto
+  int dist_chunks = -1;                        // copy-engine exchange: z chunks of the forward half (-1 = auto)
+  DevBuf sendb;                                // copy-engine exchange: way-back send buffer [dest][j][k][i] (the forward one is scratch2)
+  DevBuf ytab_fwd_loc, ytab_fwd_loc_pk, ztab_loc;   // ... row tables that point into the local send buffers
+  std::vector<cudaStream_t> dist_cs;           // ... one copy stream per peer
   cudaStream_t dist_sT = nullptr, dist_sB = nullptr;   // pipeline stages: tridiagonal solve / backward y transform (forward = caller's stream)
   std::vector<cudaEvent_t> dist_ev;            // [w] forward window done, [W + w] tridiagonal window done, [2 W] backward done
   DevBuf ytab_fwd, ytab_bwd, ztab;
@@ -297,6 +319,7 @@ template <class T>
 static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, const R2RGeom& g, int tile_hint,
                    cudaStream_t st) {
   if (nt < 1 || g.lines_per_group < 1 || g.ngroups < 1) return 0;
+  NvtxRange nvtx_r2r(g.ymode ? (kind_is_forward(kind) ? "fft_y_fwd" : "fft_y_bwd") : (kind_is_forward(kind) ? "fft_x_fwd" : "fft_x_bwd"));
   // fast path: two-for-one register transforms (r2r2.cuh) for the instantiated lengths
   if (!ctx->force_generic && kind_is_fast(kind)) {
     bool ok = true;
@@ -560,6 +583,7 @@ template <class T> static int gaussel_prepare(cansb200_plan* pl, const ThomasDev
 // substitution on the column window D.xb .. D.xb + D.xn - 1
 template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T>& D, T* p, T norm, cudaStream_t st) {
   cansb200_ctx* ctx = pl->ctx;
+  NvtxRange nvtx_th("gaussel");
   CacheState* cs = (CacheState*)pl->state.p;
   if (thomas_is_pipelined(pl)) {
     // 16-byte tile copies need every row segment aligned: even (FP64) / multiple-of-4 (FP32) column counts and offsets
@@ -729,26 +753,35 @@ int cansb200_dist_export(cansb200_ctx* c, void* blob) {
 
 }  // extern "C"
 
-// device-side row tables of the peer-mapped stores / loads
-template <class T> static int build_dist_tables(cansb200_ctx* c) {
+// device-side row tables of the peer-mapped stores / loads.  `packed`: the rows of a periodic y direction are dealt out
+// to the z pencils by their position in the _OPENACC eigenvalue order (pack_index), so that the local slice of
+// lambdaxy an unchanged OpenACC-build initsolver hands over matches the rows a rank owns.
+template <class T> static int build_dist_tables(cansb200_ctx* c, bool packed) {
   const int P = c->nranks, r = c->rank;
   const long long nx = c->ng[0];
   const int ny = c->ng[1], nz = c->ng[2];
-  const long long nzl_r = c->zs[r + 1] - c->zs[r], nyl_r = c->ys[r + 1] - c->ys[r];
+  const long long nzl_r = c->zs[r + 1] - c->zs[r];
   std::vector<R2Row<T>> yf(ny), yb(ny);
-  for (int s = 0; s < P; ++s) {
-    const long long nyl_s = c->ys[s + 1] - c->ys[s];
+  T* XB_r = (T*)((char*)c->region + c->off_XB);
+  for (int j = 0; j < ny; ++j) {
+    const int pj = packed ? pack_index(j, ny) : j;   // position that decides the owner and the local row
+    int s = 0;
+    while (pj >= c->ys[s + 1]) ++s;
+    const long long nyl_s = c->ys[s + 1] - c->ys[s], jl = pj - c->ys[s];
     T* C_s = (T*)((char*)c->peer[s] + c->off_C);        // C sits at the same offset in every rank's region
-    T* XB_r = (T*)((char*)c->region + c->off_XB);
-    for (int j = c->ys[s]; j < c->ys[s + 1]; ++j) {
-      // forward y output row j of my plane g: z pencil of rank s, plane zs[r] + g, row j - ys[s]
-      yf[j].ptr = C_s + ((long long)c->zs[r] * nyl_s + (j - c->ys[s])) * nx;
-      yf[j].gs = nyl_s * nx;
-      // backward y input row j of my plane g: block s of my way-back buffer [s][j - ys[s]][g][i]
-      yb[j].ptr = XB_r + (nzl_r * c->ys[s] + (long long)(j - c->ys[s]) * nzl_r) * nx;
-      yb[j].gs = nx;
-    }
+    // forward y output row j of my plane g: z pencil of rank s, plane zs[r] + g, row jl
+    yf[j].ptr = C_s + ((long long)c->zs[r] * nyl_s + jl) * nx;
+    yf[j].gs = nyl_s * nx;
+    // backward y input row j of my plane g: block s of my way-back buffer [s][jl][g][i]
+    yb[j].ptr = XB_r + (nzl_r * c->ys[s] + jl * nzl_r) * nx;
+    yb[j].gs = nx;
   }
+  DevBuf& tf = packed ? c->ytab_fwd_pk : c->ytab_fwd;
+  DevBuf& tb = packed ? c->ytab_bwd_pk : c->ytab_bwd;
+  if (tf.ensure(sizeof(R2Row<T>) * ny) || tb.ensure(sizeof(R2Row<T>) * ny)) return fail(CANSB200_ENOMEM, "dist_connect: tables");
+  CK(cudaMemcpy(tf.p, yf.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(tb.p, yb.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
+  if (packed) { c->tabs_pk = true; return 0; }
   std::vector<OutRow<T>> zt(nz);
   for (int s = 0; s < P; ++s) {
     const long long nzl_s = c->zs[s + 1] - c->zs[s];
@@ -758,11 +791,7 @@ template <class T> static int build_dist_tables(cansb200_ctx* c) {
       zt[k].sj = nzl_s * nx;
     }
   }
-  (void)nyl_r;
-  if (c->ytab_fwd.ensure(sizeof(R2Row<T>) * ny) || c->ytab_bwd.ensure(sizeof(R2Row<T>) * ny) || c->ztab.ensure(sizeof(OutRow<T>) * nz))
-    return fail(CANSB200_ENOMEM, "dist_connect: tables");
-  CK(cudaMemcpy(c->ytab_fwd.p, yf.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->ytab_bwd.p, yb.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
+  if (c->ztab.ensure(sizeof(OutRow<T>) * nz)) return fail(CANSB200_ENOMEM, "dist_connect: tables");
   CK(cudaMemcpy(c->ztab.p, zt.data(), sizeof(OutRow<T>) * nz, cudaMemcpyHostToDevice));
   return 0;
 }
@@ -784,7 +813,9 @@ int cansb200_dist_connect(cansb200_ctx* c, const void* blobs) {
     CK(cudaIpcOpenMemHandle(&q, b[s].handle, cudaIpcMemLazyEnablePeerAccess));
     c->peer[s] = q;
   }
-  const int rc = c->is_fp32 ? build_dist_tables<float>(c) : build_dist_tables<double>(c);
+  int rc = c->is_fp32 ? build_dist_tables<float>(c, false) : build_dist_tables<double>(c, false);
+  if (rc) return rc;
+  rc = c->is_fp32 ? build_dist_tables<float>(c, true) : build_dist_tables<double>(c, true);
   if (rc) return rc;
   c->connected = true;
   return 0;
@@ -810,7 +841,9 @@ int cansb200_dist_connect_local(cansb200_ctx* const* ctxs, int n) {
       c->peer[s] = ctxs[s]->region;
     }
     c->local_peers = true;
-    const int rc = c->is_fp32 ? build_dist_tables<float>(c) : build_dist_tables<double>(c);
+    int rc = c->is_fp32 ? build_dist_tables<float>(c, false) : build_dist_tables<double>(c, false);
+    if (rc) return rc;
+    rc = c->is_fp32 ? build_dist_tables<float>(c, true) : build_dist_tables<double>(c, true);
     if (rc) return rc;
     c->connected = true;
   }
@@ -833,11 +866,15 @@ int cansb200_finalize(cansb200_ctx* c) {
   if (c->region) cudaFree(c->region);
   if (c->dist_status) cudaFreeHost(c->dist_status);
   if (c->dist_status_dev) cudaFree(c->dist_status_dev);
+  c->sendb.release(); c->ytab_fwd_loc.release(); c->ytab_fwd_loc_pk.release(); c->ztab_loc.release();
+  for (cudaStream_t q : c->dist_cs) if (q) cudaStreamDestroy(q);
   if (c->dist_sT) cudaStreamDestroy(c->dist_sT);
   if (c->dist_sB) cudaStreamDestroy(c->dist_sB);
   for (cudaEvent_t q : c->dist_ev) cudaEventDestroy(q);
   for (cudaEvent_t q : c->prof_events) cudaEventDestroy(q);
-  c->ytab_fwd.release(); c->ytab_bwd.release(); c->ztab.release();
+  c->ytab_fwd.release(); c->ytab_bwd.release(); c->ztab.release(); c->ytab_fwd_pk.release(); c->ytab_bwd_pk.release();
+  c->lam_perm.release();
+  { auto zp = c->zplans; c->zplans.clear(); for (auto& kv : zp) cansb200_plan_destroy(kv.second); }
   for (cudaStream_t q : c->aux) cudaStreamDestroy(q);
   for (cudaEvent_t q : c->aux_done) cudaEventDestroy(q);
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
@@ -885,6 +922,16 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
   if (what == CANSB200_CTX_DIST_WINDOWS) {
     if (value < -1 || value == 0 || value > CB_MAX_WINDOWS) return fail(CANSB200_EINVAL, "ctx_set: dist_windows must be -1 (auto) or 1..8");
     c->dist_windows = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_DIST_MODE) {
+    if (value < -1 || value > 1) return fail(CANSB200_EINVAL, "ctx_set: dist_mode must be -1 (auto), 0 (peer stores) or 1 (copy engines)");
+    c->dist_mode = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_DIST_CHUNKS) {
+    if (value < -1 || value == 0 || value > CB_MAX_WINDOWS) return fail(CANSB200_EINVAL, "ctx_set: dist_chunks must be -1 (auto) or 1..8");
+    c->dist_chunks = value;
     return 0;
   }
   if (what == CANSB200_CTX_DIST_THOMAS_CTAS) {
@@ -1025,6 +1072,11 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
 
 int cansb200_plan_destroy(cansb200_plan* pl) {
   if (!pl) return 0;
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (auto& q : g_plan_ids)
+      if (q == pl) q = nullptr;
+  }
   pl->ctx->nplans--;
   pl->zcache.release(); pl->p2cache.release(); pl->dencache.release(); pl->state.release();
   pl->dtdma_big.release(); pl->dtdma_small.release();
@@ -1073,11 +1125,12 @@ int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
 
 // ---------------------------------------------------------------------------
 // device-side flags over the ranks of the box, stream ordered (dist_kernels.cuh): announce and / or wait for slot `slot`
-static int dist_flag(cansb200_ctx* c, int slot, unsigned long long seq, bool signal, bool wait, cudaStream_t st) {
+static int dist_flag(cansb200_ctx* c, int slot, unsigned long long seq, bool signal, bool wait, cudaStream_t st, int target = -1,
+                     bool skip_self = false) {
   DistPeers pp;
   for (int s = 0; s < CB_MAX_RANKS; ++s) pp.flags[s] = s < c->nranks ? (unsigned long long*)c->peer[s] : nullptr;
   dist_flag_kernel<<<1, 32, 0, st>>>(pp, c->rank, c->nranks, slot, seq, signal ? 1 : 0, wait ? 1 : 0, c->dist_status,
-                                     c->dist_status_dev, 20ULL * 1000000000ULL);
+                                     c->dist_status_dev, 20ULL * 1000000000ULL, target, skip_self ? 1 : 0);
   c->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1100,8 +1153,10 @@ static int dist_check(cansb200_ctx* c, const char* who) {
 // that read the local field) overlap instead of alternating.
 template <class T>
 static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, const T* lam, const T* a, const T* b,
-                      const T* c, cudaStream_t st) {
+                      const T* c, bool y_packed, cudaStream_t st) {
   cansb200_ctx* ctx = pl->ctx;
+  const void* ytab_fwd = y_packed ? ctx->ytab_fwd_pk.p : ctx->ytab_fwd.p;
+  const void* ytab_bwd = y_packed ? ctx->ytab_bwd_pk.p : ctx->ytab_bwd.p;
   const unsigned long long seq = ++ctx->seq;   // first: every rank counts every collective call, whatever happens next
   int rc = dist_check(ctx, "solve");
   if (rc) return rc;
@@ -1156,7 +1211,7 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     const int xb = w * ww;
     // ---- stage F: forward y transform of the window; rows go straight to the z pencils of their owners
     R2RGeom gyf{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, ww, nzl, ny, 1};
-    gyf.row_tab = ctx->ytab_fwd.p;
+    gyf.row_tab = ytab_fwd;
     gyf.x0 = xb;
     rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + xb, A + xb, gyf, pl->opt.fft_y_lines, sF);
     if (rc) return rc;
@@ -1209,7 +1264,7 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     if (W == 1) prof_mark(ctx, st);
     // ---- stage B: backward y transform of the window; gathers its rows from the way-back buffer
     R2RGeom gyb{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, ww, nzl, ny, 1};
-    gyb.row_tab = ctx->ytab_bwd.p;
+    gyb.row_tab = ytab_bwd;
     gyb.x0 = xb;
     rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], XB, A + xb, gyb, pl->opt.fft_y_lines, sB);
     if (rc) return rc;
@@ -1218,6 +1273,209 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     CK(cudaEventRecord(ctx->dist_ev[2 * CB_MAX_WINDOWS], sB));
     CK(cudaStreamWaitEvent(st, ctx->dist_ev[2 * CB_MAX_WINDOWS], 0));
   }
+  prof_mark(ctx, st);
+  R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nzl, nx, 0};
+  rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
+  if (rc) return rc;
+  prof_mark(ctx, st);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Copy-engine flavour of the exchange (CANSB200_CTX_DIST_MODE = 1).
+//
+// Measured on this box (profiles/r2a_nvlink_store_patterns.txt): SM stores fill NVLink to ~690 GB/s per direction in any
+// pattern, but only with ~300 resident CTAs -- a producing kernel that stores to its peers holds the whole GPU while the
+// link drains, so the HBM-only stages (x transforms, backward y transform) cannot overlap it.  A copy-engine transfer
+// moves 700-760 GB/s (dense blocks, or 2-D blocks with >= 2 KB rows) with no SM involved.  So here the producers write
+// dense per-destination blocks into LOCAL send buffers (same kernels, the row tables simply point at local memory; the
+// block for this rank itself goes straight to its final place) and one copy stream per peer moves them:
+//   forward  : z chunks.  x transform + y transform of chunk c + 1 run while chunk c is on the wire; a chunk's block for
+//              peer s is contiguous on both sides ([plane][row][x]).
+//   backward : x windows.  Tridiagonal solve of window w + 1, transfer of window w (2-D copy, rows of window width) and
+//              backward y transform of window w - 1 run concurrently.
+// Every transfer is announced to its receiver by a flag written on the copy stream behind it.
+template <class T> static int build_dma_tables(cansb200_ctx* c) {
+  const int P = c->nranks, r = c->rank;
+  const long long nx = c->ng[0];
+  const int ny = c->ng[1], nz = c->ng[2];
+  const long long nzl_r = c->zs[r + 1] - c->zs[r], nyl_r = c->ys[r + 1] - c->ys[r];
+  if (c->scratch2.ensure((size_t)nx * ny * nzl_r * sizeof(T)) || c->sendb.ensure((size_t)nx * nyl_r * nz * sizeof(T)))
+    return fail(CANSB200_ENOMEM, "solve: send buffers of the copy-engine exchange");
+  T* SF = (T*)c->scratch2.p;
+  T* SB = (T*)c->sendb.p;
+  T* C_r = (T*)((char*)c->region + c->off_C);
+  T* XB_r = (T*)((char*)c->region + c->off_XB);
+  for (int packed = 0; packed < 2; ++packed) {
+    std::vector<R2Row<T>> yf(ny);
+    for (int j = 0; j < ny; ++j) {
+      const int pj = packed ? pack_index(j, ny) : j;
+      int s = 0;
+      while (pj >= c->ys[s + 1]) ++s;
+      const long long nyl_s = c->ys[s + 1] - c->ys[s], jl = pj - c->ys[s];
+      // forward y output row j of my plane g: block s of the send buffer, [g][jl][i]; my own block goes home directly
+      yf[j].ptr = s == r ? C_r + ((long long)c->zs[r] * nyl_s + jl) * nx : SF + nx * nzl_r * c->ys[s] + jl * nx;
+      yf[j].gs = nyl_s * nx;
+    }
+    DevBuf& tf = packed ? c->ytab_fwd_loc_pk : c->ytab_fwd_loc;
+    if (tf.ensure(sizeof(R2Row<T>) * ny)) return fail(CANSB200_ENOMEM, "solve: tables");
+    CK(cudaMemcpy(tf.p, yf.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
+  }
+  std::vector<OutRow<T>> zt(nz);
+  for (int s = 0; s < P; ++s) {
+    const long long nzl_s = c->zs[s + 1] - c->zs[s];
+    for (int k = c->zs[s]; k < c->zs[s + 1]; ++k) {   // result row k of my columns: block s of the send buffer, [jl][k - zs[s]][i]
+      zt[k].ptr = s == r ? XB_r + nzl_r * c->ys[r] * nx + (long long)(k - c->zs[s]) * nx
+                         : SB + nx * nyl_r * c->zs[s] + (long long)(k - c->zs[s]) * nx;
+      zt[k].sj = nzl_s * nx;
+    }
+  }
+  if (c->ztab_loc.ensure(sizeof(OutRow<T>) * nz)) return fail(CANSB200_ENOMEM, "solve: tables");
+  CK(cudaMemcpy(c->ztab_loc.p, zt.data(), sizeof(OutRow<T>) * nz, cudaMemcpyHostToDevice));
+  int lo = 0, hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  c->dist_cs.assign(P, nullptr);
+  for (int s = 0; s < P; ++s)
+    if (s != r) CK(cudaStreamCreateWithPriority(&c->dist_cs[s], cudaStreamNonBlocking, hi));
+  return 0;
+}
+
+template <class T>
+static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normfft, const T* lam, const T* a, const T* b,
+                          const T* c, bool y_packed, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  const unsigned long long seq = ++ctx->seq;
+  int rc = dist_check(ctx, "solve");
+  if (rc) return rc;
+  const int P = ctx->nranks, r = ctx->rank;
+  const int nx = n[0], ny = n[1], nzl = n[2];
+  const int nyl = ctx->n_z[1], nz = ctx->ng[2];
+  const long long px = nx + 2, py = ny + 2;
+  if (pl->th_n != nz - pl->q) return fail(CANSB200_EINVAL, "solve: plan / grid mismatch");
+  if (ctx->dist_cs.empty()) {
+    rc = build_dma_tables<T>(ctx);
+    if (rc) return rc;
+  }
+  T* A = (T*)ctx->scratch.p;
+  T* SF = (T*)ctx->scratch2.p;
+  T* SB = (T*)ctx->sendb.p;
+  T* Cz = (T*)((char*)ctx->region + ctx->off_C);
+  T* XB = (T*)((char*)ctx->region + ctx->off_XB);
+  T* pin = p + (px * py + px + 1);
+  const void* ytab_fwd = y_packed ? ctx->ytab_fwd_loc_pk.p : ctx->ytab_fwd_loc.p;
+  const void* ytab_bwd = y_packed ? ctx->ytab_bwd_pk.p : ctx->ytab_bwd.p;
+  const int wide = (int)(128 / sizeof(T));
+  // z chunks of the forward half, x windows of the backward half
+  int Cn = ctx->profiling ? 1 : (ctx->dist_chunks > 0 ? ctx->dist_chunks : 4);
+  if (Cn > nzl) Cn = nzl;
+  int W = 1;
+  if (!ctx->profiling) {
+    const int want = ctx->dist_windows > 0 ? ctx->dist_windows : 4;
+    for (W = want < CB_MAX_WINDOWS ? want : CB_MAX_WINDOWS; W > 1; --W)
+      if (nx % (W * wide) == 0) break;
+  }
+  if (!thomas_is_pipelined(pl)) W = 1;   // the sequential kernel has no column windows
+  if (!ctx->dist_sT) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ctx->dist_sT, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&ctx->dist_sB, cudaStreamNonBlocking, hi));
+  }
+  while ((int)ctx->dist_ev.size() < 2 * CB_MAX_WINDOWS + 1) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->dist_ev.push_back(e);
+  }
+  cudaStream_t sT = ctx->dist_sT, sB = ctx->dist_sB;
+  const size_t esz = sizeof(T);
+  prof_mark(ctx, st);
+  ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam, a, b, c);
+  D.out_rows = (const OutRow<T>*)ctx->ztab_loc.p;
+  rc = gaussel_prepare<T>(pl, D, st);   // pivot-cache lookup (factorisation on a miss) ahead of everything
+  if (rc) return rc;
+  // ---- forward half: x transform, y transform into the send blocks, one transfer per peer and chunk
+  for (int q = 0; q < Cn; ++q) {
+    const int g0 = (int)((long long)nzl * q / Cn), g1 = (int)((long long)nzl * (q + 1) / Cn), ng_ = g1 - g0;
+    if (ng_ < 1) continue;
+    R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, ng_, nx, 0};
+    rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin + (long long)g0 * px * py, A + (long long)g0 * nx * ny, gx, pl->opt.fft_x_lines, st);
+    if (rc) return rc;
+    if (Cn == 1) prof_mark(ctx, st);
+    R2RGeom gyf{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, ng_, ny, 1};
+    gyf.row_tab = ytab_fwd;
+    gyf.g0 = g0;
+    rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + (long long)g0 * nx * ny, A + (long long)g0 * nx * ny, gyf, pl->opt.fft_y_lines, st);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->dist_ev[q], st));
+    for (int d = 1; d < P; ++d) {
+      const int s = (r + d) % P;   // every rank starts with a different peer
+      const long long nyl_s = ctx->ys[s + 1] - ctx->ys[s];
+      T* dst = (T*)((char*)ctx->peer[s] + ctx->off_C) + ((long long)(ctx->zs[r] + g0) * nyl_s) * nx;
+      const T* src = SF + (long long)nx * nzl * ctx->ys[s] + (long long)g0 * nyl_s * nx;
+      CK(cudaStreamWaitEvent(ctx->dist_cs[s], ctx->dist_ev[q], 0));
+      CK(cudaMemcpyAsync(dst, src, (size_t)ng_ * nyl_s * nx * esz, cudaMemcpyDeviceToDevice, ctx->dist_cs[s]));
+    }
+  }
+  for (int d = 1; d < P; ++d) {
+    const int s = (r + d) % P;
+    rc = dist_flag(ctx, CB_SLOT_FWD, seq, true, false, ctx->dist_cs[s], s);   // "my block has landed on your z pencil"
+    if (rc) return rc;
+  }
+  CK(cudaStreamWaitEvent(sT, ctx->dist_ev[Cn - 1], 0));   // my own block is written by my own kernels
+  rc = dist_flag(ctx, CB_SLOT_FWD, seq, false, true, sT, -1, true);
+  if (rc) return rc;
+  prof_mark(ctx, sT);
+  prof_mark(ctx, sT);
+  // ---- backward half: tridiagonal solve of an x window into the send blocks, 2-D transfers, backward y transform
+  const int ww = nx / W;
+  const bool pipelined = thomas_is_pipelined(pl);
+  for (int w = 0; w < W; ++w) {
+    const int xb = w * ww;
+    if (pipelined) {
+      D.xb = xb; D.xn = ww;
+      rc = gaussel_apply<T>(pl, D, Cz, (T)normfft, sT);
+      if (rc) return rc;
+      if (pl->th_n < nz) {
+        scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, sT>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, pl->th_n, nz, nyl, nx, xb, ww);
+        ctx->launches++;
+      }
+    } else {
+      ThomasDev<T> D2 = D;
+      D2.out_rows = nullptr;
+      rc = gaussel_apply<T>(pl, D2, Cz, (T)normfft, sT);
+      if (rc) return rc;
+      scatter_rows_kernel<T><<<ctx->num_sms * 4, 256, 0, sT>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, 0, nz, nyl, nx, 0, nx);
+      ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->dist_ev[CB_MAX_WINDOWS + w], sT));
+    for (int d = 1; d < P; ++d) {
+      const int s = (r + d) % P;
+      const long long nzl_s = ctx->zs[s + 1] - ctx->zs[s];
+      T* dst = (T*)((char*)ctx->peer[s] + ctx->peer_off_XB[s]) + nzl_s * ctx->ys[r] * nx + xb;
+      const T* src = SB + (long long)nx * nyl * ctx->zs[s] + xb;
+      CK(cudaStreamWaitEvent(ctx->dist_cs[s], ctx->dist_ev[CB_MAX_WINDOWS + w], 0));
+      if (W == 1)
+        CK(cudaMemcpyAsync(dst, src, (size_t)nyl * nzl_s * nx * esz, cudaMemcpyDeviceToDevice, ctx->dist_cs[s]));
+      else
+        CK(cudaMemcpy2DAsync(dst, (size_t)nx * esz, src, (size_t)nx * esz, (size_t)ww * esz, (size_t)nyl * nzl_s, cudaMemcpyDeviceToDevice,
+                             ctx->dist_cs[s]));
+      rc = dist_flag(ctx, CB_SLOT_BWD + w, seq, true, false, ctx->dist_cs[s], s);
+      if (rc) return rc;
+    }
+    CK(cudaStreamWaitEvent(sB, ctx->dist_ev[CB_MAX_WINDOWS + w], 0));
+    rc = dist_flag(ctx, CB_SLOT_BWD + w, seq, false, true, sB, -1, true);
+    if (rc) return rc;
+    if (W == 1) prof_mark(ctx, sB);
+    R2RGeom gyb{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, ww, nzl, ny, 1};
+    gyb.row_tab = ytab_bwd;
+    gyb.x0 = xb;
+    rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], XB, A + xb, gyb, pl->opt.fft_y_lines, sB);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(ctx->dist_ev[2 * CB_MAX_WINDOWS], sB));
+  CK(cudaStreamWaitEvent(st, ctx->dist_ev[2 * CB_MAX_WINDOWS], 0));
+  // the copy streams must not run into the next solve's events before this one is over
   prof_mark(ctx, st);
   R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nzl, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
@@ -1314,6 +1572,7 @@ template <class T>
 static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double normfft, const void* lam_any, const void* a_any,
                       const void* b_any, const void* c_any, int mem_kind, cudaStream_t st) {
   cansb200_ctx* ctx = pl->ctx;
+  NvtxRange nvtx_solve("cansb200_solve");
   const int nx = n[0], ny = n[1], nz = n[2];
   const long long px = nx + 2, py = ny + 2;          // haloed pitches
   const size_t nh = (size_t)px * py * (nz + 2);
@@ -1347,6 +1606,22 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
     CK(cudaMemcpyAsync(cf + 3 * nzg, lam_any, nlam * sizeof(T), cudaMemcpyHostToDevice, st));
     p = (T*)ctx->staging.p;
     a = cf; b = cf + nzg; c = cf + 2 * nzg; lam = cf + 3 * nzg;
+  }
+  // eigenvalues in the order of an _OPENACC-built initsolver (option lambda_order = 1): bring them to halfcomplex order.
+  // Several ranks: x only -- the y rows are dealt out in packed order instead (build_dist_tables), so that the local
+  // slice of lambdaxy means what it means in the reference.
+  const bool pk = pl->opt.lambda_order == 1;
+  const bool pkx = pk && pl->bc[0] == 'P', pky = pk && pl->bc[2] == 'P';
+  const bool pky_local = pky && (ctx->nranks == 1 || ctx->dtdma);
+  if (pkx || pky_local) {
+    const int lx = ctx->n_z[0], ly = ctx->n_z[1];
+    if (ctx->lam_perm.ensure((size_t)lx * ly * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: eigenvalue buffer");
+    const long long tot = (long long)lx * ly;
+    lambda_unpack_kernel<T><<<(unsigned)((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184), 256, 0, st>>>(lam, (T*)ctx->lam_perm.p, lx, ly,
+                                                                                                          pkx ? 1 : 0, pky_local ? 1 : 0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    lam = (const T*)ctx->lam_perm.p;
   }
   if (chunked) {
     const int nch = ctx->host_chunks < nz ? ctx->host_chunks : nz;
@@ -1404,7 +1679,8 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   }
   if (ctx->nranks > 1) {
     const int rcd = ctx->dtdma ? solve_dist_dtdma<T>(pl, p, n, normfft, lam, a, b, c, st)
-                               : solve_dist<T>(pl, p, n, normfft, lam, a, b, c, st);
+                               : (ctx->dist_mode == 1 ? solve_dist_dma<T>(pl, p, n, normfft, lam, a, b, c, pky, st)
+                                                      : solve_dist<T>(pl, p, n, normfft, lam, a, b, c, pky, st));
     if (rcd) return rcd;
     if (mem_kind == CANSB200_MEM_HOST) {
       CK(cudaMemcpyAsync(p_any, ctx->staging.p, nh * sizeof(T), cudaMemcpyDeviceToHost, st));
@@ -1659,6 +1935,66 @@ int cansb200_solve_z(cansb200_plan* pl, void* p, const int n[3], int nhalo, doub
   cudaStream_t st = (cudaStream_t)stream;
   return ctx->is_fp32 ? solve_z_impl<float>(pl, p, n, norm, a, b, c, mem_kind, st)
                       : solve_z_impl<double>(pl, p, n, norm, a, b, c, mem_kind, st);
+}
+
+int cansb200_plan_id(cansb200_plan* pl) {
+  if (!pl) return 0;
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  for (size_t i = 0; i < g_plan_ids.size(); ++i)
+    if (g_plan_ids[i] == pl) return (int)i + 1;
+  for (size_t i = 0; i < g_plan_ids.size(); ++i)
+    if (!g_plan_ids[i]) { g_plan_ids[i] = pl; return (int)i + 1; }
+  g_plan_ids.push_back(pl);
+  return (int)g_plan_ids.size();
+}
+
+cansb200_plan* cansb200_plan_from_id(int id) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  if (id < 1 || id > (int)g_plan_ids.size()) return nullptr;
+  return g_plan_ids[id - 1];
+}
+
+int cansb200_solve_z_bc(cansb200_ctx* ctx, const char bcz[2], char c_or_f_z, void* p, const int n[3], int nhalo, double norm,
+                        const void* a, const void* b, const void* c, int mem_kind, void* stream) {
+  if (!ctx || !bcz) return fail(CANSB200_EINVAL, "solve_z_bc: null argument");
+  const std::string key{bcz[0], bcz[1], c_or_f_z};
+  auto it = ctx->zplans.find(key);
+  if (it == ctx->zplans.end()) {
+    const char bc6[6] = {'P', 'P', 'P', 'P', bcz[0], bcz[1]};   // x / y kinds are never used by the z-only solve
+    const char cf3[3] = {'c', 'c', c_or_f_z};
+    cansb200_plan* pl = nullptr;
+    const int rc = cansb200_plan_create(ctx, &pl, bc6, cf3, nullptr, nullptr);
+    if (rc) return rc;
+    it = ctx->zplans.emplace(key, pl).first;
+  }
+  return cansb200_solve_z(it->second, p, n, nhalo, norm, a, b, c, mem_kind, stream);
+}
+
+int cansb200_updt_rhs_b(cansb200_ctx* ctx, const char cf[3], const char bc[6], const int n[3], const int is_bound[6],
+                        const int have[3], const double rhsb[6], double norm, void* p, void* stream) {
+  if (!ctx || !cf || !bc || !n || !is_bound || !have || !rhsb || !p) return fail(CANSB200_EINVAL, "updt_rhs_b: null argument");
+  RhsbPlanes B;
+  for (int d = 0; d < 3; ++d) {
+    const int q = (cf[d] == 'f' && bc[2 * d + 1] == 'D') ? 1 : 0;   // src/bound.f90:528-530
+    for (int sd = 0; sd < 2; ++sd) {
+      const bool on = have[d] && is_bound[2 * d + sd];
+      B.idx[d][sd] = on ? (sd == 0 ? 1 : n[d] - q) : 0;
+      // value * norm in the working precision, as `rhsbx(j,k,0)*norm` is evaluated
+      B.val[d][sd] = ctx->is_fp32 ? (double)((float)rhsb[2 * d + sd] * (float)norm) : rhsb[2 * d + sd] * norm;
+      if (on && B.idx[d][sd] < 1) return fail(CANSB200_EINVAL, "updt_rhs_b: empty direction");
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int d = 0; d < 3; ++d) {
+    if (!B.idx[d][0] && !B.idx[d][1]) continue;
+    const long long face = d == 0 ? (long long)n[1] * n[2] : (d == 1 ? (long long)n[0] * n[2] : (long long)n[0] * n[1]);
+    const unsigned blocks = (unsigned)((face + 255) / 256 < 1184 ? (face + 255) / 256 : 1184);
+    if (ctx->is_fp32) updt_rhs_b_kernel<float><<<blocks, 256, 0, st>>>((float*)p, n[0], n[1], n[2], B, d);
+    else updt_rhs_b_kernel<double><<<blocks, 256, 0, st>>>((double*)p, n[0], n[1], n[2], B, d);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
 }
 
 int cansb200_solve(cansb200_plan* pl, void* p, const int n[3], int nhalo, double normfft, const void* lambdaxy,

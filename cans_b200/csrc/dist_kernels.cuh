@@ -48,15 +48,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // every rank has announced the same.  A rank that never shows up trips the timeout instead of hanging the GPU;
 // `status` is a host-mapped word the library checks before the next solve (CANSB200_ECOMM), `status_dev` its
 // device-resident twin (what later waits look at).
+// `target` >= 0: signal that one rank only (the copy-engine exchange announces every transfer to its receiver);
+// `skip_self`: the wait leaves out this rank's own word (nobody announces a transfer to itself).
 __global__ void dist_flag_kernel(DistPeers peers, int rank, int nranks, int slot, unsigned long long seq, int do_signal,
-                                 int do_wait, volatile int* status, volatile int* status_dev, unsigned long long timeout_ns) {
+                                 int do_wait, volatile int* status, volatile int* status_dev, unsigned long long timeout_ns,
+                                 int target, int skip_self) {
   const int s = threadIdx.x;
   if (s >= nranks) return;
-  if (do_signal) {
+  if (do_signal && (target < 0 || target == s)) {
     __threadfence_system();
     st_release_sys(peers.flags[s] + slot * CB_MAX_RANKS + rank, seq);
   }
-  if (!do_wait || *status_dev) return;   // after one time-out the solve is lost anyway: later waits do not add 20 s each
+  if (!do_wait || *status_dev || (skip_self && s == rank)) return;   // after one time-out the solve is lost anyway: later waits do not add 20 s each
   const unsigned long long* mine = peers.flags[rank] + slot * CB_MAX_RANKS + s;
   const unsigned long long t0 = global_timer_ns();
   while (ld_acquire_sys(mine) < seq) {

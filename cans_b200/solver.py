@@ -59,6 +59,9 @@ def _stream_ptr(stream=None) -> int:
     return 0
 
 
+_current_ctx = None   # the most recently created context: what the Fortran shim keeps as a module variable
+
+
 class Context:
     """cansb200_ctx: replaces initmpi's decomposition setup + workspaces.  One rank: dims = [1, 1];
     several ranks (one per GPU of a box): dims = [1, nranks], z slabs, followed by `connect()`."""
@@ -77,6 +80,15 @@ class Context:
         n, lo, nz, loz = i3([0] * 3), i3([0] * 3), i3([0] * 3), i3([0] * 3)
         check(lib.cansb200_get_extents(self._h, n, lo, nz, loz), "get_extents")
         self.n, self.lo, self.n_z, self.lo_z = list(n), list(lo), list(nz), list(loz)
+        global _current_ctx
+        _current_ctx = self
+
+    def get_work(self, which: int):
+        """-> (device pointer, number of elements) of the buffer an OpenACC host aliases as `work` (0), `solver_buf_0` (1),
+        `solver_buf_1` (2) (src/rk.f90:27-29)."""
+        ptr, nel = C.c_void_p(), C.c_size_t()
+        check(lib.cansb200_get_work(self._h, int(which), C.byref(ptr), C.byref(nel)), "get_work")
+        return ptr.value, nel.value
 
     def connect(self, group=None):
         """Rendezvous of the ranks of one box: gather every rank's IPC blob (torch.distributed plays the role
@@ -115,6 +127,12 @@ class Context:
         tridiagonal kernel may take while it shares the GPU with the y transforms."""
         check(lib.cansb200_ctx_set(self._h, 10, int(windows)), "ctx_set")
         check(lib.cansb200_ctx_set(self._h, 11, int(thomas_ctas)), "ctx_set")
+
+    def set_dist_mode(self, mode: int = -1, chunks: int = -1):
+        """Several ranks: 0 = the producing kernels store straight into the peers' buffers, 1 = dense local send blocks moved
+        by the copy engines (z chunks forward, x windows back), -1 = auto."""
+        check(lib.cansb200_ctx_set(self._h, 12, int(mode)), "ctx_set")
+        check(lib.cansb200_ctx_set(self._h, 13, int(chunks)), "ctx_set")
 
     def dist_status(self) -> int:
         st = C.c_int()
@@ -207,6 +225,15 @@ class Plan:
     def handle(self):
         return self._h
 
+    @property
+    def id(self) -> int:
+        """integer name of the plan: what arrplan(1,1) holds on the reference's CUDA build (`integer, dimension(2,2)`)"""
+        return int(lib.cansb200_plan_id(self._h))
+
+    @staticmethod
+    def handle_from_id(i: int):
+        return lib.cansb200_plan_from_id(int(i))
+
     def stats(self):
         s = (C.c_ulonglong * 4)()
         check(lib.cansb200_plan_stats(self._h, s), "plan_stats")
@@ -227,8 +254,10 @@ class Plan:
 # ---------------------------------------------------------------------------
 # initsolver and its pieces (host arithmetic, as in the reference)
 # ---------------------------------------------------------------------------
-def eigenvalues(n, bc, c_or_f, dtype=np.float64):
-    """src/initsolver.f90:85-144, CPU-build (halfcomplex) ordering for 'PP'."""
+def eigenvalues(n, bc, c_or_f, dtype=np.float64, openacc_order=False):
+    """src/initsolver.f90:85-144.  `openacc_order`: the `#if defined(_OPENACC)` permutation of a periodic direction
+    (:98-117, `iswap`): (r0, r[n/2], r1, i1, ...) instead of the CPU build's halfcomplex order; a plan created with
+    `lambda_order=1` takes lambdaxy in that order."""
     pi = np.arccos(dtype(-1.0))
     l = np.arange(1, n + 1)
     key = bc[0] + bc[1]
@@ -244,6 +273,18 @@ def eigenvalues(n, bc, c_or_f, dtype=np.float64):
     lam = (-two * (one - np.cos(th))).astype(dtype)
     if key == "DD" and c_or_f == "f":
         lam[n - 1] = 0.0
+    if key == "PP" and openacc_order:
+        nh = (n + 1) // 2
+        iswap = np.zeros(n + 1, dtype=np.int64)   # 1-based, exactly the reference's loop
+        iswap[1] = 1
+        if n >= 2:
+            iswap[2] = nh + (1 - n % 2)
+        for ll in range(2, n):
+            if ll <= nh:
+                iswap[2 * ll - 1] = ll
+            else:
+                iswap[n - 2 * (ll - (nh + 1)) - n % 2] = ll + 1
+        lam = lam[iswap[1:] - 1]
     return lam
 
 
@@ -316,15 +357,18 @@ class SolverData:
     host: dict = field(default_factory=dict)
 
 
-def initsolver(ctx: Context, ng, dli, dzci_g, dzfi_g, cbc, bc, c_or_f, device=None, **options) -> SolverData:
+def initsolver(ctx: Context, ng, dli, dzci_g, dzfi_g, cbc, bc, c_or_f, device=None, openacc_order=False, **options) -> SolverData:
     """src/initsolver.f90:15-83.  Returns lambdaxy[j,i], a, b, c (on `device` if given, else numpy),
-    arrplan, normfft and the boundary RHS values."""
+    arrplan, normfft and the boundary RHS values.  `openacc_order`: behave like the _OPENACC build of initsolver
+    (packed eigenvalue order in periodic directions) and create the plan with `lambda_order=1`."""
     dt = ctx.dtype
+    if openacc_order:
+        options["lambda_order"] = 1
     dli = [dt(v) for v in dli]
     dzci_g = np.asarray(dzci_g, dtype=dt)
     dzfi_g = np.asarray(dzfi_g, dtype=dt)
-    lx = eigenvalues(ng[0], cbc[0], c_or_f[0], dt) * dli[0] ** 2
-    ly = eigenvalues(ng[1], cbc[1], c_or_f[1], dt) * dli[1] ** 2
+    lx = eigenvalues(ng[0], cbc[0], c_or_f[0], dt, openacc_order) * dli[0] ** 2
+    ly = eigenvalues(ng[1], cbc[1], c_or_f[1], dt, openacc_order) * dli[1] ** 2
     # lambdaxy(lo_z(1):hi_z(1), lo_z(2):hi_z(2)): the z-pencil slice of this rank (src/initsolver.f90:54-58)
     y0 = ctx.lo_z[1] - 1
     ly = ly[y0:y0 + ctx.n_z[1]]
@@ -371,15 +415,12 @@ def solver(n, ng, arrplan: Plan, normfft, lambdaxy, a, b, c, bc, c_or_f, p, stre
     return p
 
 
-def solver_gaussel_z(n, ng, hi, a, b, c, bcz, c_or_f, norm, p, arrplan: Plan = None, stream=None):
+def solver_gaussel_z(n, ng, hi, a, b, c, bcz, c_or_f, norm, p, arrplan: Plan = None, stream=None, ctx: Context = None):
     """src/solver.f90:547-616 (`solver_gaussel_z`, the implicit-z-diffusion solve of `is_impdiff_1d`):
-    lambda-less tridiagonal solve in z on the interior of the haloed `p`, in place.  Argument order as in the
-    reference; `arrplan` is the plan of the solved variable (it carries the context and the z variant) -- the
-    reference needs none because this path uses no transforms."""
-    if arrplan is None:
-        raise ValueError("solver_gaussel_z: pass the variable's plan (arrplan=...)")
-    if list(bcz) != arrplan.cbc[2] or c_or_f[2] != arrplan.c_or_f[2]:
-        raise ValueError("solver_gaussel_z: bcz / c_or_f(3) differ from the ones the plan was created with")
+    lambda-less tridiagonal solve in z on the interior of the haloed `p`, in place.  The first ten arguments are the
+    reference's (`call solver_gaussel_z(n,ng,hi,a,bb,c,cbc(:,3),c_or_f,alphai,p)`, src/solve_helmholtz.f90:73): no plan
+    is needed -- the context (the most recently created one unless `ctx=` is given, like the module variable of the Fortran
+    shim) keeps one z-only plan per (bcz, c_or_f(3)) (`cansb200_solve_z_bc`).  Passing `arrplan=` uses that plan instead."""
     dev = _is_torch(p) and p.is_cuda
     for name, arr in (("a", a), ("b", b), ("c", c)):
         if (_is_torch(arr) and arr.is_cuda) != dev:
@@ -387,15 +428,36 @@ def solver_gaussel_z(n, ng, hi, a, b, c, bcz, c_or_f, norm, p, arrplan: Plan = N
     want = (n[2] + 2, n[1] + 2, n[0] + 2)
     if tuple(p.shape) != want:
         raise ValueError(f"solver_gaussel_z: p has shape {tuple(p.shape)}, expected {want}")
-    check(lib.cansb200_solve_z(arrplan.handle, _ptr(p), i3(n), 1, float(norm), _ptr(a), _ptr(b), _ptr(c),
-                               MEM_DEVICE if dev else MEM_HOST, _stream_ptr(stream)), "cansb200_solve_z")
+    mk = MEM_DEVICE if dev else MEM_HOST
+    if arrplan is not None:
+        if list(bcz) != arrplan.cbc[2] or c_or_f[2] != arrplan.c_or_f[2]:
+            raise ValueError("solver_gaussel_z: bcz / c_or_f(3) differ from the ones the plan was created with")
+        check(lib.cansb200_solve_z(arrplan.handle, _ptr(p), i3(n), 1, float(norm), _ptr(a), _ptr(b), _ptr(c), mk, _stream_ptr(stream)),
+              "cansb200_solve_z")
+        return p
+    ctx = ctx or _current_ctx
+    if ctx is None:
+        raise ValueError("solver_gaussel_z: no context exists yet")
+    check(lib.cansb200_solve_z_bc(ctx.handle, (bcz[0] + bcz[1]).encode(), c_or_f[2].encode(), _ptr(p), i3(n), 1, float(norm),
+                                  _ptr(a), _ptr(b), _ptr(c), mk, _stream_ptr(stream)), "cansb200_solve_z_bc")
     return p
 
 
-def updt_rhs_b(c_or_f, cbc, n, is_bound, rhsbx, rhsby, rhsbz, p, alpha=None):
+def updt_rhs_b(c_or_f, cbc, n, is_bound, rhsbx, rhsby, rhsbz, p, alpha=None, ctx: Context = None, stream=None):
     """src/bound.f90:514-598: adds the wall contributions to the first / last interior planes of the ranks that own
     the wall (`is_bound[idir][ibound]`, as `Context.is_bound()` returns it)."""
     norm = 1.0 if alpha is None else alpha
+    if _is_torch(p) and p.is_cuda:
+        # device arrays: one CUDA kernel per direction (cansb200_updt_rhs_b), stream ordered like the solve that follows
+        ctx = ctx or _current_ctx
+        rh = [v if v is not None else [0.0, 0.0] for v in (rhsbx, rhsby, rhsbz)]
+        have = (C.c_int * 3)(*[int(v is not None) for v in (rhsbx, rhsby, rhsbz)])
+        isb = (C.c_int * 6)(*[int(bool(is_bound[d][sd])) for d in range(3) for sd in range(2)])
+        vals = (C.c_double * 6)(*[float(rh[d][sd]) for d in range(3) for sd in range(2)])
+        bc6 = "".join(cbc[d][i] for d in range(3) for i in range(2)).encode()
+        check(lib.cansb200_updt_rhs_b(ctx.handle, "".join(c_or_f).encode(), bc6, i3(n), isb, have, vals, float(norm), _ptr(p),
+                                      _stream_ptr(stream)), "cansb200_updt_rhs_b")
+        return
     q = [1 if (c_or_f[d] == "f" and cbc[d][1] == "D") else 0 for d in range(3)]
     n1, n2, n3 = n
     K, J, I = slice(1, n3 + 1), slice(1, n2 + 1), slice(1, n1 + 1)
@@ -420,7 +482,7 @@ def solve_helmholtz(n, ng, hi, arrplan, normfft, alpha, lambdaxy, a, b, c, rhsbx
                     stream=None, is_impdiff_1d=False):
     """src/solve_helmholtz.f90:28-75 (same argument order): p/alpha + lap(p) = rhs.  `is_impdiff_1d` is a module
     parameter in the reference (`mod_param`); here a keyword."""
-    updt_rhs_b(c_or_f, cbc, n, is_bound, rhsbx, rhsby, rhsbz, p, alpha)
+    updt_rhs_b(c_or_f, cbc, n, is_bound, rhsbx, rhsby, rhsbz, p, alpha, ctx=arrplan.ctx if arrplan is not None else None, stream=stream)
     ty = p.dtype.type if isinstance(p, np.ndarray) else (np.float32 if p.dtype == torch.float32 else np.float64)
     alphai = ty(1.0) / ty(alpha)
     bb = b + alphai if not _is_torch(b) else b + float(alphai)

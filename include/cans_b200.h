@@ -50,7 +50,13 @@ typedef struct cansb200_options {
   int fft_x_lines;      /* lines per tile of the contiguous transforms (0 = auto) */
   int fft_y_lines;      /* 8 or 16: x-width of the strided-transform tile (0 = auto) */
   int exchange;         /* reserved (multi-GPU exchange flavour): only the fused peer stores over CUDA IPC exist; the value is ignored */
-  int reserved[11];
+  int lambda_order;     /* order of lambdaxy along a periodic direction: 0 (default) = FFTW halfcomplex (r0, r1, .., r[n/2], i[n/2-1], .., i1),
+                           what the CPU build's initsolver produces; 1 = the packed order (r0, r[n/2], r1, i1, r2, i2, ..)
+                           an _OPENACC build's initsolver produces (src/initsolver.f90:98-117), so that initsolver stays
+                           unchanged on an OpenACC host too.  On several ranks the rows of a periodic y direction are then
+                           dealt out to the z pencils in packed order, i.e. lambdaxy(lo_z(1):hi_z(1), lo_z(2):hi_z(2)) means what
+                           it means in the reference */
+  int reserved[10];
 } cansb200_options;
 
 /* -- context: replaces initmpi's cuDecomp setup (src/initmpi.f90:84-146), common_cudecomp.f90
@@ -108,6 +114,26 @@ int cansb200_solve(cansb200_plan* plan, void* p, const int n[3], int nhalo, doub
  *    peer-mapped row tables as the full solve.  norm as in the reference (1 for the diffusion solves). */
 int cansb200_solve_z(cansb200_plan* plan, void* p, const int n[3], int nhalo, double norm,
                      const void* a, const void* b, const void* c, int mem_kind, void* stream);
+
+/* The same solve for a host that holds no plan for it: the reference's call is
+ *   solver_gaussel_z(n,ng,hi,a,b,c,bcz,c_or_f,norm,p)     (src/solve_helmholtz.f90:73, src/solver_gpu.f90:956-963)
+ * -- no arrplan.  The context keeps one z-only plan per (bcz, c_or_f(3)), created on first use. */
+int cansb200_solve_z_bc(cansb200_ctx* ctx, const char bcz[2], char c_or_f_z, void* p, const int n[3], int nhalo, double norm,
+                        const void* a, const void* b, const void* c, int mem_kind, void* stream);
+
+/* -- integer names for plans.  On the reference's CUDA build `arrplan` is `integer, dimension(2,2)` (cuFFT handles:
+ *    src/main.f90:94,107, src/fft.f90:31-35), not type(C_PTR): a 64-bit pointer does not fit one element.  The shim stores
+ *    cansb200_plan_id(plan) (a small positive integer, unique per process while the plan lives) in arrplan(1,1) and gets
+ *    the plan back with cansb200_plan_from_id (NULL for an unknown id). */
+int cansb200_plan_id(cansb200_plan* plan);
+cansb200_plan* cansb200_plan_from_id(int id);
+
+/* -- updt_rhs_b (src/bound.f90:514-598) on the device: adds rhsb*(d, side) * norm to the first / last interior planes.
+ *    rhsb[d][side] are the (uniform) wall values of bc_rhs (src/initsolver.f90:189-232); is_bound[d][side] != 0 where this
+ *    rank owns the wall; have[d] = 0 skips a direction (an absent optional argument); norm = alpha for Helmholtz solves,
+ *    1 otherwise.  c_or_f / bc as in cansb200_plan_create (face-centred Dirichlet tops end one plane early). */
+int cansb200_updt_rhs_b(cansb200_ctx* ctx, const char c_or_f[3], const char bc[6], const int n[3], const int is_bound[6],
+                        const int have[3], const double rhsb[6], double norm, void* p, void* stream);
 
 /* -- stage-level entry points (device pointers only), so that tests can compare every stage
  *    with the oracle the way the reference composes them:
@@ -179,6 +205,13 @@ enum {
                                     per-window flags); -1 = auto (4 when nx allows), 1 = one window (two whole-field barriers) */
   CANSB200_CTX_DIST_THOMAS_CTAS = 11, /* CTAs of the persistent tridiagonal kernel while it shares the GPU with the y transforms of the
                                     neighbouring windows (one CTA fills an SM); -1 = auto (5/8 of the SMs) */
+  CANSB200_CTX_DIST_MODE = 12,    /* several ranks: how the two exchanges travel.  0 = the producing kernels store their rows straight into
+                                    the peers' buffers (pack + wire + unpack in one store; the kernel holds its SMs while NVLink drains);
+                                    1 = the producing kernels write dense per-destination blocks locally and the copy engines move them
+                                    (SMs are free for the HBM-only stages meanwhile, at the price of one more local write + read);
+                                    -1 = auto */
+  CANSB200_CTX_DIST_CHUNKS = 13,  /* copy-engine exchange: z chunks of the forward half (x transform of chunk c + 1 runs while chunk c is on
+                                    the wire); -1 = auto */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
                                     bit 2 = force the maximum shared-memory carveout (default: the driver picks, which leaves L1 to the twiddles) */
 };

@@ -116,6 +116,57 @@ int main(int argc, char** argv) {
     run("TMA bulk store, 2 KB chunks", both, [&](int d) { k_bulk<<<G, 256, 2048, st[d]>>>(rem[1 - d], loc[d], bytes / 2048, 2048); });
     run("TMA bulk store, 128 B rows 8 KB apart", both, [&](int d) { k_bulk_rows<<<G, 256, 8192, st[d]>>>(rem[1 - d], loc[d], bytes / 8192, 64, 8192); });
     run("remote loads (pull) 16 B/thread", both, [&](int d) { k_pull16<<<G, 256, 0, st[d]>>>((double2*)loc[d], (const double2*)rem[1 - d], bytes / 16); });
+    // copy engines: strided 2-D copies (one x window of the way-back exchange: 2 KB rows, 8 KB pitch) and chunked copies
+    run("cudaMemcpy2DAsync 2 KB rows, pitch 8 KB", both, [&](int d) {
+      for (int w = 0; w < 4; ++w) CK(cudaMemcpy2DAsync(rem[1 - d] + w * 2048, 8192, loc[d] + w * 2048, 8192, 2048, bytes / 8192, cudaMemcpyDeviceToDevice, st[d]));
+    });
+    run("cudaMemcpy2DAsync 512 B rows, pitch 8 KB", both, [&](int d) {
+      for (int w = 0; w < 16; ++w) CK(cudaMemcpy2DAsync(rem[1 - d] + w * 512, 8192, loc[d] + w * 512, 8192, 512, bytes / 8192, cudaMemcpyDeviceToDevice, st[d]));
+    });
+    run("cudaMemcpyAsync 32 chunks of 8 MB", both, [&](int d) {
+      for (int c = 0; c < 32; ++c) CK(cudaMemcpyAsync(rem[1 - d] + (size_t)c * (8 << 20), loc[d] + (size_t)c * (8 << 20), 8 << 20, cudaMemcpyDeviceToDevice, st[d]));
+    });
+    run("cudaMemcpyAsync 128 chunks of 2 MB", both, [&](int d) {
+      for (int c = 0; c < 128; ++c) CK(cudaMemcpyAsync(rem[1 - d] + (size_t)c * (2 << 20), loc[d] + (size_t)c * (2 << 20), 2 << 20, cudaMemcpyDeviceToDevice, st[d]));
+    });
+  }
+  // how many CTAs (of 256 threads) does a store kernel need to fill the link?  (can a producer kernel leave SMs to others?)
+  for (int ctas : {18, 37, 74, 148, 296, 592}) {
+    char name[64];
+    snprintf(name, sizeof(name), "128 B rows 8 KB apart, %d CTAs", ctas);
+    run(name, 1, [&](int d) { k_rows<<<ctas, 256, 0, st[d]>>>(rem[1 - d], loc[d], bytes / 128, 128, 8192, 64); });
+  }
+  // a copy-engine transfer next to an HBM-bound kernel on the same GPU: does either slow the other down?
+  {
+    char *big0, *big1;
+    const size_t nb = (size_t)1 << 30;
+    CK(cudaSetDevice(0));
+    CK(cudaMalloc(&big0, nb));
+    CK(cudaMalloc(&big1, nb));
+    cudaStream_t s2;
+    CK(cudaStreamCreate(&s2));
+    cudaEvent_t a0, a1, b0, b1;
+    CK(cudaEventCreate(&a0)); CK(cudaEventCreate(&a1)); CK(cudaEventCreate(&b0)); CK(cudaEventCreate(&b1));
+    for (int mode = 0; mode < 3; ++mode) {   // 0: kernel alone, 1: copies alone (both directions), 2: together
+      float tk = 0, tc = 0;
+      for (int it = 0; it < 4; ++it) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaSetDevice(1)); CK(cudaDeviceSynchronize()); CK(cudaSetDevice(0));
+        if (mode != 1) { CK(cudaEventRecord(a0, s2)); for (int r = 0; r < 2; ++r) k_contig16<<<G, 256, 0, s2>>>((double2*)big1, (const double2*)big0, nb / 16); CK(cudaEventRecord(a1, s2)); }
+        if (mode != 0) {
+          CK(cudaEventRecord(b0, st[0]));
+          CK(cudaMemcpyAsync(rem[1], loc[0], bytes, cudaMemcpyDeviceToDevice, st[0]));
+          CK(cudaEventRecord(b1, st[0]));
+          CK(cudaSetDevice(1)); CK(cudaMemcpyAsync(rem[0], loc[1], bytes, cudaMemcpyDeviceToDevice, st[1])); CK(cudaSetDevice(0));
+        }
+        CK(cudaDeviceSynchronize());
+        CK(cudaSetDevice(1)); CK(cudaDeviceSynchronize()); CK(cudaSetDevice(0));
+        if (mode != 1) CK(cudaEventElapsedTime(&tk, a0, a1));
+        if (mode != 0) CK(cudaEventElapsedTime(&tc, b0, b1));
+      }
+      printf("overlap mode %d: local copy kernel (2 x 2 GiB traffic) %.3f ms = %.0f GB/s ; peer DMA (256 MiB out, 256 MiB in) %.3f ms = %.0f GB/s\n",
+             mode, tk, tk > 0 ? 4.0 * nb / tk / 1e6 : 0.0, tc, tc > 0 ? bytes / tc / 1e6 : 0.0);
+    }
   }
   return 0;
 }

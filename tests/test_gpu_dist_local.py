@@ -25,7 +25,7 @@ def cb():
     return importlib.import_module("cans_b200")
 
 
-def _run_virtual_ranks(cb, name, P, windows):
+def _run_virtual_ranks(cb, name, P, windows, mode=0, chunks=-1):
     from cans_b200.decomp import SlabDecomp
     ng, l, cbc, cf, gr, dt, helm = cases.DIST_CASES[name]
     if P > ng[1] or P > ng[2]:
@@ -44,6 +44,7 @@ def _run_virtual_ranks(cb, name, P, windows):
         dec = SlabDecomp(ng, P, r)
         assert c.n == dec.n and c.lo == dec.lo and c.n_z == dec.n_z and c.lo_z == dec.lo_z
         c.set_dist_windows(windows)
+        c.set_dist_mode(mode, chunks)
     cb.Context.connect_local(ctxs)
     sds = [cb.initsolver(c, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], cf, device=dev) for c in ctxs]
     streams = [torch.cuda.Stream() for _ in range(P)]
@@ -119,6 +120,19 @@ def test_virtual_ranks_one_window(cb, name):
 
 def test_virtual_ranks_four(cb):
     _run_virtual_ranks(cb, "chan_64x64x64", 4, -1)
+
+
+@pytest.mark.parametrize("name", sorted(cases.DIST_CASES))
+@pytest.mark.parametrize("P", [2, 3])
+def test_virtual_ranks_copy_engines(cb, name, P):
+    """CANSB200_CTX_DIST_MODE = 1: dense local send blocks moved by the copy engines (z chunks forward, x windows back)"""
+    _run_virtual_ranks(cb, name, P, -1, mode=1)
+
+
+@pytest.mark.parametrize("windows,chunks", [(1, 1), (2, 3), (8, 8)])
+def test_virtual_ranks_copy_engines_shapes(cb, windows, chunks):
+    _run_virtual_ranks(cb, "duct_128x64x96", 4, windows, mode=1, chunks=chunks)
+    _run_virtual_ranks(cb, "uneven_64x64x70", 3, windows, mode=1, chunks=chunks)
 
 
 def test_missing_rank_is_reported(cb):

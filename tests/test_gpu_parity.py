@@ -391,8 +391,9 @@ def test_sanity_solver_on_gpu(cb, S):
     ([1024, 768, 768], [cases.P, cases.N, cases.N], 1.5),   # C4 duct (radix-3 stage, DCT in y)
 ])
 def test_full_size_residual(cb, S, ng, cbc, gr):
-    """At BASELINE.json's full sizes the oracle is too slow; check size-independent properties:
-    the discrete Poisson residual (chk_poisson, src/debug.f90:91-132) and linearity."""
+    """Size-independent property at BASELINE.json's full sizes: the discrete Poisson residual of the result
+    (chk_poisson, src/debug.f90:91-132) is below `small`.  The 1e-12 comparison with the oracle at the same sizes is
+    test_full_size_parity below."""
     l = [6.2832, 6.2832, 6.2832] if gr == 0.0 else [12.0, 6.0, 2.0]
     per_z = cbc[2] == cases.P
     dzc, dzf, _, _ = O.initgrid(1, ng[2], gr, l[2], per_z)
@@ -428,3 +429,106 @@ def test_full_size_residual(cb, S, ng, cbc, gr):
     assert resmax < O.small(np.float64), resmax
     st = sd.arrplan.stats()
     assert st["factorisations"] == 1
+
+
+FULL_SIZE = [
+    ("C2_tgv_512x512x512", [512, 512, 512], [6.283185307179586] * 3, [cases.P, cases.P, cases.P], 0.0),
+    ("C3_channel_1024x512x512", [1024, 512, 512], [12.0, 6.0, 2.0], [cases.P, cases.P, cases.N], 2.0),
+    ("C4_duct_1024x768x768", [1024, 768, 768], [12.0, 2.0, 2.0], [cases.P, cases.N, cases.N], 1.5),
+]
+
+
+@pytest.mark.parametrize("name,ng,l,cbc,gr", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_parity(cb, S, name, ng, l, cbc, gr):
+    """BASELINE.json's criterion at BASELINE.json's sizes: pressure within 1e-12 relative L2 of the reference's CPU
+    path on identical inputs.  Oracle = `solver_fast` (threaded pocketfft + the C restatement of gaussel that
+    tests/test_oracle.py shows bit-identical to the Python one).  C3 and C4 are singular operators on a stretched
+    grid: the constant mode of the reference's own answer is rounding noise there, the asserted metric is
+    the one modulo the constant mode and the strict number is printed beside it."""
+    cs = O.make_case(ng, l, cbc, gr=gr)
+    p = cases.make_rhs(cs)
+    ref = p.copy()
+    O.solver_fast(ng, ng, cs["arrplan"], cs["normfft"], cs["lambdaxy"], cs["a"], cs["b"], cs["c"], cbc, ["c"] * 3, ref)
+    ctx = cb.Context(ng)
+    dev = _dev()
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], ["c"] * 3, device=dev)
+    pd = torch.from_numpy(p).to(dev)
+    del p
+    cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, ["c"] * 3, pd)
+    torch.cuda.synchronize()
+    got = pd.cpu().numpy()[1:-1, 1:-1, 1:-1]
+    ref = ref[1:-1, 1:-1, 1:-1]
+    strict = cases.rel_l2(got, ref)
+    modc = cases.rel_l2_mod_const(got, ref)
+    pinned = cases.null_mode_is_pinned(cs)
+    print(f"\n{name}: rel L2 strict = {strict:.3e}, modulo the constant mode = {modc:.3e}, "
+          f"null mode pinned by the reference's test: {pinned}")
+    assert (strict if pinned else modc) < 1e-12
+    sd.arrplan.destroy()
+    ctx.close()
+
+
+def test_chkdiv_not_larger_than_oracle(cb, S):
+    """BASELINE.json: "post-correction divergence from chkdiv no larger than the reference's".  The reference's
+    self-test (src/sanity.f90:262-283: noise -> fillps -> solver -> boundp -> correc -> bounduvw -> chkdiv) on the
+    scaled C3 operator, once through the oracle and once through the CUDA path on identical u, v, w.  Both divergences
+    are rounding residue of O(1e-13); "no larger" is asserted with the 10 % slack two different summation orders need
+    to be comparable at all, and both must be below `small`."""
+    ng, l = [256, 128, 96], [12.0, 6.0, 2.0]
+    cbc = [cases.P, cases.P, cases.N]
+    cs = O.make_case(ng, l, cbc, gr=2.0)
+    shp = (ng[2] + 2, ng[1] + 2, ng[0] + 2)
+    dt = float(np.arccos(-1.0))
+
+    def bounduvw_np(u, v, w):
+        for t in (u, v, w):
+            t[:, :, 0] = t[:, :, -2]; t[:, :, -1] = t[:, :, 1]
+            t[:, 0, :] = t[:, -2, :]; t[:, -1, :] = t[:, 1, :]
+        for t in (u, v):
+            t[0] = -t[1]; t[-1] = -t[-2]
+        w[0] = 0.0; w[-2] = 0.0; w[-1] = w[-3]
+
+    def boundp_np(p):
+        p[:, :, 0] = p[:, :, -2]; p[:, :, -1] = p[:, :, 1]
+        p[:, 0, :] = p[:, -2, :]; p[:, -1, :] = p[:, 1, :]
+        p[0] = p[1]; p[-1] = p[-2]
+
+    uvw = []
+    for seed in (123, 456, 789):
+        t = np.zeros(shp)
+        t[1:-1, 1:-1, 1:-1] = 0.5 * O.hash_field(ng, seed)
+        uvw.append(t)
+    bounduvw_np(*uvw)
+    # oracle
+    uo, vo, wo = (t.copy() for t in uvw)
+    po = np.zeros(shp)
+    O.fillps(ng, cs["dli"], cs["dzfi"], 1.0 / dt, uo, vo, wo, po)
+    O.solver(ng, ng, cs["arrplan"], cs["normfft"], cs["lambdaxy"], cs["a"], cs["b"], cs["c"], cbc, ["c"] * 3, po)
+    boundp_np(po)
+    O.correc(ng, cs["dli"], cs["dzci"], dt, po, uo, vo, wo)
+    bounduvw_np(uo, vo, wo)
+    _, div_o = O.chkdiv(ng, l, cs["dli"], cs["dzfi"], uo, vo, wo)
+    # CUDA path
+    dev = _dev()
+    ctx = cb.Context(ng)
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], ["c"] * 3, device=dev)
+    u, v, w = (torch.from_numpy(t).to(dev) for t in uvw)
+    p = torch.zeros(shp, dtype=torch.float64, device=dev)
+    dzfi = torch.from_numpy(cs["dzfi"]).to(dev)
+    dzci = torch.from_numpy(cs["dzci"]).to(dev)
+    S.fillps(ctx, ng, cs["dli"], dzfi, 1.0 / dt, u, v, w, p)
+    cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, ["c"] * 3, p)
+    p[:, :, 0] = p[:, :, -2]; p[:, :, -1] = p[:, :, 1]
+    p[:, 0, :] = p[:, -2, :]; p[:, -1, :] = p[:, 1, :]
+    p[0] = p[1]; p[-1] = p[-2]
+    S.correc(ctx, ng, cs["dli"], dzci, dt, p, u, v, w)
+    for t in (u, v, w):
+        t[:, :, 0] = t[:, :, -2]; t[:, :, -1] = t[:, :, 1]
+        t[:, 0, :] = t[:, -2, :]; t[:, -1, :] = t[:, 1, :]
+    for t in (u, v):
+        t[0] = -t[1]; t[-1] = -t[-2]
+    w[0] = 0.0; w[-2] = 0.0; w[-1] = w[-3]
+    _, div_g = S.chkdiv(ctx, ng, l, cs["dli"], dzfi, u, v, w)
+    print(f"\nchkdiv: divmax CUDA = {div_g:.3e}, oracle = {div_o:.3e}, small = {O.small(np.float64):.1e}")
+    assert div_g < O.small(np.float64) and div_o < O.small(np.float64)
+    assert div_g <= 1.1 * div_o, (div_g, div_o)
