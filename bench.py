@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--dist-thomas-ctas", type=int, default=-1, help="N > 1: CTAs of the tridiagonal kernel inside the pipeline (-1 auto)")
     ap.add_argument("--dist-mode", type=int, default=-1, help="N > 1: 0 = peer stores of the producing kernels, 1 = copy engines, -1 = auto")
     ap.add_argument("--dist-chunks", type=int, default=-1, help="N > 1, copy engines: z chunks of the forward half (-1 auto)")
+    ap.add_argument("--dist-split-pad", type=int, default=-1, help="N > 1, mode 2: KB of shared-memory padding of the forward y transforms")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the check of the distributed result against a single-GPU solve")
     ap.add_argument("--helmholtz", type=float, default=0.0,
                     help="alpha != 0: time the implicit-diffusion Helmholtz solve p/alpha + lap p = rhs (regular operator) instead")
@@ -333,7 +334,7 @@ def main():
     if args.dtdma and world > 1:
         ctx.set_dtdma(True)
     ctx.set_dist_windows(args.dist_windows, args.dist_thomas_ctas)
-    ctx.set_dist_mode(args.dist_mode, args.dist_chunks)
+    ctx.set_dist_mode(args.dist_mode, args.dist_chunks, args.dist_split_pad)
     ctx.set_variant(args.x_variant, args.y_variant)
     if args.r2_flags >= 0:
         ctx.set_r2_flags(args.r2_flags)

@@ -140,10 +140,12 @@ struct cansb200_ctx {
   int dist_windows = -1;                       // x windows of the pipelined exchange (-1 = auto: up to 4)
   int dist_thomas_ctas = -1;                   // CTAs of the tridiagonal kernel while it shares the GPU with the y transforms (-1 = auto)
   int dist_mode = -1;                          // exchange flavour: 0 = stores of the producing kernels, 1 = copy engines, -1 = auto
-  int dist_chunks = -1;                        // copy-engine exchange: z chunks of the forward half (-1 = auto)
+  int dist_chunks = -1;                        // z chunks of the forward half (-1 = auto)
+  int dist_split_pad = -1;                     // KB of shared-memory padding of the forward SPLIT kernels (-1 = auto: one CTA per SM)
   DevBuf sendb;                                // copy-engine exchange: way-back send buffer [dest][j][k][i] (the forward one is scratch2)
   DevBuf ytab_fwd_loc, ytab_fwd_loc_pk, ztab_loc;   // ... row tables that point into the local send buffers
   std::vector<cudaStream_t> dist_cs;           // ... one copy stream per peer
+  cudaStream_t dist_sF = nullptr;              // two-half schedule: stream of the forward y transforms
   cudaStream_t dist_sT = nullptr, dist_sB = nullptr;   // pipeline stages: tridiagonal solve / backward y transform (forward = caller's stream)
   std::vector<cudaEvent_t> dist_ev;            // [w] forward window done, [W + w] tridiagonal window done, [2 W] backward done
   DevBuf ytab_fwd, ytab_bwd, ztab;
@@ -304,6 +306,7 @@ struct R2RGeom {
   long long in_es, out_es, in_ls, out_ls, in_gs, out_gs;
   int lines_per_group, ngroups, line_len, ymode;
   const void* row_tab = nullptr;   // distributed y transforms: peer-mapped output (forward) / input (backward) rows
+  int smem_pad = 0;                // ... extra shared memory per CTA (caps the CTAs per SM while the kernel shares the GPU)
   int x0 = 0, g0 = 0;              // ... launched on a window of the slab: its first column / plane (the row table addresses whole rows)
 };
 
@@ -346,7 +349,7 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
       for (int s = 0; s < 4; ++s) A.tw[s] = rt->tw[s];
       A.mak = rt->mak;
       A.row_tab = (const R2Row<T>*)g.row_tab;
-      A.x0 = g.x0; A.g0 = g.g0;
+      A.x0 = g.x0; A.g0 = g.g0; A.smem_pad = g.smem_pad;
       A.flags = ctx->r2_flags & 3;
       cb::g_r2_default_carveout = (ctx->r2_flags & 4) ? 0 : 1;
       const int rc = !g.ymode ? r2r2_run<T, false, false>(A, nt, var, kind_is_forward(kind), st)
@@ -868,6 +871,7 @@ int cansb200_finalize(cansb200_ctx* c) {
   if (c->dist_status_dev) cudaFree(c->dist_status_dev);
   c->sendb.release(); c->ytab_fwd_loc.release(); c->ytab_fwd_loc_pk.release(); c->ztab_loc.release();
   for (cudaStream_t q : c->dist_cs) if (q) cudaStreamDestroy(q);
+  if (c->dist_sF) cudaStreamDestroy(c->dist_sF);
   if (c->dist_sT) cudaStreamDestroy(c->dist_sT);
   if (c->dist_sB) cudaStreamDestroy(c->dist_sB);
   for (cudaEvent_t q : c->dist_ev) cudaEventDestroy(q);
@@ -925,13 +929,18 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
     return 0;
   }
   if (what == CANSB200_CTX_DIST_MODE) {
-    if (value < -1 || value > 1) return fail(CANSB200_EINVAL, "ctx_set: dist_mode must be -1 (auto), 0 (peer stores) or 1 (copy engines)");
+    if (value < -1 || value > 2) return fail(CANSB200_EINVAL, "ctx_set: dist_mode must be -1 (auto), 0, 1 or 2");
     c->dist_mode = value;
     return 0;
   }
   if (what == CANSB200_CTX_DIST_CHUNKS) {
     if (value < -1 || value == 0 || value > CB_MAX_WINDOWS) return fail(CANSB200_EINVAL, "ctx_set: dist_chunks must be -1 (auto) or 1..8");
     c->dist_chunks = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_DIST_SPLIT_PAD) {
+    if (value < -1 || value > 160) return fail(CANSB200_EINVAL, "ctx_set: dist_split_pad must be -1 (auto) or 0..160 KB");
+    c->dist_split_pad = value;
     return 0;
   }
   if (what == CANSB200_CTX_DIST_THOMAS_CTAS) {
@@ -1173,7 +1182,9 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
   const int wide = (int)(128 / sizeof(T));
   int W = 1;
   if (pipelined && !ctx->profiling) {
-    const int want = ctx->dist_windows > 0 ? ctx->dist_windows : 4;
+    // auto: measured on C3 (profiles/r2b_exchange_schedules.md) the windows pay on 2 ranks (2.82 -> 2.73 ms) and cost a
+    // little on 4 and 8 (the kernels that store to the peers hold every SM while NVLink drains, whatever the schedule)
+    const int want = ctx->dist_windows > 0 ? ctx->dist_windows : (ctx->nranks == 2 ? 4 : 1);
     for (W = want < CB_MAX_WINDOWS ? want : CB_MAX_WINDOWS; W > 1; --W)
       if (nx % (W * wide) == 0) break;
   }
@@ -1340,9 +1351,14 @@ template <class T> static int build_dma_tables(cansb200_ctx* c) {
   return 0;
 }
 
+// Two-half schedule of the distributed solve.  dma = true: the copy-engine exchange described above.  dma = false: the
+// producing kernels store straight into the peers' buffers (as solve_dist does), but in the same two halves -- z chunks
+// forward, so that the x transform of chunk c + 1 (HBM only) runs next to the y transform of chunk c (NVLink bound; its
+// CTAs are padded to one per SM so that it leaves room), x windows backward (tridiagonal kernel on part of the SMs next to
+// the backward y transform of the previous window).
 template <class T>
-static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normfft, const T* lam, const T* a, const T* b,
-                          const T* c, bool y_packed, cudaStream_t st) {
+static int solve_dist2(cansb200_plan* pl, T* p, const int n[3], double normfft, const T* lam, const T* a, const T* b,
+                       const T* c, bool y_packed, bool dma, cudaStream_t st) {
   cansb200_ctx* ctx = pl->ctx;
   const unsigned long long seq = ++ctx->seq;
   int rc = dist_check(ctx, "solve");
@@ -1352,7 +1368,7 @@ static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normff
   const int nyl = ctx->n_z[1], nz = ctx->ng[2];
   const long long px = nx + 2, py = ny + 2;
   if (pl->th_n != nz - pl->q) return fail(CANSB200_EINVAL, "solve: plan / grid mismatch");
-  if (ctx->dist_cs.empty()) {
+  if (dma && ctx->dist_cs.empty()) {
     rc = build_dma_tables<T>(ctx);
     if (rc) return rc;
   }
@@ -1362,7 +1378,7 @@ static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normff
   T* Cz = (T*)((char*)ctx->region + ctx->off_C);
   T* XB = (T*)((char*)ctx->region + ctx->off_XB);
   T* pin = p + (px * py + px + 1);
-  const void* ytab_fwd = y_packed ? ctx->ytab_fwd_loc_pk.p : ctx->ytab_fwd_loc.p;
+  const void* ytab_fwd = dma ? (y_packed ? ctx->ytab_fwd_loc_pk.p : ctx->ytab_fwd_loc.p) : (y_packed ? ctx->ytab_fwd_pk.p : ctx->ytab_fwd.p);
   const void* ytab_bwd = y_packed ? ctx->ytab_bwd_pk.p : ctx->ytab_bwd.p;
   const int wide = (int)(128 / sizeof(T));
   // z chunks of the forward half, x windows of the backward half
@@ -1374,26 +1390,30 @@ static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normff
     for (W = want < CB_MAX_WINDOWS ? want : CB_MAX_WINDOWS; W > 1; --W)
       if (nx % (W * wide) == 0) break;
   }
-  if (!thomas_is_pipelined(pl)) W = 1;   // the sequential kernel has no column windows
+  const bool pipelined = thomas_is_pipelined(pl);
+  if (!pipelined) W = 1;   // the sequential kernel has no column windows
   if (!ctx->dist_sT) {
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&ctx->dist_sT, cudaStreamNonBlocking, hi));
     CK(cudaStreamCreateWithPriority(&ctx->dist_sB, cudaStreamNonBlocking, hi));
   }
-  while ((int)ctx->dist_ev.size() < 2 * CB_MAX_WINDOWS + 1) {
+  if (!ctx->dist_sF) CK(cudaStreamCreateWithFlags(&ctx->dist_sF, cudaStreamNonBlocking));
+  while ((int)ctx->dist_ev.size() < 2 * CB_MAX_WINDOWS + 2) {
     cudaEvent_t e;
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->dist_ev.push_back(e);
   }
   cudaStream_t sT = ctx->dist_sT, sB = ctx->dist_sB;
+  cudaStream_t sF = (dma || Cn == 1) ? st : ctx->dist_sF;   // stream of the forward y transforms
   const size_t esz = sizeof(T);
+  const int pad_kb = dma || Cn == 1 ? 0 : (ctx->dist_split_pad >= 0 ? ctx->dist_split_pad : 52);
   prof_mark(ctx, st);
   ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam, a, b, c);
-  D.out_rows = (const OutRow<T>*)ctx->ztab_loc.p;
+  D.out_rows = (const OutRow<T>*)(dma ? ctx->ztab_loc.p : ctx->ztab.p);
   rc = gaussel_prepare<T>(pl, D, st);   // pivot-cache lookup (factorisation on a miss) ahead of everything
   if (rc) return rc;
-  // ---- forward half: x transform, y transform into the send blocks, one transfer per peer and chunk
+  // ---- forward half: x transform, y transform (into the send blocks / the peers' z pencils), chunk by chunk
   for (int q = 0; q < Cn; ++q) {
     const int g0 = (int)((long long)nzl * q / Cn), g1 = (int)((long long)nzl * (q + 1) / Cn), ng_ = g1 - g0;
     if (ng_ < 1) continue;
@@ -1401,11 +1421,17 @@ static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normff
     rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin + (long long)g0 * px * py, A + (long long)g0 * nx * ny, gx, pl->opt.fft_x_lines, st);
     if (rc) return rc;
     if (Cn == 1) prof_mark(ctx, st);
+    if (sF != st) {
+      CK(cudaEventRecord(ctx->dist_ev[q], st));
+      CK(cudaStreamWaitEvent(sF, ctx->dist_ev[q], 0));
+    }
     R2RGeom gyf{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, nx, ng_, ny, 1};
     gyf.row_tab = ytab_fwd;
     gyf.g0 = g0;
-    rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + (long long)g0 * nx * ny, A + (long long)g0 * nx * ny, gyf, pl->opt.fft_y_lines, st);
+    gyf.smem_pad = pad_kb * 1024;
+    rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + (long long)g0 * nx * ny, A + (long long)g0 * nx * ny, gyf, pl->opt.fft_y_lines, sF);
     if (rc) return rc;
+    if (!dma) continue;
     CK(cudaEventRecord(ctx->dist_ev[q], st));
     for (int d = 1; d < P; ++d) {
       const int s = (r + d) % P;   // every rank starts with a different peer
@@ -1416,24 +1442,34 @@ static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normff
       CK(cudaMemcpyAsync(dst, src, (size_t)ng_ * nyl_s * nx * esz, cudaMemcpyDeviceToDevice, ctx->dist_cs[s]));
     }
   }
-  for (int d = 1; d < P; ++d) {
-    const int s = (r + d) % P;
-    rc = dist_flag(ctx, CB_SLOT_FWD, seq, true, false, ctx->dist_cs[s], s);   // "my block has landed on your z pencil"
+  if (dma) {
+    for (int d = 1; d < P; ++d) {
+      const int s = (r + d) % P;
+      rc = dist_flag(ctx, CB_SLOT_FWD, seq, true, false, ctx->dist_cs[s], s);   // "my block has landed on your z pencil"
+      if (rc) return rc;
+    }
+    CK(cudaStreamWaitEvent(sT, ctx->dist_ev[Cn - 1], 0));   // my own block is written by my own kernels
+    rc = dist_flag(ctx, CB_SLOT_FWD, seq, false, true, sT, -1, true);
+  } else {
+    rc = dist_flag(ctx, CB_SLOT_FWD, seq, true, false, sF);
     if (rc) return rc;
+    CK(cudaEventRecord(ctx->dist_ev[2 * CB_MAX_WINDOWS + 1], sF));
+    CK(cudaStreamWaitEvent(sT, ctx->dist_ev[2 * CB_MAX_WINDOWS + 1], 0));
+    rc = dist_flag(ctx, CB_SLOT_FWD, seq, false, true, sT);
   }
-  CK(cudaStreamWaitEvent(sT, ctx->dist_ev[Cn - 1], 0));   // my own block is written by my own kernels
-  rc = dist_flag(ctx, CB_SLOT_FWD, seq, false, true, sT, -1, true);
   if (rc) return rc;
   prof_mark(ctx, sT);
   prof_mark(ctx, sT);
-  // ---- backward half: tridiagonal solve of an x window into the send blocks, 2-D transfers, backward y transform
+  // ---- backward half: tridiagonal solve of an x window (into the send blocks / the peers' slabs), backward y transform
   const int ww = nx / W;
-  const bool pipelined = thomas_is_pipelined(pl);
+  const int cap = ctx->dist_thomas_ctas > 0 ? ctx->dist_thomas_ctas : (ctx->num_sms * 5) / 8;
   for (int w = 0; w < W; ++w) {
     const int xb = w * ww;
     if (pipelined) {
       D.xb = xb; D.xn = ww;
+      ctx->cta_cap = (!dma && W > 1) ? cap : 0;
       rc = gaussel_apply<T>(pl, D, Cz, (T)normfft, sT);
+      ctx->cta_cap = 0;
       if (rc) return rc;
       if (pl->th_n < nz) {
         scatter_rows_kernel<T><<<ctx->num_sms, 256, 0, sT>>>(Cz, D.sk, (const DistOutRow<T>*)D.out_rows, pl->th_n, nz, nyl, nx, xb, ww);
@@ -1448,8 +1484,12 @@ static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normff
       ctx->launches++;
     }
     CK(cudaGetLastError());
+    if (!dma) {
+      rc = dist_flag(ctx, CB_SLOT_BWD + w, seq, true, false, sT);
+      if (rc) return rc;
+    }
     CK(cudaEventRecord(ctx->dist_ev[CB_MAX_WINDOWS + w], sT));
-    for (int d = 1; d < P; ++d) {
+    for (int d = 1; dma && d < P; ++d) {
       const int s = (r + d) % P;
       const long long nzl_s = ctx->zs[s + 1] - ctx->zs[s];
       T* dst = (T*)((char*)ctx->peer[s] + ctx->peer_off_XB[s]) + nzl_s * ctx->ys[r] * nx + xb;
@@ -1464,7 +1504,7 @@ static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normff
       if (rc) return rc;
     }
     CK(cudaStreamWaitEvent(sB, ctx->dist_ev[CB_MAX_WINDOWS + w], 0));
-    rc = dist_flag(ctx, CB_SLOT_BWD + w, seq, false, true, sB, -1, true);
+    rc = dist_flag(ctx, CB_SLOT_BWD + w, seq, false, true, sB, -1, dma);
     if (rc) return rc;
     if (W == 1) prof_mark(ctx, sB);
     R2RGeom gyb{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, ww, nzl, ny, 1};
@@ -1475,7 +1515,6 @@ static int solve_dist_dma(cansb200_plan* pl, T* p, const int n[3], double normff
   }
   CK(cudaEventRecord(ctx->dist_ev[2 * CB_MAX_WINDOWS], sB));
   CK(cudaStreamWaitEvent(st, ctx->dist_ev[2 * CB_MAX_WINDOWS], 0));
-  // the copy streams must not run into the next solve's events before this one is over
   prof_mark(ctx, st);
   R2RGeom gxb{1, 1, nx, px, (long long)nx * ny, px * py, ny, nzl, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][1], pl->nt[0], A, pin, gxb, pl->opt.fft_x_lines, st);
@@ -1679,7 +1718,7 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   }
   if (ctx->nranks > 1) {
     const int rcd = ctx->dtdma ? solve_dist_dtdma<T>(pl, p, n, normfft, lam, a, b, c, st)
-                               : (ctx->dist_mode == 1 ? solve_dist_dma<T>(pl, p, n, normfft, lam, a, b, c, pky, st)
+                               : (ctx->dist_mode >= 1 ? solve_dist2<T>(pl, p, n, normfft, lam, a, b, c, pky, ctx->dist_mode == 1, st)
                                                       : solve_dist<T>(pl, p, n, normfft, lam, a, b, c, pky, st));
     if (rcd) return rcd;
     if (mem_kind == CANSB200_MEM_HOST) {

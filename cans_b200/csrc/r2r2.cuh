@@ -240,6 +240,7 @@ template <class T> struct R2Args {
   const Cx<T>* mak;          // (cos, sin)(pi k / (2N)), k = 0..N/2
   const R2Row<T>* row_tab;   // SPLIT kernels: where each output (forward) / input (backward) row lives
   int flags;                 // CB_R2_LD_NA | CB_R2_ST_CS
+  int smem_pad = 0;          // host only: extra dynamic shared memory per CTA, to cap the CTAs per SM of a kernel that shares the GPU
   int x0 = 0, g0 = 0;        // SPLIT kernels launched on a window of the slab: first column / first plane of the window
                              // (the row table addresses whole slab rows; in / out already point at the window)
 };

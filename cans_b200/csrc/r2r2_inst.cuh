@@ -65,11 +65,13 @@ namespace cb {
 extern int g_r2_default_carveout;
 
 template <class K>
-static int r2r2_launch_kernel(K k, const void* args, unsigned grid, unsigned block, size_t smem, cudaStream_t st) {
+static int r2r2_launch_kernel(K k, const void* args, unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool split = false) {
   // one attribute call per kernel and process (keyed by the function address)
   static std::set<const void*> done;
   if (!done.count((const void*)k)) {
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+    // the SPLIT kernels may be launched with padded shared memory (R2Args::smem_pad): allow the maximum once
+    const size_t lim = split && smem < 200 * 1024 ? 200 * 1024 : smem;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim) != cudaSuccess) return -3;
     if (!g_r2_default_carveout)
       cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     done.insert((const void*)k);
@@ -81,7 +83,8 @@ static int r2r2_launch_kernel(K k, const void* args, unsigned grid, unsigned blo
 template <class T, class Cfg, bool YMODE, bool SPLIT>
 static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
   using Lay = R2Lay<T, Cfg, YMODE>;
-  const size_t smem = Lay::smem_bytes();
+  size_t smem = Lay::smem_bytes();
+  if (SPLIT && A.smem_pad > 0 && smem + (size_t)A.smem_pad <= 200 * 1024) smem += (size_t)A.smem_pad;
   long long grid;
   if (YMODE) grid = (long long)A.ngroups * ((A.lines_per_group + 2 * Cfg::G - 1) / (2 * Cfg::G));
   else {
@@ -97,9 +100,9 @@ static int r2r2_launch(const R2Args<T>& A, bool fwd, cudaStream_t st) {
 #define CB_R2_LAUNCH(KERNEL, KIND_)                                                                        \
   case KIND_:                                                                                              \
     if constexpr (YMODE) {                                                                                 \
-      if (!full) return r2r2_launch_kernel(KERNEL<T, Cfg, YMODE, SPLIT, KIND_, false>, &A, g, b, smem, st); \
+      if (!full) return r2r2_launch_kernel(KERNEL<T, Cfg, YMODE, SPLIT, KIND_, false>, &A, g, b, smem, st, SPLIT); \
     }                                                                                                      \
-    return r2r2_launch_kernel(KERNEL<T, Cfg, YMODE, SPLIT, KIND_, true>, &A, g, b, smem, st);
+    return r2r2_launch_kernel(KERNEL<T, Cfg, YMODE, SPLIT, KIND_, true>, &A, g, b, smem, st, SPLIT);
   switch (A.kind) {
     CB_R2_LAUNCH(r2r2_fwd_kernel, K_R2HC)
     CB_R2_LAUNCH(r2r2_fwd_kernel, K_REDFT10)

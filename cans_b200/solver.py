@@ -128,11 +128,12 @@ class Context:
         check(lib.cansb200_ctx_set(self._h, 10, int(windows)), "ctx_set")
         check(lib.cansb200_ctx_set(self._h, 11, int(thomas_ctas)), "ctx_set")
 
-    def set_dist_mode(self, mode: int = -1, chunks: int = -1):
+    def set_dist_mode(self, mode: int = -1, chunks: int = -1, split_pad_kb: int = -1):
         """Several ranks: 0 = the producing kernels store straight into the peers' buffers, 1 = dense local send blocks moved
         by the copy engines (z chunks forward, x windows back), -1 = auto."""
         check(lib.cansb200_ctx_set(self._h, 12, int(mode)), "ctx_set")
         check(lib.cansb200_ctx_set(self._h, 13, int(chunks)), "ctx_set")
+        check(lib.cansb200_ctx_set(self._h, 14, int(split_pad_kb)), "ctx_set")
 
     def dist_status(self) -> int:
         st = C.c_int()

@@ -209,9 +209,12 @@ enum {
                                     the peers' buffers (pack + wire + unpack in one store; the kernel holds its SMs while NVLink drains);
                                     1 = the producing kernels write dense per-destination blocks locally and the copy engines move them
                                     (SMs are free for the HBM-only stages meanwhile, at the price of one more local write + read);
-                                    -1 = auto */
+                                    2 = peer stores as 0, but scheduled in two halves: z chunks forward (x transform of chunk c + 1 next to
+                                    the y transform of chunk c), x windows backward; -1 = auto */
   CANSB200_CTX_DIST_CHUNKS = 13,  /* copy-engine exchange: z chunks of the forward half (x transform of chunk c + 1 runs while chunk c is on
                                     the wire); -1 = auto */
+  CANSB200_CTX_DIST_SPLIT_PAD = 14, /* z-chunked forward half: KB of shared-memory padding per CTA of the y transforms that store to the peers,
+                                    so that they leave room on every SM for the x transform of the next chunk; -1 = auto, 0 = none */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
                                     bit 2 = force the maximum shared-memory carveout (default: the driver picks, which leaves L1 to the twiddles) */
 };

@@ -129,10 +129,17 @@ def test_virtual_ranks_copy_engines(cb, name, P):
     _run_virtual_ranks(cb, name, P, -1, mode=1)
 
 
+@pytest.mark.parametrize("name", sorted(cases.DIST_CASES))
+def test_virtual_ranks_two_halves(cb, name):
+    """CANSB200_CTX_DIST_MODE = 2: peer stores, z chunks forward (y transforms padded to one CTA per SM), x windows back"""
+    _run_virtual_ranks(cb, name, 3 if "fp32" not in name else 2, -1, mode=2)
+
+
 @pytest.mark.parametrize("windows,chunks", [(1, 1), (2, 3), (8, 8)])
 def test_virtual_ranks_copy_engines_shapes(cb, windows, chunks):
     _run_virtual_ranks(cb, "duct_128x64x96", 4, windows, mode=1, chunks=chunks)
     _run_virtual_ranks(cb, "uneven_64x64x70", 3, windows, mode=1, chunks=chunks)
+    _run_virtual_ranks(cb, "uneven_64x64x70", 2, windows, mode=2, chunks=chunks)
 
 
 def test_missing_rank_is_reported(cb):
