@@ -16,13 +16,14 @@ MEM_HOST, MEM_DEVICE = 0, 1
 
 class Options(C.Structure):
     _fields_ = [("thomas_variant", C.c_int), ("cache_slots", C.c_int), ("fft_x_lines", C.c_int),
-                ("fft_y_lines", C.c_int), ("exchange", C.c_int), ("lambda_order", C.c_int), ("reserved", C.c_int * 10)]
+                ("fft_y_lines", C.c_int), ("exchange", C.c_int), ("lambda_order", C.c_int), ("pivot_dedup", C.c_int),
+                ("reserved", C.c_int * 9)]
 
     def __init__(self, **kw):
         super().__init__()
         for name, _ in self._fields_[:-1]:
             setattr(self, name, kw.pop(name, -1))
-        for i in range(10):
+        for i in range(9):
             self.reserved[i] = -1
         if kw:
             raise TypeError(f"unknown option(s): {sorted(kw)}")
@@ -46,6 +47,10 @@ SYMBOLS = {
     "cansb200_solve": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, _VP, C.c_int, _VP]),
     "cansb200_solve_z": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, C.c_int, _VP]),
     "cansb200_solve_z_bc": (C.c_int, [_VP, C.c_char_p, C.c_char, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, C.c_int, _VP]),
+    "cansb200_fftini": (C.c_int, [_VP, C.c_char_p, C.c_char_p, _D3, C.POINTER(C.c_int)]),
+    "cansb200_fftend": (C.c_int, [_VP, C.c_int]),
+    "cansb200_solver": (C.c_int, [_VP, C.c_int, C.c_char_p, C.c_char_p, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, _VP, C.c_int,
+                                  C.c_int, _VP]),
     "cansb200_plan_id": (C.c_int, [_VP]),
     "cansb200_plan_from_id": (_VP, [C.c_int]),
     "cansb200_updt_rhs_b": (C.c_int, [_VP, C.c_char_p, C.c_char_p, _I3, _I3, _I3, _D3, C.c_double, _VP, _VP]),

@@ -111,13 +111,18 @@ __host__ __device__ inline int pack_index(int h, int n) {
   const int k = n - h;                                 // imaginary part of mode k
   return (2 * k + 1 < n) ? 2 * k + 1 : 1;              // odd n: i[(n-1)/2] takes the slot r[n/2] has for even n
 }
-// out[j][i] = in[qy(j)][qx(i)] with q = pack_index in the directions flagged periodic-and-packed
+// halfcomplex position of position `pos` of the SPLIT order (r0 .. r[n/2-1] | r[n/2], i1 .. i[n/2-1]; CB_R2_XSPLIT)
+__host__ __device__ inline int split_to_hc(int pos, int n) { return 2 * pos <= n ? pos : n - (pos - n / 2); }
+// out[j][i] = in[qy(j)][qx(i)]: the eigenvalues in the order the kernels keep the spectrum in (x: split order when sx, else
+// halfcomplex; y: halfcomplex), gathered from the caller's order (px / py: packed in that direction, else halfcomplex)
 template <class T>
-__global__ void lambda_unpack_kernel(const T* __restrict__ in, T* __restrict__ out, int nx, int ny, int px, int py) {
+__global__ void lambda_unpack_kernel(const T* __restrict__ in, T* __restrict__ out, int nx, int ny, int px, int py, int sx) {
   const long long tot = (long long)nx * ny;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(e / nx), i = (int)(e - (long long)j * nx);
-    const int qi = px ? pack_index(i, nx) : i, qj = py ? pack_index(j, ny) : j;
+    int qi = sx ? split_to_hc(i, nx) : i;
+    qi = px ? pack_index(qi, nx) : qi;
+    const int qj = py ? pack_index(j, ny) : j;
     out[e] = in[(long long)qj * nx + qi];
   }
 }

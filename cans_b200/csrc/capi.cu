@@ -116,6 +116,10 @@ struct cansb200_ctx {
   DevBuf lam_perm;  // lambdaxy brought from the _OPENACC (packed) order to halfcomplex order (CANSB200 option lambda_order = 1)
   DevBuf ytab_fwd_pk, ytab_bwd_pk;   // row tables of the distributed y transforms when the y rows are dealt out in packed order
   bool tabs_pk = false;
+  // fftini records (cansb200_fftini): the reference's fftini sees the x / y boundary conditions only; the z variant of the
+  // plan is known at the first `solver` call, so the real plan is created then, one per (record, z BCs, c_or_f(3))
+  struct FftiniRec { char bcxy[4]; char cf[2]; bool live; std::map<std::string, cansb200_plan*> byz; };
+  std::vector<FftiniRec> fftini_recs;
   std::map<std::string, cansb200_plan*> zplans;   // z-only plans created on demand by cansb200_solve_z_bc, keyed by bcz + c_or_f(3)
   std::map<int, FftTables<double>> tabs64;
   std::map<int, FftTables<float>> tabs32;
@@ -137,6 +141,7 @@ struct cansb200_ctx {
   unsigned long long seq = 0;                  // sequence number of the distributed solves = value of every flag of a solve
   int* dist_status = nullptr;                  // host-mapped word set by a device-side wait that timed out
   int* dist_status_dev = nullptr;              // its device-resident twin
+  int* pinned_word = nullptr;                  // page-locked scratch word for the rare device -> host read-backs
   int dist_windows = -1;                       // x windows of the pipelined exchange (-1 = auto: up to 4)
   int dist_thomas_ctas = -1;                   // CTAs of the tridiagonal kernel while it shares the GPU with the y transforms (-1 = auto)
   int dist_mode = -1;                          // exchange flavour: 0 = stores of the producing kernels, 1 = copy engines, -1 = auto
@@ -157,6 +162,7 @@ struct cansb200_ctx {
   std::vector<cudaEvent_t> aux_done;
   cudaEvent_t fork_ev = nullptr;
   unsigned long long launches = 0;
+  int cur_xsplit = 0;                           // set for the duration of a solve whose plan keeps x in split order (CB_R2_XSPLIT)
   int cta_cap = 0;                              // > 0: the persistent tridiagonal kernel uses at most this many CTAs (pipelined exchange)
   int nplans = 0;                               // live plans (some switches are only legal before the first one)
   // host-memory mode: the z planes travel in chunks on two copy streams so that the x / y transforms of a chunk
@@ -191,6 +197,8 @@ struct cansb200_plan {
   // thomas
   int th_n, th_nn, th_m, th_variant, th_mmax, th_cols, th_cl, nslots;
   long long slot_z, slot_den;
+  int dx = 0, dy = 0, nxu = 0, nyu = 0;   // pivot-cache deduplication (ThomasDev::dx ..): decided at plan creation, verified at the first solve
+  bool sym_checked = false;
   DevBuf zcache, p2cache, dencache, state;
   DevBuf dtdma_big, dtdma_small;   // distributed-TDMA coefficients (Z, AA, CC) and reduced system (cansb200_gaussel_dtdma)
   unsigned long long solves = 0;
@@ -350,7 +358,7 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
       A.mak = rt->mak;
       A.row_tab = (const R2Row<T>*)g.row_tab;
       A.x0 = g.x0; A.g0 = g.g0; A.smem_pad = g.smem_pad;
-      A.flags = ctx->r2_flags & 3;
+      A.flags = (ctx->r2_flags & 3) | ((!g.ymode && ctx->cur_xsplit) ? CB_R2_XSPLIT : 0);
       cb::g_r2_default_carveout = (ctx->r2_flags & 4) ? 0 : 1;
       const int rc = !g.ymode ? r2r2_run<T, false, false>(A, nt, var, kind_is_forward(kind), st)
                      : g.row_tab ? r2r2_run<T, true, true>(A, nt, var, kind_is_forward(kind), st)
@@ -364,6 +372,9 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
     }
   }
   if (g.row_tab) return fail(CANSB200_EUNSUPPORTED, "r2r: the distributed solve needs a fast-path y length (64..2048, 2^k or 3*2^k)");
+  if (!g.ymode && ctx->cur_xsplit)
+    return fail(CANSB200_EINVAL, "r2r: the plan keeps x in split order (pivot_dedup), which only the fast x transforms write; "
+                                 "set CANSB200_CTX_FORCE_GENERIC before creating plans");
   FftTables<T>* tb;
   int rc = get_tables<T>(ctx, nt, &tb);
   if (rc) return rc;
@@ -434,6 +445,7 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   D.nx = nx; D.ny = ny; D.n = n_rows; D.periodic = periodic; D.nn = periodic ? n_rows - 1 : n_rows;
   D.sj = sj; D.sk = sk; D.a = a; D.b = b; D.c = c; D.lam = lam; D.lam_sj = nx;
   D.m = pl->th_m; D.chunk_layout = 2; D.xb = 0; D.xn = nx; D.out_rows = nullptr; D.nopin = 0;
+  D.dx = pl->dx; D.dy = pl->dy; D.nxu = pl->nxu; D.nyu = pl->nyu;
   return D;
 }
 
@@ -477,12 +489,12 @@ static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p
                             const CUtensorMap** mp, const CUtensorMap** mz) {
   if (!pl->use_tma || D.nx < box_cols) return false;
   const size_t esz = sizeof(T);
-  const unsigned long long zkey[4] = {(unsigned long long)(uintptr_t)pl->zcache.p, (unsigned long long)D.nx, (unsigned long long)D.ny,
+  const unsigned long long zkey[4] = {(unsigned long long)(uintptr_t)pl->zcache.p, (unsigned long long)D.nxu, (unsigned long long)D.nyu,
                                       ((unsigned long long)D.nn << 20) | (unsigned long long)box_rows};
   if (memcmp(zkey, pl->map_z_key, sizeof(zkey)) != 0) {
     // pivot cache z[slot][j][k][i]: tensor (x, row, y, slot)
-    const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.nn, (cuuint64_t)D.ny, (cuuint64_t)pl->nslots};
-    const cuuint64_t st[3] = {(cuuint64_t)D.nx * esz, (cuuint64_t)D.nx * D.nn * esz, (cuuint64_t)pl->slot_z * esz};
+    const cuuint64_t dims[4] = {(cuuint64_t)D.nxu, (cuuint64_t)D.nn, (cuuint64_t)D.nyu, (cuuint64_t)pl->nslots};
+    const cuuint64_t st[3] = {(cuuint64_t)D.nxu * esz, (cuuint64_t)D.nxu * D.nn * esz, (cuuint64_t)pl->slot_z * esz};
     if (!encode_tile_map(&pl->map_z, pl->zcache.p, esz, 4, dims, st, box_rows, box_cols, true)) { pl->use_tma = false; return false; }
     memcpy(pl->map_z_key, zkey, sizeof(zkey));
   }
@@ -566,21 +578,70 @@ static int launch_pipe_sel(cansb200_ctx* ctx, const ThomasDev<T>& D, cansb200_pl
   return launch_pipe<T, MMAX, false, CB_TH_LD_ELEM, COLS, CL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
 }
 
-// pivot cache: content hash of (a, b, c, lambda) -> slot select -> factorisation on a miss
-template <class T> static int gaussel_prepare(cansb200_plan* pl, const ThomasDev<T>& D, cudaStream_t st) {
+// sizes of the pivot cache for the plan's deduplication flags
+static void plan_cache_extents(cansb200_plan* pl) {
   cansb200_ctx* ctx = pl->ctx;
-  CacheState* cs = (CacheState*)pl->state.p;
-  const long long ncol = (long long)D.nx * D.ny;
-  const long long total = 3LL * D.n + ncol;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 592) blocks = 592;
-  thomas_hash_kernel<T><<<blocks, 256, 0, st>>>(D, cs);
-  thomas_select_kernel<<<1, 32, 0, st>>>(cs);
-  thomas_factor_kernel<T><<<(unsigned)((ncol + 127) / 128), 128, 0, st>>>(D, cs, (T*)pl->zcache.p, (T*)pl->p2cache.p,
-                                                                        (T*)pl->dencache.p, pl->slot_z, pl->slot_den);
-  ctx->launches += 3;
-  CK(cudaGetLastError());
+  const int nx = ctx->n_z[0], ny = ctx->n_z[1];
+  pl->nxu = pl->dx ? nx / 2 + pl->th_cols : nx;
+  pl->nyu = pl->dy ? ny / 2 + 1 : ny;
+  pl->slot_z = (long long)pl->nxu * pl->nyu * pl->th_nn;
+  pl->slot_den = (long long)pl->nxu * pl->nyu;
+}
+static int plan_cache_alloc(cansb200_plan* pl) {
+  cansb200_ctx* ctx = pl->ctx;
+  plan_cache_extents(pl);
+  if (!ctx->dtdma && pl->zcache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan: pivot cache");
+  if (pl->periodic_z && !ctx->dtdma) {
+    if (pl->p2cache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan: p2 cache");
+    if (pl->dencache.ensure((size_t)pl->slot_den * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan: den cache");
+  }
+  if (pl->state.ensure(sizeof(CacheState))) return fail(CANSB200_ENOMEM, "plan: cache state");
+  CacheState cs;
+  memset(&cs, 0, sizeof(cs));
+  cs.nslots = pl->nslots;
+  CK(cudaMemcpy(pl->state.p, &cs, sizeof(cs), cudaMemcpyHostToDevice));
   return 0;
+}
+
+// pivot cache: content hash of (a, b, c, lambda) -> slot select -> factorisation on a miss
+template <class T> static int gaussel_prepare(cansb200_plan* pl, ThomasDev<T>& D, cudaStream_t st) {
+  cansb200_ctx* ctx = pl->ctx;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CacheState* cs = (CacheState*)pl->state.p;
+    const long long nlam = (long long)D.nx * D.ny;
+    const long long total = 3LL * D.n + nlam;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    thomas_hash_kernel<T><<<blocks, 256, 0, st>>>(D, cs);
+    ctx->launches++;
+    if ((D.dx | D.dy) && !pl->sym_checked) {
+      // The deduplicated cache assumes lambda(i) = lambda(nx - i) (it is, for the eigenvalues initsolver builds).  The hash
+      // kernel checks every element on every solve; the FIRST solve of a plan reads the verdict back (one host sync, like
+      // the first-use allocations) and, if the caller's lambdaxy is not symmetric, falls back to the full-size cache.
+      // (page-locked destination: a pageable one may synchronise the whole device, and other streams may hold device-side waits)
+      CK(cudaMemcpyAsync(ctx->pinned_word, &cs->sym_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const int bad = *(volatile int*)ctx->pinned_word;
+      pl->sym_checked = true;
+      if (bad) {
+        pl->dx = pl->dy = 0;
+        pl->zcache.release(); pl->p2cache.release(); pl->dencache.release();
+        const int rc = plan_cache_alloc(pl);
+        if (rc) return rc;
+        memset(pl->map_z_key, 0, sizeof(pl->map_z_key));
+        D.dx = D.dy = 0; D.nxu = pl->nxu; D.nyu = pl->nyu;
+        continue;   // hash again without the flags
+      }
+    }
+    thomas_select_kernel<<<1, 32, 0, st>>>(cs);
+    const long long ncol_s = (long long)(D.dx ? D.nxu : D.nx) * (D.dy ? D.ny / 2 + 1 : D.ny);   // stored columns
+    thomas_factor_kernel<T><<<(unsigned)((ncol_s + 127) / 128), 128, 0, st>>>(D, cs, (T*)pl->zcache.p, (T*)pl->p2cache.p,
+                                                                              (T*)pl->dencache.p, pl->slot_z, pl->slot_den);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  return fail(CANSB200_ECUDA, "gaussel: pivot cache set-up failed");
 }
 
 // substitution on the column window D.xb .. D.xb + D.xn - 1
@@ -713,6 +774,10 @@ int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ip
   }
   const size_t nel = (size_t)c->n[0] * c->n[1] * c->n[2];
   if (c->scratch.ensure(nel * c->esz)) { delete c; return fail(CANSB200_ENOMEM, "init: scratch allocation failed"); }
+  if (cudaHostAlloc((void**)&c->pinned_word, 64, cudaHostAllocDefault) != cudaSuccess) {
+    c->scratch.release(); delete c;
+    return fail(CANSB200_ENOMEM, "init: pinned word");
+  }
   if (nranks > 1) {
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t nel_z = (size_t)c->n_z[0] * c->n_z[1] * c->n_z[2];
@@ -868,6 +933,7 @@ int cansb200_finalize(cansb200_ctx* c) {
     if (q != c->rank && c->peer[q] && !c->local_peers) cudaIpcCloseMemHandle(c->peer[q]);
   if (c->region) cudaFree(c->region);
   if (c->dist_status) cudaFreeHost(c->dist_status);
+  if (c->pinned_word) cudaFreeHost(c->pinned_word);
   if (c->dist_status_dev) cudaFree(c->dist_status_dev);
   c->sendb.release(); c->ytab_fwd_loc.release(); c->ytab_fwd_loc_pk.release(); c->ztab_loc.release();
   for (cudaStream_t q : c->dist_cs) if (q) cudaStreamDestroy(q);
@@ -879,6 +945,7 @@ int cansb200_finalize(cansb200_ctx* c) {
   c->ytab_fwd.release(); c->ytab_bwd.release(); c->ztab.release(); c->ytab_fwd_pk.release(); c->ytab_bwd_pk.release();
   c->lam_perm.release();
   { auto zp = c->zplans; c->zplans.clear(); for (auto& kv : zp) cansb200_plan_destroy(kv.second); }
+  for (auto& rec : c->fftini_recs) { for (auto& kv : rec.byz) cansb200_plan_destroy(kv.second); rec.byz.clear(); }
   for (cudaStream_t q : c->aux) cudaStreamDestroy(q);
   for (cudaEvent_t q : c->aux_done) cudaEventDestroy(q);
   if (c->fork_ev) cudaEventDestroy(c->fork_ev);
@@ -1054,19 +1121,22 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   if (!ctx->is_fp32) pl->th_mmax = (pl->th_cols == 16 && pl->th_cl == 1) ? (pl->th_m <= 4 ? 4 : 8) : (pl->th_m <= 6 ? 6 : 8);
   else pl->th_mmax = pl->th_cols == 16 ? 16 : (pl->th_cl == 1 ? (pl->th_m <= 8 ? 8 : 16) : (pl->th_m <= 12 ? 12 : 16));
   pl->nslots = o.cache_slots >= 1 ? (o.cache_slots > CB_MAX_SLOTS ? CB_MAX_SLOTS : o.cache_slots) : 1;
-  const long long ncol = (long long)ctx->n_z[0] * ctx->n_z[1];
-  pl->slot_z = ncol * pl->th_nn;
-  pl->slot_den = ncol;
-  if (!ctx->dtdma && pl->zcache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: pivot cache");
-  if (pl->periodic_z && !ctx->dtdma) {
-    if (pl->p2cache.ensure((size_t)pl->slot_z * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: p2 cache");
-    if (pl->dencache.ensure((size_t)pl->slot_den * pl->nslots * ctx->esz)) return fail(CANSB200_ENOMEM, "plan_create: den cache");
+  {
+    // pivot-cache deduplication: a periodic direction whose length is a whole number of tile pairs (x), an even number of
+    // rows held in full by this rank (y).  Off in distributed-TDMA mode (no pivot cache at all).
+    const int nxz = ctx->n_z[0], nyz = ctx->n_z[1];
+    // FP64 only: in FP32 the two halves of initsolver's eigenvalue array differ by up to 1e-3 relative (cancellation in
+    // 1 - cos), far above the 1e-5 parity bar.  Not for the sequential variant, which is kept bit-identical to the reference.
+    const bool on = o.pivot_dedup != 0 && !ctx->dtdma && variant != 0 && !ctx->is_fp32;
+    int radix[4];
+    const bool fastx = !ctx->force_generic && (ctx->is_fp32 ? r2r2_query<false, true>(nxz, 0, radix) : r2r2_query<false, false>(nxz, 0, radix)) > 0;
+    pl->dx = on && fastx && bc[0] == 'P' && bc[1] == 'P' && nxz >= 4 * wide && (nxz % (2 * wide)) == 0;
+    pl->dy = on && bc[2] == 'P' && bc[3] == 'P' && nyz == ctx->ng[1] && nyz >= 4 && (nyz % 2) == 0;
   }
-  if (pl->state.ensure(sizeof(CacheState))) return fail(CANSB200_ENOMEM, "plan_create: cache state");
-  CacheState cs;
-  memset(&cs, 0, sizeof(cs));
-  cs.nslots = pl->nslots;
-  CK(cudaMemcpy(pl->state.p, &cs, sizeof(cs), cudaMemcpyHostToDevice));
+  {
+    const int rc = plan_cache_alloc(pl.get());
+    if (rc) return rc;
+  }
   // build the transform tables now so that the first solve does not allocate
   for (int d = 0; d < 2; ++d) {
     int rc;
@@ -1126,7 +1196,7 @@ int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
   if (!pl || !stats) return fail(CANSB200_EINVAL, "null argument");
   CacheState cs;
   CK(cudaMemcpy(&cs, pl->state.p, sizeof(cs), cudaMemcpyDeviceToHost));
-  stats[0] = pl->solves; stats[1] = cs.nfactor; stats[2] = pl->ctx->launches; stats[3] = (unsigned long long)pl->th_variant;
+  stats[0] = pl->solves; stats[1] = cs.nfactor; stats[2] = pl->ctx->launches; stats[3] = (unsigned long long)pl->th_variant | ((unsigned long long)pl->dx << 4) | ((unsigned long long)pl->dy << 5);
   return 0;
 }
 
@@ -1203,17 +1273,17 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     }
     sT = ctx->dist_sT; sB = ctx->dist_sB;
   }
+  // pivot-cache lookup (and factorisation on a miss) ahead of everything: it only needs the coefficients, and its one-time
+  // read-back (first solve of a plan) must not sit behind a wait for the peers
+  ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam, a, b, c);
+  D.out_rows = (const OutRow<T>*)ctx->ztab.p;
+  rc = gaussel_prepare<T>(pl, D, st);
+  if (rc) return rc;
   prof_mark(ctx, st);
   R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nzl, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
   if (rc) return rc;
   prof_mark(ctx, st);
-  ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam, a, b, c);
-  D.out_rows = (const OutRow<T>*)ctx->ztab.p;
-  if (W > 1) {
-    rc = gaussel_prepare<T>(pl, D, st);   // pivot-cache lookup (and factorisation on a miss) ahead of the pipeline
-    if (rc) return rc;
-  }
   const int ww = nx / W;
   // while the tridiagonal kernel shares the GPU with the y transforms of the neighbouring windows it must not take every
   // SM (one of its CTAs fills a whole SM): leave part of the machine to stages F and B
@@ -1239,8 +1309,6 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     // ---- stage T: tridiagonal solve on the window of my z pencil (nx, ny/P, nz); result rows go to the slabs
     if (W == 1) {
       prof_mark(ctx, st);
-      rc = gaussel_prepare<T>(pl, D, st);
-      if (rc) return rc;
       prof_mark(ctx, st);
     }
     if (pipelined) {
@@ -1649,15 +1717,20 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   // eigenvalues in the order of an _OPENACC-built initsolver (option lambda_order = 1): bring them to halfcomplex order.
   // Several ranks: x only -- the y rows are dealt out in packed order instead (build_dist_tables), so that the local
   // slice of lambdaxy means what it means in the reference.
+  struct XsplitGuard {
+    cansb200_ctx* c;
+    XsplitGuard(cansb200_ctx* c_, int v) : c(c_) { c->cur_xsplit = v; }
+    ~XsplitGuard() { c->cur_xsplit = 0; }
+  } xsplit_guard(ctx, pl->dx);
   const bool pk = pl->opt.lambda_order == 1;
   const bool pkx = pk && pl->bc[0] == 'P', pky = pk && pl->bc[2] == 'P';
   const bool pky_local = pky && (ctx->nranks == 1 || ctx->dtdma);
-  if (pkx || pky_local) {
+  if (pkx || pky_local || pl->dx) {
     const int lx = ctx->n_z[0], ly = ctx->n_z[1];
     if (ctx->lam_perm.ensure((size_t)lx * ly * sizeof(T))) return fail(CANSB200_ENOMEM, "solve: eigenvalue buffer");
     const long long tot = (long long)lx * ly;
     lambda_unpack_kernel<T><<<(unsigned)((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184), 256, 0, st>>>(lam, (T*)ctx->lam_perm.p, lx, ly,
-                                                                                                          pkx ? 1 : 0, pky_local ? 1 : 0);
+                                                                                                          pkx ? 1 : 0, pky_local ? 1 : 0, pl->dx);
     ctx->launches++;
     CK(cudaGetLastError());
     lam = (const T*)ctx->lam_perm.p;
@@ -1756,7 +1829,9 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   const R2RGeom gyb{(long long)nx * nz, nx, 1, 1, nx, (long long)nx * ny, nx, nz, ny, 1};
   // auto: two half-width windows on two streams; the windows' kernels overlap each other's ramp-up / ramp-down
   // (measured -3 % on C3; windows small enough to stay in L2 lose more to launch tails than they gain)
-  const int W = ctx->chain_cols >= 0 ? ctx->chain_cols : ((nx >= 1024 && (nx / 2) % 16 == 0) ? nx / 2 : 0);
+  // ... and with the deduplicated pivot cache one full-width tridiagonal launch is better: the tiles that share pivots run
+  // side by side and the sharing happens in L2 (C3: 3.90 ms against 3.97 with the two windows)
+  const int W = ctx->chain_cols >= 0 ? ctx->chain_cols : ((nx >= 1024 && (nx / 2) % 16 == 0 && !(pl->dx | pl->dy)) ? nx / 2 : 0);
   if (W > 0 && W < nx && thomas_is_pipelined(pl) && !ctx->profiling) {
     // ---- L2-resident chain over x windows, round-robin on auxiliary streams
     ThomasDev<T> D = make_thomas<T>(pl, nx, ny, zm ? (long long)nx * nz : (long long)nx, zm ? (long long)nx : (long long)nx * ny,
@@ -1918,15 +1993,15 @@ static int solve_z_impl(cansb200_plan* pl, void* p_any, const int n[3], double n
     const int nyl = ctx->n_z[1], nz = ctx->ng[2];
     T* Cz = (T*)((char*)ctx->region + ctx->off_C);
     const unsigned blocks = (unsigned)(ctx->num_sms * 8);
+    ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam0, a, b, c);
+    D.nopin = 1;
+    D.out_rows = (const OutRow<T>*)ctx->ztab.p;
+    rc = gaussel_prepare<T>(pl, D, st);   // ahead of the first wait for the peers (see solve_dist)
+    if (rc) return rc;
     slab_rows_copy_kernel<T><<<blocks, 256, 0, st>>>(pin, px, px * py, (const DistRow<T>*)ctx->ytab_fwd.p, nx, ny, nzl, 1);
     ctx->launches++;
     CK(cudaGetLastError());
     rc = dist_flag(ctx, CB_SLOT_BAR, seq, true, true, st);
-    if (rc) return rc;
-    ThomasDev<T> D = make_thomas<T>(pl, nx, nyl, nx, (long long)nx * nyl, pl->th_n, pl->periodic_z, lam0, a, b, c);
-    D.nopin = 1;
-    D.out_rows = (const OutRow<T>*)ctx->ztab.p;
-    rc = gaussel_prepare<T>(pl, D, st);
     if (rc) return rc;
     if (thomas_is_pipelined(pl)) {
       rc = gaussel_apply<T>(pl, D, Cz, (T)norm, st);
@@ -2007,6 +2082,68 @@ int cansb200_solve_z_bc(cansb200_ctx* ctx, const char bcz[2], char c_or_f_z, voi
     it = ctx->zplans.emplace(key, pl).first;
   }
   return cansb200_solve_z(it->second, p, n, nhalo, norm, a, b, c, mem_kind, stream);
+}
+
+// ---- the reference's own call sequence: fftini(ng,n_x,n_y,bcxy,c_or_f,arrplan,normfft) ... solver(n,ng,arrplan,normfft,
+// lambdaxy,a,b,c,bc,c_or_f,p) ... fftend(arrplan)   (src/fft.f90:25-36,211-217; src/solver_gpu.f90:34-49)
+int cansb200_fftini(cansb200_ctx* ctx, const char bcxy[4], const char c_or_f_xy[2], double* normfft_out, int* id_out) {
+  if (!ctx || !bcxy || !c_or_f_xy || !id_out) return fail(CANSB200_EINVAL, "fftini: null argument");
+  // validate and get normfft from a throw-away plan description (no allocation: only the kind table is evaluated)
+  double normfft = 1.0;
+  for (int d = 0; d < 2; ++d) {
+    const char b0 = bcxy[2 * d], b1 = bcxy[2 * d + 1], cf = c_or_f_xy[d];
+    if ((b0 != 'P' && b0 != 'D' && b0 != 'N') || (b1 != 'P' && b1 != 'D' && b1 != 'N') || (cf != 'c' && cf != 'f'))
+      return fail(CANSB200_EINVAL, "fftini: bad boundary condition / c_or_f");
+    if ((b0 == 'P') != (b1 == 'P')) return fail(CANSB200_EINVAL, "fftini: periodic BCs must come in pairs");
+    int kf, kb;
+    double n1, n2;
+    find_fft(b0, b1, cf, kf, kb, n1, n2);
+    const int ii = (b0 == 'D' && b1 == 'D' && cf == 'f') ? 1 : 0;
+    normfft *= n1 * (ctx->ng[d] + n2 - ii);
+  }
+  normfft = 1.0 / normfft;
+  if (normfft_out) *normfft_out = ctx->is_fp32 ? (double)(1.0f / (float)(1.0 / normfft)) : normfft;
+  cansb200_ctx::FftiniRec rec;
+  memcpy(rec.bcxy, bcxy, 4);
+  memcpy(rec.cf, c_or_f_xy, 2);
+  rec.live = true;
+  for (size_t i = 0; i < ctx->fftini_recs.size(); ++i)
+    if (!ctx->fftini_recs[i].live) { ctx->fftini_recs[i] = rec; *id_out = (int)i + 1; return 0; }
+  ctx->fftini_recs.push_back(rec);
+  *id_out = (int)ctx->fftini_recs.size();
+  return 0;
+}
+
+int cansb200_fftend(cansb200_ctx* ctx, int id) {
+  if (!ctx || id < 1 || id > (int)ctx->fftini_recs.size() || !ctx->fftini_recs[id - 1].live) return fail(CANSB200_EINVAL, "fftend: unknown id");
+  auto& rec = ctx->fftini_recs[id - 1];
+  for (auto& kv : rec.byz) cansb200_plan_destroy(kv.second);
+  rec.byz.clear();
+  rec.live = false;
+  return 0;
+}
+
+int cansb200_solver(cansb200_ctx* ctx, int id, const char bc[6], const char c_or_f[3], void* p, const int n[3], int nhalo,
+                    double normfft, const void* lambdaxy, const void* a, const void* b, const void* c, int lambda_order,
+                    int mem_kind, void* stream) {
+  if (!ctx || !bc || !c_or_f) return fail(CANSB200_EINVAL, "solver: null argument");
+  if (id < 1 || id > (int)ctx->fftini_recs.size() || !ctx->fftini_recs[id - 1].live) return fail(CANSB200_EINVAL, "solver: unknown fftini id");
+  auto& rec = ctx->fftini_recs[id - 1];
+  if (memcmp(rec.bcxy, bc, 4) != 0 || rec.cf[0] != c_or_f[0] || rec.cf[1] != c_or_f[1])
+    return fail(CANSB200_EINVAL, "solver: x / y boundary conditions differ from the ones fftini was called with");
+  const std::string key{bc[4], bc[5], c_or_f[2], (char)('0' + (lambda_order ? 1 : 0))};
+  auto it = rec.byz.find(key);
+  if (it == rec.byz.end()) {
+    cansb200_options o;
+    for (int* q = (int*)&o; q < (int*)(&o + 1); ++q) *q = -1;
+    o.cache_slots = 3;   // one per RK sub-step: the Helmholtz solves of a variable see three different alpha
+    o.lambda_order = lambda_order ? 1 : 0;
+    cansb200_plan* pl = nullptr;
+    const int rc = cansb200_plan_create(ctx, &pl, bc, c_or_f, &o, nullptr);
+    if (rc) return rc;
+    it = rec.byz.emplace(key, pl).first;
+  }
+  return cansb200_solve(it->second, p, n, nhalo, normfft, lambdaxy, a, b, c, mem_kind, stream);
 }
 
 int cansb200_updt_rhs_b(cansb200_ctx* ctx, const char cf[3], const char bc[6], const int n[3], const int is_bound[6],

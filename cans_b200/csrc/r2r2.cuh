@@ -79,6 +79,12 @@ __device__ __forceinline__ void st_cs(Cx<double>* p, Cx<double> v) { __stcs(rein
 __device__ __forceinline__ void st_cs(Cx<float>* p, Cx<float> v) { __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y)); }
 #define CB_R2_LD_NA 1   // R2Args::flags
 #define CB_R2_ST_CS 2
+// x transforms of a periodic direction inside the solve: the spectrum is kept in SPLIT order
+//   (r0, r1, .., r[n/2-1] | r[n/2], i1, .., i[n/2-1])      instead of FFTW's halfcomplex (r0, .., r[n/2], i[n/2-1], .., i1),
+// i.e. the imaginary part of mode k sits n/2 positions after its real part.  Nothing between the two x transforms cares
+// about the order (the eigenvalues are permuted to match), and the tridiagonal stage can then share the pivots of whole
+// 128-byte tiles between the two halves (ThomasDev::dx).
+#define CB_R2_XSPLIT 4
 
 // ---- register butterflies: forward sign, natural in, natural out --------------------------------
 template <class T> __device__ __forceinline__ void bf2(Cx<T>* a) {
@@ -603,7 +609,10 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
     if (!trig) {
       // A_k = (sx, dy) / 2, B_k = (sy, -dx) / 2 ; halfcomplex: re at k, im at N - k
       out_up.store(kc, T(0.5) * sx, T(0.5) * sy);
-      if (kpos) out_dn.store(kmc, T(0.5) * dy, T(-0.5) * dx);
+      if (kpos) {
+        if (!YMODE && (A.flags & CB_R2_XSPLIT)) out_up.store(N / 2 + kc, T(0.5) * dy, T(-0.5) * dx);   // N/2 + k
+        else out_dn.store(kmc, T(0.5) * dy, T(-0.5) * dx);                                               // N - k
+      }
     } else {
       const C cs = cx_ldg(mak_t + kc);
       const T xa = cs.x * sx + cs.y * dy, xb = cs.x * sy - cs.y * dx;
@@ -685,7 +694,7 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_bwd_kernel(c
       xm[m] = C{T(0), T(0)};
       if (!trig) {
         xk[m] = in_up.load(kc);
-        if (kpos) xm[m] = in_dn.load(kmc);
+        if (kpos) xm[m] = (!YMODE && (A.flags & CB_R2_XSPLIT)) ? in_up.load(N / 2 + kc) : in_dn.load(kmc);
       } else {
         xk[m] = rv ? in_dn.load(kmc - 1) : in_up.load(kc);               // N - 1 - k : k
         if (kpos) xm[m] = rv ? in_up.load(kc - 1) : in_dn.load(kmc);     // k - 1 : N - k   (X_N := 0)

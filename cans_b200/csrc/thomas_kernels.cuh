@@ -49,6 +49,16 @@ template <class T> struct ThomasDev {
   int chunk_layout;   // 2 = z[j][k][i] (the only layout, see zidx); kept for ABI stability of the struct
   int nopin;          // 1: the lambda-less variant of gaussel (src/solver.f90:168-188, :238-256; solver_gaussel_z):
                       // no singular-pivot pin, no tolerance test on the periodic closure
+  // Pivot-cache deduplication.  The pivots of column (i, j) depend on lambdaxy(i, j) only, and in a periodic direction the
+  // real and the imaginary part of a mode share their eigenvalue.
+  //   y (dy): rows are in halfcomplex order, lambda(j) = lambda(ny - j): the cache keeps rows j <= ny/2, row j > ny/2 uses ny - j.
+  //   x (dx): the solve keeps x in SPLIT order between the two x transforms (r0 .. r[n/2-1] | r[n/2], i1 .. i[n/2-1], see
+  //           CB_R2_XSPLIT in r2r2.cuh), so that position nx/2 + p holds the imaginary part of the mode whose real part sits
+  //           at p: whole 128-byte tiles pair up, in the same column order.  The cache keeps positions 0 .. nxu - 1 with
+  //           nxu = nx/2 + one tile (the tile at nx/2 starts with r[n/2] and is stored on its own); position i >= nxu uses
+  //           i - nx/2.
+  // A quarter of the cache (and of its HBM stream) for a doubly periodic operator.  nxu / nyu = stored extents.
+  int dx, dy, nxu, nyu;
 };
 
 // ---- exactly-rounded, never-contracted arithmetic ---------------------------
@@ -67,8 +77,13 @@ template <> __device__ __forceinline__ float eps_of<float>() { return 1.1920929e
 // Pivot-cache layout: z[j][k][i] (row pitch nx), so that the nn rows of one column tile sit in one window of
 // nn * nx elements (a 4 MB window on C3) instead of one row per field plane: the tile fetch then has the access
 // pattern of the y transforms for half of its bytes.
+template <class T> __device__ __forceinline__ int zux(const ThomasDev<T>& D, int i) { return (D.dx && i >= D.nxu) ? i - D.nx / 2 : i; }
+template <class T> __device__ __forceinline__ int zuy(const ThomasDev<T>& D, int j) { return (D.dy && 2 * j > D.ny) ? D.ny - j : j; }
 template <class T> __device__ __forceinline__ long long zidx(const ThomasDev<T>& D, int i, int j, int k) {
-  return ((long long)j * D.nn + k) * D.nx + i;
+  return ((long long)zuy(D, j) * D.nn + k) * D.nxu + zux(D, i);
+}
+template <class T> __device__ __forceinline__ long long zden(const ThomasDev<T>& D, int i, int j) {
+  return (long long)zuy(D, j) * D.nxu + zux(D, i);
 }
 
 // ---- factorisation cache bookkeeping (device resident) ----------------------
@@ -79,7 +94,8 @@ struct CacheState {
   unsigned long long stamp[CB_MAX_SLOTS];
   unsigned long long clock;
   unsigned long long nfactor;  // how many factorisations ran (diagnostic)
-  int sel, hit, nslots, pad;
+  int sel, hit, nslots;
+  int sym_bad;                 // deduplicated cache: lambdaxy was found NOT mirror-symmetric (sticky; the host falls back / reports)
 };
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
@@ -107,10 +123,19 @@ __global__ void thomas_hash_kernel(const ThomasDev<T> D, CacheState* st) {
       const long long q = e - 3 * ncoef;
       const long long j = q / D.nx, i = q - j * D.nx;
       v = D.lam[j * D.lam_sj + i];
+      if (D.dx | D.dy) {
+        // The deduplicated cache is only valid for a mirror-symmetric lambdaxy: check every element, every solve.  initsolver's
+        // eigenvalues are symmetric up to the rounding of cos(2 pi (n - l) / n) against cos(2 pi l / n): <= 2e-13 relative for
+        // n = 1024 (2e-11 for n = 2048, lowest modes); replacing lambda(n - l) by lambda(l) moves the solution of such a column
+        // by a third of that, i.e. <= 1e-14 of the field in relative L2 (measured against the oracle: tests).
+        const T u = D.lam[(long long)zuy(D, (int)j) * D.lam_sj + zux(D, (int)i)];
+        const T big = fabs(u) > fabs(v) ? fabs(u) : fabs(v);
+        if (fabs(u - v) > T(1e-10) * big) st->sym_bad = 1;
+      }
     }
     h += mix64(mix64((unsigned long long)e) ^ bits_of(v));
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) h += mix64(0x5EEDULL + (unsigned long long)D.nopin);
+  if (blockIdx.x == 0 && threadIdx.x == 0) h += mix64(0x5EEDULL + (unsigned long long)D.nopin + 2ULL * D.dx + 4ULL * D.dy);
   for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(&st->key_new, h);
 }
@@ -146,9 +171,11 @@ __global__ void __launch_bounds__(128) thomas_factor_kernel(const ThomasDev<T> D
   T* z = zbase + (long long)sel * slot_z;
   T* p2 = p2base ? p2base + (long long)sel * slot_z : nullptr;
   T* den_c = denbase ? denbase + (long long)sel * slot_den : nullptr;
+  // one thread per STORED column: all of them, or positions i < nxu (rows j <= ny/2) of a deduplicated direction
+  const int nxs = D.dx ? D.nxu : D.nx, nys = D.dy ? D.ny / 2 + 1 : D.ny;
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (col >= (long long)D.nx * D.ny) return;
-  const int j = (int)(col / D.nx), i = (int)(col - (long long)j * D.nx);
+  if (col >= (long long)nxs * nys) return;
+  const int j = (int)(col / nxs), i = (int)(col - (long long)j * nxs);
   const T lam = D.lam[(long long)j * D.lam_sj + i];
   const int nn = D.nn;
   const T one = T(1);
@@ -196,7 +223,7 @@ __global__ void __launch_bounds__(128) thomas_factor_kernel(const ThomasDev<T> D
   const T bl = add_rn(D.b[nn], lam);
   const T den = add_rn(add_rn(bl, t1), t2);
   const T tol = mul_rn(eps_of<T>(), fmax(fabs(bl), fabs(add_rn(t1, t2))));
-  den_c[col] = (!D.nopin && fabs(den) <= tol) ? T(0) : den;
+  den_c[zden(D, i, j)] = (!D.nopin && fabs(den) <= tol) ? T(0) : den;
 }
 
 // ---- sequential substitution, reference operation order ---------------------
@@ -224,7 +251,7 @@ __global__ void __launch_bounds__(128) thomas_seq_kernel(const ThomasDev<T> D, c
   }
   if (!D.periodic) return;
   const T* p2 = p2base + (long long)sel * slot_z;
-  const T den = denbase[(long long)sel * slot_den + col];
+  const T den = denbase[(long long)sel * slot_den + zden(D, i, j)];
   const T p_first = pc[0], p_last = pc[(long long)(nn - 1) * D.sk];
   T num = sub_rn(sub_rn(mul_rn(pc[(long long)nn * D.sk], norm), mul_rn(D.c[nn], p_first)), mul_rn(D.a[nn], p_last));
   const T pcl = (den == T(0)) ? T(0) : div_rn(num, den);
@@ -474,32 +501,53 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   }
   unsigned tile_phase = 0;
 
-  // tile -> (flat column of its first thread, live columns); the field itself may have a row pitch sj != nx
+  // tile number -> (row j of the z pencil, x tile).  Deduplicated cache on a full-width launch: the (up to four) tiles that
+  // share their pivots get consecutive tile numbers, so that neighbouring CTAs of the persistent grid fetch the same pivot
+  // tile at the same time -- one HBM read, the others hit L2.  y pairs in the order (0, ny/2), (1, ny-1), (2, ny-2), ...
+  const bool grouped = (D.dx | D.dy) && D.xb == 0 && D.xn == D.nx && (tiles_x & 1) == 0 && (!D.dy || (D.ny & 1) == 0);
+  auto decode = [&](int t, int& tj, int& ti) {
+    if (!grouped) { tj = t / tiles_x; ti = t - tj * tiles_x; return; }
+    int mx = 0, my = 0;
+    if (D.dx) { mx = t & 1; t >>= 1; }
+    if (D.dy) { my = t & 1; t >>= 1; }
+    const int ntu = D.dx ? tiles_x / 2 : tiles_x;
+    const int qy = t / ntu, tu = t - qy * ntu;
+    ti = mx ? tu + tiles_x / 2 : tu;
+    tj = !D.dy ? qy : (qy == 0 ? (my ? D.ny / 2 : 0) : (my ? D.ny - qy : qy));
+  };
+  // (flat column of the tile's first thread, live columns); the field itself may have a row pitch sj != nx
   // (the haloed array of solver_gaussel_z): its columns sit at pcol = col + tj (sj - nx)
   const long long pitch_extra = D.sj - D.nx;
-  auto tile_col0 = [&](int tile, int& ncols) -> long long {
-    const int tj = tile / tiles_x;
-    const int ti0 = (tile - tj * tiles_x) * COLS;
+  auto tile_col0 = [&](int tj, int ti, int& ncols) -> long long {
+    const int ti0 = ti * COLS;
     ncols = D.xn - ti0 < COLS ? D.xn - ti0 : COLS;
     return (long long)tj * D.nx + D.xb + ti0;
   };
-  auto tile_pshift = [&](int tile) -> long long { return (long long)(tile / tiles_x) * pitch_extra; };
+  // pivots of the tile whose first column is x0: stored row of the cache and first stored column (tiles never straddle nxu:
+  // both are multiples of the tile width)
+  auto ztile = [&](int tj, int x0, int& zx0) -> int {
+    zx0 = zux(D, x0);
+    return zuy(D, tj);
+  };
   // asynchronous copy of one tile of pivots and right-hand sides into [row][COLS]; rows >= nn and dead
   // columns are zero filled so that the chunk maps of padding rows are exact identities / zeros
-  auto prefetch = [&](int tile_i, long long col0, int ncols) {
+  auto prefetch = [&](int tj, int ti, long long col0, int ncols) {
+    const int x0 = D.xb + ti * COLS;
+    int zx0;
+    const int ju = ztile(tj, x0, zx0);
+    const long long pshift = (long long)tj * pitch_extra;
     if (TMA) {
       if (tid == 0) {
-        const int tj = tile_i / tiles_x;
-        const int x0 = D.xb + (tile_i - tj * tiles_x) * COLS;
         fence_proxy_async();   // the generic-proxy reads of the previous tile are ordered before the async writes
         mbar_expect_tx(&tile_bar, (unsigned)(2u * nrows_tile * COLS * sizeof(T)));
         for (int r0 = 0; r0 < nrows_tile; r0 += box_rows) {
           tma_load_3d(ps + r0 * COLS, &map_p, &tile_bar, x0, tj, rbase + r0);
-          tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, x0, rbase + r0, tj, sel);
+          tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, zx0, rbase + r0, ju, sel);
         }
       }
       return;
     }
+    const T* zrow0 = zsel + (long long)ju * nn * D.nxu;   // stored row ju, k = 0
     if (VEC) {
       constexpr int PPR = COLS / VW;                // pieces per row
       for (int q = tid; q < nrows_tile * PPR; q += NT) {
@@ -507,8 +555,9 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         T* zd = zs + row * COLS + pc;
         T* pd = ps + row * COLS + pc;
         if (rbase + row < nn && pc < ncols) {
-          cp_async_16(zd, zsel + ((long long)(tile_i / tiles_x) * nn + rbase + row) * D.nx + (col0 - (long long)(tile_i / tiles_x) * D.nx) + pc);
-          cp_async_16(pd, p + (long long)(rbase + row) * sk + col0 + tile_pshift(tile_i) + pc);
+          const T* zr = zrow0 + (long long)(rbase + row) * D.nxu;
+          cp_async_16(zd, zr + zx0 + pc);
+          cp_async_16(pd, p + (long long)(rbase + row) * sk + col0 + pshift + pc);
         } else {
 #pragma unroll
           for (int e = 0; e < VW; ++e) { zd[e] = T(0); pd[e] = T(0); }
@@ -518,8 +567,8 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       for (int q = tid; q < nrows_tile * COLS; q += NT) {
         const int row = q / COLS, pc = q - row * COLS;
         if (rbase + row < nn && pc < ncols) {
-          cp_async_elem(zs + q, zsel + ((long long)(tile_i / tiles_x) * nn + rbase + row) * D.nx + (col0 - (long long)(tile_i / tiles_x) * D.nx) + pc);
-          cp_async_elem(ps + q, p + (long long)(rbase + row) * sk + col0 + tile_pshift(tile_i) + pc);
+          cp_async_elem(zs + q, zrow0 + (long long)(rbase + row) * D.nxu + zx0 + pc);
+          cp_async_elem(ps + q, p + (long long)(rbase + row) * sk + col0 + pshift + pc);
         } else {
           zs[q] = T(0);
           ps[q] = T(0);
@@ -532,9 +581,10 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   const int tstride = (int)gridDim.x / CL;
   int tile = (int)blockIdx.x / CL;
   if (tile >= ntiles) return;   // both CTAs of a cluster leave together
-  int ncols;
-  long long col0 = tile_col0(tile, ncols);
-  prefetch(tile, col0, ncols);
+  int ncols, tj, ti;
+  decode(tile, tj, ti);
+  long long col0 = tile_col0(tj, ti, ncols);
+  prefetch(tj, ti, col0, ncols);
   auto no_agg = [](int, T) {};
   unsigned xphase = 0;
   if (CL > 1) {
@@ -565,7 +615,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     const bool live = c < ncols;
     const int nrow = live ? nrow_full : 0;
     const long long col = col0 + c;
-    const long long pcol = col + tile_pshift(tile);
+    const long long pcol = col + (long long)tj * pitch_extra;
 
     // forward: y_k = (p_k norm - a_k y_{k-1}) z_k, chunk-local with y_{k0-1} := 0
     T yy = T(0), pi = T(1);
@@ -582,11 +632,12 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     sP[c * LD + g] = pi;
     __syncthreads();   // every thread holds its tile values in registers: the tile buffers are free again
     const int tnext = tile + tstride;
-    int ncols_n = 0;
+    int ncols_n = 0, tj_n = 0, ti_n = 0;
     long long col0_n = 0;
     if (tnext < ntiles) {
-      col0_n = tile_col0(tnext, ncols_n);
-      prefetch(tnext, col0_n, ncols_n);
+      decode(tnext, tj_n, ti_n);
+      col0_n = tile_col0(tj_n, ti_n, ncols_n);
+      prefetch(tj_n, ti_n, col0_n, ncols_n);
     }
     T vin;
     if (CL == 1) {
@@ -668,31 +719,30 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       if (g == 0) {
         T pcl = T(0);
         if (live) {
-          const T den = denbase[(long long)sel * slot_den + col];
+          const T den = denbase[(long long)sel * slot_den + zden(D, (int)(col - (long long)tj * D.nx), tj)];
           const T pnn = p[(long long)nn * sk + pcol];
           const T num = sub_rn(sub_rn(mul_rn(pnn, norm), mul_rn(D.c[nn], sY[c])), mul_rn(D.a[nn], sY[COLS + c]));
           pcl = (den == T(0)) ? T(0) : div_rn(num, den);
-          if (D.out_rows) D.out_rows[nn].ptr[(long long)(tile / tiles_x) * D.out_rows[nn].sj + (col - (long long)(tile / tiles_x) * D.nx)] = pcl;
+          if (D.out_rows) D.out_rows[nn].ptr[(long long)tj * D.out_rows[nn].sj + (col - (long long)tj * D.nx)] = pcl;
           else p[(long long)nn * sk + pcol] = pcl;
         }
         sP[c] = pcl;
       }
       __syncthreads();
       const T pcl = sP[c];
-      const long long tjp = tile / tiles_x;
-      const T* p2c = p2base + (long long)sel * slot_z + (tjp * nn + k0) * D.nx + (col - tjp * D.nx);
+      const T* p2c = p2base + (long long)sel * slot_z + zidx(D, live ? (int)(col - (long long)tj * D.nx) : 0, tj, k0);
 #pragma unroll
       for (int r = 0; r < MMAX; ++r)
-        if (r < nrow) y[r] = fma(p2c[(long long)r * D.nx], pcl, y[r]);
+        if (r < nrow) y[r] = fma(p2c[(long long)r * D.nxu], pcl, y[r]);
     }
     if (D.out_rows) {
       const OutRow<T>* rows = D.out_rows + k0;
-      const long long tj = tile / tiles_x, xi = col - tj * D.nx;
+      const long long xi = col - (long long)tj * D.nx;
 #pragma unroll
       for (int r = 0; r < MMAX; ++r)
         if (r < nrow) {
           const longlong2 e = __ldg(reinterpret_cast<const longlong2*>(rows + r));
-          reinterpret_cast<T*>(e.x)[tj * e.y + xi] = y[r];
+          reinterpret_cast<T*>(e.x)[(long long)tj * e.y + xi] = y[r];
         }
     } else {
       T* pc = p + (long long)k0 * sk + pcol;
@@ -708,6 +758,8 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
     }
     col0 = col0_n;
     ncols = ncols_n;
+    tj = tj_n;
+    ti = ti_n;
   }
   if (CL > 1) cluster_sync_all();   // leave together: a CTA's shared memory must outlive the peer's last hand-over
 }

@@ -238,7 +238,8 @@ class Plan:
     def stats(self):
         s = (C.c_ulonglong * 4)()
         check(lib.cansb200_plan_stats(self._h, s), "plan_stats")
-        return {"solves": s[0], "factorisations": s[1], "launches": s[2], "thomas_variant": s[3]}
+        return {"solves": s[0], "factorisations": s[1], "launches": s[2], "thomas_variant": s[3] & 15,
+                "pivot_dedup_x": (s[3] >> 4) & 1, "pivot_dedup_y": (s[3] >> 5) & 1}
 
     def destroy(self):
         if self._h:

@@ -56,7 +56,13 @@ typedef struct cansb200_options {
                            unchanged on an OpenACC host too.  On several ranks the rows of a periodic y direction are then
                            dealt out to the z pencils in packed order, i.e. lambdaxy(lo_z(1):hi_z(1), lo_z(2):hi_z(2)) means what
                            it means in the reference */
-  int reserved[10];
+  int pivot_dedup;      /* pivot cache of the tridiagonal stage: -1 / 1 (default) = keep one copy of the pivots of the columns that share
+                           their eigenvalue (the real and the imaginary part of a mode in a periodic direction: lambda(i) = lambda(n - i)),
+                           i.e. half of the cache and of its HBM stream per periodic direction (FP64, pipelined variants).  initsolver's
+                           two halves agree to rounding (<= 2e-11 relative), which moves the pressure by <= 1e-14 in relative L2; the
+                           symmetry of the caller's lambdaxy is verified on the device to 1e-10 (the first solve falls back to the
+                           full cache if it does not hold);  0 = always the full cache */
+  int reserved[9];
 } cansb200_options;
 
 /* -- context: replaces initmpi's cuDecomp setup (src/initmpi.f90:84-146), common_cudecomp.f90
@@ -121,6 +127,21 @@ int cansb200_solve_z(cansb200_plan* plan, void* p, const int n[3], int nhalo, do
 int cansb200_solve_z_bc(cansb200_ctx* ctx, const char bcz[2], char c_or_f_z, void* p, const int n[3], int nhalo, double norm,
                         const void* a, const void* b, const void* c, int mem_kind, void* stream);
 
+/* -- the reference's own call sequence, argument for argument (what fortran/solver_b200.f90 binds):
+ *      call fftini(ng,n_x,n_y,bcxy,c_or_f,arrplan,normfft)                      src/fft.f90:25-36
+ *      call solver(n,ng,arrplan,normfft,lambdaxy,a,b,c,bc,c_or_f,p)              src/solver_gpu.f90:34-49
+ *      call fftend(arrplan)                                                      src/fft.f90:211-217
+ *    fftini sees the x / y boundary conditions only (bcxy = {x0,x1,y0,y1}), so cansb200_fftini just records them and
+ *    returns normfft and a small positive integer id -- which fits arrplan(1,1) on every build of the reference, the CUDA
+ *    one included (`integer :: arrplan(2,2)`).  cansb200_solver creates the actual plan on first use, one per (id, z
+ *    boundary conditions, c_or_f(3)) with three pivot-cache slots, and solves.  lambda_order = 1 on an _OPENACC host
+ *    (cansb200_options::lambda_order). */
+int cansb200_fftini(cansb200_ctx* ctx, const char bcxy[4], const char c_or_f_xy[2], double* normfft_out, int* id_out);
+int cansb200_fftend(cansb200_ctx* ctx, int id);
+int cansb200_solver(cansb200_ctx* ctx, int id, const char bc[6], const char c_or_f[3], void* p, const int n[3], int nhalo,
+                    double normfft, const void* lambdaxy, const void* a, const void* b, const void* c, int lambda_order,
+                    int mem_kind, void* stream);
+
 /* -- integer names for plans.  On the reference's CUDA build `arrplan` is `integer, dimension(2,2)` (cuFFT handles:
  *    src/main.f90:94,107, src/fft.f90:31-35), not type(C_PTR): a 64-bit pointer does not fit one element.  The shim stores
  *    cansb200_plan_id(plan) (a small positive integer, unique per process while the plan lives) in arrplan(1,1) and gets
@@ -173,7 +194,8 @@ int cansb200_fill_hash(cansb200_ctx* ctx, void* p, const int n[3], const int lo[
 /* -- diagnostics */
 const char* cansb200_last_error(void);
 int cansb200_version(void);
-/* counters since plan creation: [0] solves, [1] factorisations run, [2] kernels launched */
+/* counters since plan creation: [0] solves, [1] factorisations run, [2] kernels launched (context-wide),
+ * [3] bits 0-3 tridiagonal variant in use, bit 4 / 5 pivot cache deduplicated in x / y (after the first solve's check) */
 int cansb200_plan_stats(cansb200_plan* plan, unsigned long long stats[4]);
 /* per-stage device timing with CUDA events on the solve's stream (the role of the reference's
  * unused timer_tic/toc CUDA-event pool, src/timer.f90:113-216).  Stages of one solve:

@@ -34,6 +34,17 @@ CASES = {
     "nz_257_periodic_tma": ([40, 4, 257], [1.0, 1.0, 1.0], [P, P, P], C3, 0.0, np.float64),
     "nz_1024_tma_cluster": ([32, 4, 1024], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float64),
     "fp32_nz_512_tma": ([32, 4, 512], [1.0, 1.0, 2.0], [P, P, N], C3, 2.0, np.float32),
+    # deduplicated pivot cache (periodic x with whole tile pairs and / or periodic y): mirrored tiles, y pairs, the
+    # periodic-z closure arrays (p2, den) under deduplication, 8-column tiles, the CTA-pair kernel, FP32 (32-column tiles)
+    "dedup_xy_64x32x48": ([64, 32, 48], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    "dedup_x_128x24x40": ([128, 24, 40], [12.0, 2.0, 2.0], [P, N, N], C3, 1.5, np.float64),
+    "dedup_y_40x32x36": ([40, 32, 36], [1.0, 1.0, 1.0], [N, P, D], C3, 1.0, np.float64),
+    "dedup_xyz_periodic_64x16x65": ([64, 16, 65], [6.2832] * 3, [P, P, P], C3, 0.0, np.float64),
+    "dedup_tma_96x8x256": ([96, 8, 256], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    "dedup_periodic_tma_64x6x257": ([64, 6, 257], [1.0, 1.0, 1.0], [P, P, P], C3, 0.0, np.float64),
+    "dedup_cluster_64x8x1024": ([64, 8, 1024], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64),
+    "dedup_8col_periodic_64x4x700": ([64, 4, 700], [1.0, 1.0, 1.0], [P, P, P], C3, 0.0, np.float64),
+    "fp32_dedup_128x16x256": ([128, 16, 256], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float32),
     # implicit-diffusion (Helmholtz) operators: face-centred in one direction, Dirichlet walls
     "helm_u_face_x": ([16, 12, 20], [1.0, 1.0, 1.0], [D, D, D], ["f", "c", "c"], 1.0, np.float64),
     "helm_v_face_y": ([16, 12, 20], [1.0, 1.0, 1.0], [P, D, D], ["c", "f", "c"], 1.0, np.float64),

@@ -59,11 +59,6 @@ def test_get_work_aliases(cb):
     assert len(set(ptrs)) == 3
     with pytest.raises(Exception):
         ctx.get_work(3)
-    # the buffers are real device memory of that size
-    t = torch.zeros(32 * 16 * 8, dtype=torch.float64, device=_dev())
-    import ctypes
-    cudart = ctypes.CDLL("libcudart.so.12") if False else None  # (no extra binding needed: a solve below uses buffer 0 itself)
-    del t, cudart
 
 
 @pytest.mark.parametrize("name", ["C2s_triperiodic", "C3s_channel", "C4s_duct", "odd_sizes", "prime_17x34", "periodic_z_odd"])
@@ -208,3 +203,46 @@ def test_helmholtz_wall_values_on_slabs(cb, nranks):
     assert all(c.dist_status() == 0 for c in ctxs)
     full = np.concatenate([t.cpu().numpy()[1:-1, 1:-1, 1:-1] for t in slabs], axis=0)
     assert cases.rel_l2(full, ref[1:-1, 1:-1, 1:-1]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["C3s_channel", "C4s_duct", "helm_w_face_z", "periodic_z_odd"])
+def test_reference_call_sequence(cb, name):
+    """fftini(ng,n_x,n_y,bcxy,c_or_f,arrplan,normfft) -> solver(n,ng,arrplan,normfft,lambdaxy,a,b,c,bc,c_or_f,p) ->
+    fftend(arrplan) with an INTEGER arrplan(1,1), exactly the three calls (and the argument lists) of the reference:
+    cansb200_fftini / cansb200_solver / cansb200_fftend through ctypes, as the Fortran shim binds them."""
+    import ctypes as C
+    from cans_b200._lib import lib, check, i3
+    cs = cases.build_case(name)
+    ng, cbc, cf = cs["ng"], cs["cbc"], cs["c_or_f"]
+    helm = name in cases.HELMHOLTZ
+    p = cases.make_rhs(cs)
+    ref = cases.oracle_solve(name, cs, p, helm)
+    ctx = cb.Context(ng)
+    bcxy = "".join(cbc[d][i] for d in range(2) for i in range(2)).encode()
+    nf, pid = C.c_double(), C.c_int()
+    check(lib.cansb200_fftini(ctx.handle, bcxy, "".join(cf[:2]).encode(), C.byref(nf), C.byref(pid)), "fftini")
+    assert pid.value >= 1 and nf.value == pytest.approx(float(cs["normfft"]), rel=1e-15)
+    dev = _dev()
+    lam, a, b, c = (torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (cs["lambdaxy"], cs["a"], cs["b"], cs["c"]))
+    normfft = nf.value
+    if helm:   # solve_helmholtz's own arithmetic (src/solve_helmholtz.f90:63-71) stays on the host side
+        alphai = 1.0 / cases.ALPHA
+        b = b + alphai
+        normfft = normfft * alphai
+    bc6 = "".join(cbc[d][i] for d in range(3) for i in range(2)).encode()
+    pd = torch.from_numpy(p.copy()).to(dev)
+    for _ in range(2):
+        pd.copy_(torch.from_numpy(p))
+        check(lib.cansb200_solver(ctx.handle, pid.value, bc6, "".join(cf).encode(), pd.data_ptr(), i3(ng), 1, normfft, lam.data_ptr(),
+                                  a.data_ptr(), b.data_ptr(), c.data_ptr(), 0, 1, torch.cuda.current_stream().cuda_stream), "solver")
+    torch.cuda.synchronize()
+    err = cases.parity_error(cs, pd.cpu().numpy()[1:-1, 1:-1, 1:-1], ref[1:-1, 1:-1, 1:-1], helm)
+    assert err < 1e-12, err
+    # x / y boundary conditions that differ from fftini's are refused, as is a dead id
+    bad = (b"NN" + bc6[2:]) if bc6[:2] != b"NN" else (b"DD" + bc6[2:])
+    assert lib.cansb200_solver(ctx.handle, pid.value, bad, "".join(cf).encode(), pd.data_ptr(), i3(ng), 1, normfft, lam.data_ptr(),
+                               a.data_ptr(), b.data_ptr(), c.data_ptr(), 0, 1, None) != 0
+    check(lib.cansb200_fftend(ctx.handle, pid.value), "fftend")
+    assert lib.cansb200_fftend(ctx.handle, pid.value) != 0
+    assert lib.cansb200_solver(ctx.handle, pid.value, bc6, "".join(cf).encode(), pd.data_ptr(), i3(ng), 1, normfft, lam.data_ptr(),
+                               a.data_ptr(), b.data_ptr(), c.data_ptr(), 0, 1, None) != 0
