@@ -2,10 +2,10 @@
  *
  * Drop-in boundary for the ONE hot path of CaNS: `solver` / `solver_gpu`
  * (reference /root/reference/src/solver.f90:17-112, src/solver_gpu.f90:34-276),
- * reused by `solve_helmholtz` (src/solve_helmholtz.f90:28-75).  A <=150-line
- * Fortran module (`fortran/solver_b200.f90`) named
- * `mod_solver_gpu` binds these symbols through ISO_C_BINDING so that
- * main.f90 / rk.f90 / mom.f90 / initsolver.f90 stay unchanged.
+ * reused by `solve_helmholtz` (src/solve_helmholtz.f90:28-75).  The Fortran
+ * modules of `fortran/solver_b200.f90` (mod_fft, mod_solver / mod_solver_gpu,
+ * mod_workspaces) bind these symbols through ISO_C_BINDING so that
+ * main.f90 / rk.f90 / mom.f90 / initsolver.f90 / solve_helmholtz.f90 stay unchanged.
  *
  * Conventions
  *  - every function returns 0 on success, a negative CANSB200_E* code otherwise,
