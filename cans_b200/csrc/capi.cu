@@ -201,6 +201,7 @@ struct cansb200_plan {
   bool sym_checked = false;
   DevBuf zcache, p2cache, dencache, state;
   DevBuf dtdma_big, dtdma_small;   // distributed-TDMA coefficients (Z, AA, CC) and reduced system (cansb200_gaussel_dtdma)
+  DevBuf dtdma_rows;               // ... gathered coefficient rows of all ranks, per cache slot (solve_dist_dtdma)
   unsigned long long solves = 0;
   // TMA descriptors of the pipelined substitution: pivots (per plan) and right-hand sides (per field pointer / shape)
   bool use_tma = true;
@@ -1158,7 +1159,7 @@ int cansb200_plan_destroy(cansb200_plan* pl) {
   }
   pl->ctx->nplans--;
   pl->zcache.release(); pl->p2cache.release(); pl->dencache.release(); pl->state.release();
-  pl->dtdma_big.release(); pl->dtdma_small.release();
+  pl->dtdma_big.release(); pl->dtdma_small.release(); pl->dtdma_rows.release();
   delete pl;
   return 0;
 }
@@ -1615,11 +1616,27 @@ static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double norm
     if (e < min_slot) min_slot = e;
   }
   if ((size_t)6 * P * ncol > min_slot) return fail(CANSB200_EUNSUPPORTED, "solve (dtdma): nz too small for the reduced-system buffer (needs nz >= 6 P^2)");
-  if (pl->dtdma_big.ensure(3 * ncol * (size_t)nloc * sizeof(T))) return fail(CANSB200_ENOMEM, "solve (dtdma): coefficient arrays");
-  if (pl->dtdma_small.ensure((size_t)(7 + 4 * P) * ncol * sizeof(T))) return fail(CANSB200_ENOMEM, "solve (dtdma): reduced system");
+  // coefficient cache: Z / AA / CC and the reduced coefficient rows per slot, keyed by the content of (a, b, c, lambda)
+  const int nslots = pl->nslots;
+  const size_t slot_big = 3 * ncol * (size_t)nloc, slot_small = 5 * ncol, slot_rows = 2 * (size_t)P * ncol;
+  if (pl->dtdma_big.ensure(slot_big * nslots * sizeof(T))) return fail(CANSB200_ENOMEM, "solve (dtdma): coefficient arrays");
+  if (pl->dtdma_small.ensure((slot_small * nslots + (2 + 4 * (size_t)P) * ncol) * sizeof(T))) return fail(CANSB200_ENOMEM, "solve (dtdma): reduced system");
+  if (pl->dtdma_rows.ensure(2 * slot_rows * nslots * sizeof(T))) return fail(CANSB200_ENOMEM, "solve (dtdma): gathered coefficient rows");
   T* A = (T*)ctx->scratch.p;
   T* G = (T*)((char*)ctx->region + ctx->off_C);
   T* pin = p + (px * py + px + 1);
+  const CacheState* cst = (const CacheState*)pl->state.p;
+  {
+    // content hash -> slot (the same device-side machinery as the pivot cache of the transposed solve)
+    ThomasDev<T> H = make_thomas<T>(pl, nx, ny, nx, (long long)nx * ny, nloc, 0, lam, a, b, c);
+    H.dx = H.dy = 0; H.nxu = nx; H.nyu = ny;
+    const long long total = 3LL * nloc + (long long)ncol;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    thomas_hash_kernel<T><<<blocks, 256, 0, st>>>(H, (CacheState*)pl->state.p);
+    thomas_select_kernel<<<1, 32, 0, st>>>((CacheState*)pl->state.p);
+    ctx->launches += 2;
+  }
   prof_mark(ctx, st);
   R2RGeom gx{1, 1, px, nx, px * py, (long long)nx * ny, ny, nzl, nx, 0};
   rc = run_r2r<T>(ctx, pl->kind[0][0], pl->nt[0], pin, A, gx, pl->opt.fft_x_lines, st);
@@ -1634,32 +1651,37 @@ static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double norm
   D.nx = nx; D.ny = ny; D.n = nloc; D.nranks = 1; D.periodic = 0;
   D.starts[0] = 0; D.starts[1] = nloc;
   D.a = a; D.b = b; D.c = c; D.lam = lam;
+  D.st = cst; D.slot_big = (long long)slot_big; D.slot_small = (long long)slot_small;
   T* big = (T*)pl->dtdma_big.p;
   D.Z = big; D.AA = big + ncol * nloc; D.CC = big + 2 * ncol * nloc;
   T* sm = (T*)pl->dtdma_small.p;
-  D.Z1 = sm;
-  D.ra = sm + ncol; D.rc = D.ra + 2 * ncol; D.rp = D.rc + 2 * ncol;
-  D.rcw = D.rp + 2 * ncol; D.rp2 = D.rcw + 2 * ncol * P;
+  D.Z1 = sm; D.ra = sm + ncol; D.rc = sm + 3 * ncol;
+  T* tail = sm + slot_small * nslots;
+  D.rp = tail; D.rcw = tail + 2 * ncol; D.rp2 = D.rcw + 2 * ncol * P;
   const unsigned cbk = (unsigned)((ncol + 127) / 128);
-  dtdma_coef_kernel<T><<<cbk, 128, 0, st>>>(D);
+  dtdma_coef_kernel<T><<<cbk, 128, 0, st>>>(D);   // returns at once on a cache hit
   prof_mark(ctx, st);
   dtdma_phase1_kernel<T><<<cbk, 128, 0, st>>>(D, A, (T)normfft);
   DtdmaPeers pp;
   for (int s = 0; s < CB_DTDMA_MAX_RANKS; ++s) pp.dst[s] = s < P ? (void*)((char*)ctx->peer[s] + ctx->off_C) : nullptr;
-  dtdma_gather_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(pp, r, P, (long long)ncol, D.ra, D.rc, D.rp);
+  dtdma_gather_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(pp, r, P, (long long)ncol, D.ra, D.rc, D.rp, cst, (long long)slot_small);
   ctx->launches += 3;
   CK(cudaGetLastError());
   rc = dist_flag(ctx, CB_SLOT_BAR, seq, true, true, st);
   if (rc) return rc;
   // reduced system of all ranks, solved redundantly on every rank; then my inner rows
+  T* GA = (T*)pl->dtdma_rows.p;
+  T* GC = GA + slot_rows * nslots;
+  dtdma_save_rows_kernel<T><<<ctx->num_sms * 2, 256, 0, st>>>(G, (long long)slot_rows, GA, GC, cst, (long long)slot_rows);
   DtdmaDev<T> R = D;
   R.nranks = P; R.periodic = pl->periodic_z;
-  R.ra = G; R.rc = G + 2 * (size_t)P * ncol; R.rp = G + 4 * (size_t)P * ncol;
+  R.ra = GA; R.rc = GC; R.slot_small = (long long)slot_rows;
+  R.rp = G + 4 * (size_t)P * ncol;
   dtdma_reduced_kernel<T><<<cbk, 128, 0, st>>>(R);
   DtdmaDev<T> F = D;
   F.rp = R.rp + 2 * (size_t)r * ncol;
   dtdma_phase3_kernel<T><<<ctx->num_sms * 8, 256, 0, st>>>(F, A);
-  ctx->launches += 2;
+  ctx->launches += 3;
   CK(cudaGetLastError());
   rc = dist_flag(ctx, CB_SLOT_BAR + 1, seq, true, true, st);   // nobody refills my gather buffer before I have read it
   if (rc) return rc;
@@ -1906,6 +1928,7 @@ static int gaussel_dtdma_impl(cansb200_plan* pl, T* pz, int nx, int ny, int n_ro
   D.nx = nx; D.ny = ny; D.n = n_rows; D.nranks = nsplit; D.periodic = periodic;
   for (int r = 0; r <= nsplit; ++r) D.starts[r] = starts[r];
   D.a = a; D.b = b; D.c = c; D.lam = lam;
+  D.st = nullptr; D.slot_big = 0; D.slot_small = 0;   // stage level: no coefficient cache
   T* big = (T*)pl->dtdma_big.p;
   D.Z = big; D.AA = big + ncol * n_rows; D.CC = big + 2 * ncol * n_rows;
   T* sm = (T*)pl->dtdma_small.p;

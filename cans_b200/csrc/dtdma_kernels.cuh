@@ -28,7 +28,15 @@ template <class T> struct DtdmaDev {
   T* Z;  T* AA; T* CC;                  // [k][j][i]: elimination pivots, and the couplings of row k to the rank's first / last row
   T* Z1;                                // [rank][j][i]: 1 / (1 - aa_2 cc_1) of the rank's first row
   T* ra; T* rc; T* rcw; T* rp; T* rp2;  // reduced system [2 P][j][i]: coefficients, work copy, right-hand side, periodic auxiliary
+  // Coefficient cache of the distributed solve (the reference keeps aa_z / cc_z between calls while the coefficients do not
+  // change: is_dtdma_update, src/solver_gpu.f90:571-591).  Z / AA / CC / Z1 / ra / rc are per cache slot; `st` is the plan's
+  // factorisation-cache state (content hash of a, b, c, lambda -> slot, hit / miss, all on the device): on a hit the
+  // coefficient kernel and the coefficient rows of the gather do nothing.  st = nullptr: no cache (stage-level entry point).
+  const CacheState* st;
+  long long slot_big, slot_small;       // elements between the slots of (Z, AA, CC) and of (Z1, ra, rc)
 };
+template <class T> __device__ __forceinline__ long long dtdma_sel_big(const DtdmaDev<T>& D) { return D.st ? (long long)D.st->sel * D.slot_big : 0; }
+template <class T> __device__ __forceinline__ long long dtdma_sel_small(const DtdmaDev<T>& D) { return D.st ? (long long)D.st->sel * D.slot_small : 0; }
 
 template <class T> __device__ __forceinline__ void dtdma_range(const DtdmaDev<T>& D, int r, int& k0, int& nl) {
   k0 = D.starts[r];
@@ -39,17 +47,19 @@ template <class T> __device__ __forceinline__ void dtdma_range(const DtdmaDev<T>
 // ---- coefficients: aa, cc of every row and the reduced coefficient rows (src/solver.f90:351-391 without p) ----
 template <class T>
 __global__ void __launch_bounds__(128) dtdma_coef_kernel(const DtdmaDev<T> D) {
+  if (D.st && D.st->hit) return;   // the slot already holds the coefficients of this (a, b, c, lambda)
   const long long ncol = (long long)D.nx * D.ny;
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (col >= ncol) return;
   const T lam = D.lam ? D.lam[col] : T(0);
   const T one = T(1);
+  const long long ob = dtdma_sel_big(D), os = dtdma_sel_small(D);
   for (int r = 0; r < D.nranks; ++r) {
     int k0, nl;
     dtdma_range(D, r, k0, nl);
-    T* Z = D.Z + (long long)k0 * ncol + col;
-    T* AA = D.AA + (long long)k0 * ncol + col;
-    T* CC = D.CC + (long long)k0 * ncol + col;
+    T* Z = D.Z + ob + (long long)k0 * ncol + col;
+    T* AA = D.AA + ob + (long long)k0 * ncol + col;
+    T* CC = D.CC + ob + (long long)k0 * ncol + col;
     const T *a = D.a + k0, *b = D.b + k0, *c = D.c + k0;
     for (int k = 0; k < 2; ++k) {
       const T zz = div_rn(one, add_rn(b[k], lam));
@@ -79,11 +89,11 @@ __global__ void __launch_bounds__(128) dtdma_coef_kernel(const DtdmaDev<T> D) {
     const T z1 = div_rn(one, sub_rn(one, mul_rn(aa1, cc0)));
     AA[0] = mul_rn(AA[0], z1);
     CC[0] = mul_rn(-mul_rn(cc0, cc1), z1);
-    D.Z1[(long long)r * ncol + col] = z1;
-    D.ra[(long long)(2 * r) * ncol + col] = AA[0];
-    D.ra[(long long)(2 * r + 1) * ncol + col] = AA[(long long)(nl - 1) * ncol];
-    D.rc[(long long)(2 * r) * ncol + col] = CC[0];
-    D.rc[(long long)(2 * r + 1) * ncol + col] = CC[(long long)(nl - 1) * ncol];
+    D.Z1[os + (long long)r * ncol + col] = z1;
+    D.ra[os + (long long)(2 * r) * ncol + col] = AA[0];
+    D.ra[os + (long long)(2 * r + 1) * ncol + col] = AA[(long long)(nl - 1) * ncol];
+    D.rc[os + (long long)(2 * r) * ncol + col] = CC[0];
+    D.rc[os + (long long)(2 * r + 1) * ncol + col] = CC[(long long)(nl - 1) * ncol];
   }
 }
 
@@ -93,11 +103,12 @@ __global__ void __launch_bounds__(128) dtdma_phase1_kernel(const DtdmaDev<T> D, 
   const long long ncol = (long long)D.nx * D.ny;
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (col >= ncol) return;
+  const long long ob = dtdma_sel_big(D), os = dtdma_sel_small(D);
   for (int r = 0; r < D.nranks; ++r) {
     int k0, nl;
     dtdma_range(D, r, k0, nl);
     T* pc = p + (long long)k0 * ncol + col;
-    const T* Z = D.Z + (long long)k0 * ncol + col;
+    const T* Z = D.Z + ob + (long long)k0 * ncol + col;
     const T *a = D.a + k0, *c = D.c + k0;
     T pv = mul_rn(mul_rn(pc[0], norm), Z[0]);
     pc[0] = pv;
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(128) dtdma_phase1_kernel(const DtdmaDev<T> D, 
     }
     // pv = p(2) of the Fortran
     const T cc0 = mul_rn(c[0], Z[0]);
-    const T p0 = mul_rn(sub_rn(pc[0], mul_rn(cc0, pc[ncol])), D.Z1[(long long)r * ncol + col]);
+    const T p0 = mul_rn(sub_rn(pc[0], mul_rn(cc0, pc[ncol])), D.Z1[os + (long long)r * ncol + col]);
     pc[0] = p0;
     D.rp[(long long)(2 * r) * ncol + col] = p0;
     D.rp[(long long)(2 * r + 1) * ncol + col] = pc[(long long)(nl - 1) * ncol];
@@ -131,8 +142,9 @@ __global__ void __launch_bounds__(128) dtdma_reduced_kernel(const DtdmaDev<T> D)
   const T one = T(1);
   const int nr = 2 * D.nranks;
   const int nn = D.periodic ? nr - 1 : nr;
-  const T* ra = D.ra + col;
-  const T* rc = D.rc + col;
+  const long long os = dtdma_sel_small(D);
+  const T* ra = D.ra + os + col;
+  const T* rc = D.rc + os + col;
   T* cw = D.rcw + col;
   T* rp = D.rp + col;
   cw[0] = rc[0];
@@ -183,6 +195,8 @@ template <class T>
 __global__ void dtdma_phase3_kernel(const DtdmaDev<T> D, T* p) {
   const long long ncol = (long long)D.nx * D.ny;
   const long long tot = ncol * D.n;
+  const T* AAs = D.AA + dtdma_sel_big(D);
+  const T* CCs = D.CC + dtdma_sel_big(D);
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(e / ncol);
     const long long col = e - (long long)k * ncol;
@@ -194,26 +208,42 @@ __global__ void dtdma_phase3_kernel(const DtdmaDev<T> D, T* p) {
     const int kl = k - k0;
     if (kl == 0) p[e] = pf;
     else if (kl == nl - 1) p[e] = pl;
-    else p[e] = sub_rn(sub_rn(p[e], mul_rn(D.AA[e], pf)), mul_rn(D.CC[e], pl));
+    else p[e] = sub_rn(sub_rn(p[e], mul_rn(AAs[e], pf)), mul_rn(CCs[e], pl));
   }
 }
 
 // ---- distributed: my two boundary rows of (aa, cc, p) into the gathered reduced system of EVERY rank ---------------
 // dst[s] = base of rank s's gather buffer [3][2 P][ncol] (peer mapped); my rows are 2 rank, 2 rank + 1
 struct DtdmaPeers { void* dst[CB_DTDMA_MAX_RANKS]; };
+// On a cache hit only the right-hand-side rows travel (the receivers kept the coefficient rows of that slot).
 template <class T>
 __global__ void dtdma_gather_kernel(DtdmaPeers peers, int rank, int nranks, long long ncol, const T* __restrict__ ra,
-                                    const T* __restrict__ rc, const T* __restrict__ rp) {
+                                    const T* __restrict__ rc, const T* __restrict__ rp, const CacheState* st, long long slot_small) {
   const long long per = 2 * ncol;                 // my two rows of one array
-  const long long tot = 3 * per * nranks;
+  const bool hit = st && st->hit;
+  const long long os = st ? (long long)st->sel * slot_small : 0;
+  const int narr = hit ? 1 : 3;
+  const long long tot = narr * per * nranks;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(e / (3 * per));
-    const long long w = e - (long long)s * 3 * per;
-    const int arr = (int)(w / per);
-    const long long o = w - (long long)arr * per;   // h * ncol + col
-    const T v = arr == 0 ? ra[o] : (arr == 1 ? rc[o] : rp[o]);
+    const int s = (int)(e / (narr * per));
+    const long long w = e - (long long)s * narr * per;
+    const int arr = hit ? 2 : (int)(w / per);
+    const long long o = hit ? w : w - (long long)arr * per;   // h * ncol + col
+    const T v = arr == 0 ? ra[os + o] : (arr == 1 ? rc[os + o] : rp[o]);
     T* g = reinterpret_cast<T*>(peers.dst[s]);
     g[((long long)arr * 2 * nranks + 2 * rank) * ncol + o] = v;
+  }
+}
+
+// after the gather of a cache miss: keep the coefficient rows of all ranks in the slot (ga, gc: [2 P][ncol] per slot)
+template <class T>
+__global__ void dtdma_save_rows_kernel(const T* __restrict__ G, long long n2p_ncol, T* __restrict__ ga, T* __restrict__ gc,
+                                       const CacheState* st, long long slot_rows) {
+  if (st->hit) return;
+  const long long os = (long long)st->sel * slot_rows;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n2p_ncol; e += (long long)gridDim.x * blockDim.x) {
+    ga[os + e] = G[e];
+    gc[os + e] = G[n2p_ncol + e];
   }
 }
 

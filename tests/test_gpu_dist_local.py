@@ -142,6 +142,57 @@ def test_virtual_ranks_copy_engines_shapes(cb, windows, chunks):
     _run_virtual_ranks(cb, "uneven_64x64x70", 2, windows, mode=2, chunks=chunks)
 
 
+@pytest.mark.parametrize("name,P", [("helm_w_64x64x64", 2), ("uneven_64x64x70", 2), ("helm_w_64x64x64", 3)])
+def test_virtual_ranks_distributed_tdma(cb, name, P):
+    """CANSB200_CTX_DTDMA (the reference's is_poisson_dtdma): z stays decomposed, only the reduced system travels; the
+    coefficient arrays are cached per coefficient set (the reference's is_dtdma_update / aa_z_save, src/solver_gpu.f90:571-591):
+    three solves with two different alpha must run the coefficient kernel twice, not three times."""
+    from cans_b200.decomp import SlabDecomp
+    ng, l, cbc, cf, gr, dt, helm = cases.DIST_CASES[name]
+    dev = torch.device("cuda:0")
+    cs = O.make_case(ng, l, cbc, c_or_f=cf, gr=gr, dtype=dt)
+    p = cases.make_rhs(cs)
+    q3 = 1 if (cf[2] == "f" and cbc[2][1] == "D") else 0
+    zs = SlabDecomp(ng, P, 0).zs
+    ctxs = [cb.Context(ng, rank=r, nranks=P) for r in range(P)]
+    cb.Context.connect_local(ctxs)
+    for c in ctxs:
+        c.set_dtdma(True)
+    sds = [cb.initsolver(c, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], cf, device=dev, cache_slots=2) for c in ctxs]
+    streams = [torch.cuda.Stream() for _ in range(P)]
+    slabs_h, slabs_d = [], []
+    for r in range(P):
+        z0, z1 = zs[r], zs[r + 1]
+        h = np.zeros((z1 - z0 + 2, ng[1] + 2, ng[0] + 2), dtype=dt)
+        h[1:-1] = p[1 + z0:1 + z1]
+        slabs_h.append(h)
+        slabs_d.append(torch.from_numpy(h).to(dev))
+    for alpha in (cases.ALPHA, 2.5 * cases.ALPHA, cases.ALPHA):
+        alphai = dt(1.0) / dt(alpha)
+        # oracle: the same stages with the distributed elimination on the global field
+        px = np.ascontiguousarray(p[1:-1, 1:-1, 1:-1])
+        O.fft(cs["arrplan"][0][0], px)
+        O.fft(cs["arrplan"][1][0], px)
+        O.gaussel_dtdma(zs, ng[2] - q3, cs["a"], (cs["b"] + alphai).astype(dt), cs["c"], cbc[2] == cases.P, dt(cs["normfft"]) * alphai, px,
+                        cs["lambdaxy"])
+        O.fft(cs["arrplan"][1][1], px)
+        O.fft(cs["arrplan"][0][1], px)
+        for r in range(P):
+            slabs_d[r].copy_(torch.from_numpy(slabs_h[r]))
+        torch.cuda.synchronize()
+        for r in range(P):
+            c, sd = ctxs[r], sds[r]
+            cb.solve_helmholtz(c.n, ng, c.hi(), sd.arrplan, sd.normfft, alpha, sd.lambdaxy, sd.a, sd.b, sd.c, None, None, None,
+                               c.is_bound(), cbc, cf, slabs_d[r], stream=streams[r])
+        torch.cuda.synchronize()
+        for r, c in enumerate(ctxs):
+            assert c.dist_status() == 0
+            got = slabs_d[r].cpu().numpy()[1:-1, 1:-1, 1:-1]
+            assert cases.rel_l2(got, px[zs[r]:zs[r + 1]]) < 1e-12
+    for sd in sds:
+        assert sd.arrplan.stats()["factorisations"] == 2, sd.arrplan.stats()
+
+
 def test_missing_rank_is_reported(cb):
     """A rank that never calls the collective solve: the device-side wait gives up (no GPU hang), the solve of the
     rank that did call returns normally in device mode (stream ordered, nothing is read back), and the NEXT call on
