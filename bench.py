@@ -36,6 +36,7 @@ WORKLOADS = {
     "C5_channel_2048x1024x1024": ([2048, 1024, 1024], [12.0, 6.0, 2.0], [["P", "P"], ["P", "P"], ["N", "N"]], 2.0),
     # diagnostic shape: at N = 2 every GPU sees the z pencil of C5 at N = 8 (2048 x 128 x 1024)
     "X_2048x256x1024": ([2048, 256, 1024], [12.0, 6.0, 2.0], [["P", "P"], ["P", "P"], ["N", "N"]], 2.0),
+    "T_smoke_128x64x96": ([128, 64, 96], [6.0, 3.0, 2.0], [["P", "P"], ["P", "P"], ["N", "N"]], 2.0),   # harness smoke tests only
     "C1_ldc_2x64x64": ([2, 64, 64], [0.03125, 1.0, 1.0], [["P", "P"], ["N", "N"], ["N", "N"]], 0.0),
 }
 METRIC = "poisson_solve_ns_per_gridpoint"
@@ -296,6 +297,13 @@ def main():
     ap.add_argument("--dist-chunks", type=int, default=-1, help="N > 1, copy engines: z chunks of the forward half (-1 auto)")
     ap.add_argument("--dist-split-pad", type=int, default=-1, help="N > 1, mode 2: KB of shared-memory padding of the forward y transforms")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the check of the distributed result against a single-GPU solve")
+    ap.add_argument("--impdiff", action="store_true",
+                    help="one step = one RK substage of an is_impdiff run (src/main.f90:447-467): the Helmholtz solves of u, v, w "
+                         "(face-centred in x / y / z, three alternating alpha) + the pressure Poisson solve; value = ns per point per SOLVE")
+    ap.add_argument("--dtdma-helmholtz", action="store_true",
+                    help="--impdiff, N > 1: the three Helmholtz solves run on a distributed-TDMA context (is_poisson_dtdma), the Poisson "
+                         "solve (singular operator) stays on the transposes")
+    ap.add_argument("--weak-nz", type=int, default=0, help="weak scaling: nz = this many planes per GPU (the workload's nx, ny are kept)")
     ap.add_argument("--helmholtz", type=float, default=0.0,
                     help="alpha != 0: time the implicit-diffusion Helmholtz solve p/alpha + lap p = rhs (regular operator) instead")
     args = ap.parse_args()
@@ -320,6 +328,8 @@ def main():
     S = sys.modules["cans_b200.solver"]
 
     ng, l, cbc, gr = WORKLOADS[args.workload]
+    if args.weak_nz > 0:
+        ng = [ng[0], ng[1], args.weak_nz * world]
     cf = ["c"] * 3
     # grid + operator exactly as initgrid/initsolver build them (host arithmetic, as in the reference)
     per_z = cbc[2] == ["P", "P"]
@@ -360,7 +370,38 @@ def main():
             dist.all_reduce(den)
         p[I] -= num / den
 
-    if args.helmholtz != 0.0:
+    nsolves_per_step = 1
+    if args.impdiff:
+        # the velocity operators of the same flow: a pressure Neumann wall is a velocity Dirichlet wall; u / v / w are face
+        # centred in x / y / z (src/main.f90:296-316)
+        cbcv = [["D", "D"] if b == ["N", "N"] else list(b) for b in cbc]
+        ctx_h = ctx
+        if args.dtdma_helmholtz and world > 1:
+            ctx_h = cb.Context(ng, is_fp32=fp32, rank=rank, nranks=world)
+            ctx_h.connect()
+            ctx_h.set_dtdma(True)
+        vel = []
+        for d in range(3):
+            cfv = ["c"] * 3
+            cfv[d] = "f"
+            sdv = cb.initsolver(ctx_h, ng, dli, 1.0 / dzc, 1.0 / dzf, cbcv, [[0.0, 0.0]] * 3, cfv, device=dev, cache_slots=3)
+            f = torch.empty(shp, dtype=tdt, device=dev)
+            S.fill_hash(ctx, f, nl, ctx.lo, 1, 1000 + d)
+            vel.append((sdv, cfv, f, f.clone()))
+        p_init = p.clone()
+        visc_dt = 1.0e-4
+        alphas = [-0.5 * visc_dt * r for r in (32.0 / 60.0, 8.0 / 60.0, 20.0 / 60.0)]   # rkcoeff sums of the three substeps
+        nsolves_per_step = 4
+        irk = [0]
+
+        def step():
+            al = alphas[irk[0] % 3]
+            irk[0] += 1
+            for sdv, cfv, f, _ in vel:
+                cb.solve_helmholtz(ctx_h.n, ng, ctx_h.hi(), sdv.arrplan, sdv.normfft, al, sdv.lambdaxy, sdv.a, sdv.b, sdv.c, None, None,
+                                   None, ctx_h.is_bound(), cbcv, cfv, f)
+            cb.solver(nl, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, p)
+    elif args.helmholtz != 0.0:
         alphai = 1.0 / args.helmholtz
         b_h, norm_h = sd.b + alphai, float(sd.normfft) * alphai   # src/solve_helmholtz.f90:63-71
 
@@ -374,10 +415,15 @@ def main():
     # feeding a solution back as the next right-hand side overflows single precision after a few solves.  The FP32
     # line therefore restores the right-hand side before every solve (outside the per-solve CUDA events).
     p0 = p.clone() if fp32 else None
+    per_step_events = fp32 or args.impdiff   # the fields are restored before every step, outside the per-step events
 
     def reset():
         if fp32:
             p.copy_(p0)
+        if args.impdiff:   # a Helmholtz solve with |alpha| ~ 1e-5 shrinks its field by that factor: restore the right-hand sides
+            p.copy_(p_init)
+            for _, _, f, f0 in vel:
+                f.copy_(f0)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -395,7 +441,7 @@ def main():
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
-    if not fp32:
+    if not per_step_events:
         ev0.record()
         for _ in range(args.steps):
             step()
@@ -423,7 +469,7 @@ def main():
     assert bool(torch.isfinite(p[I]).all()), "solution is not finite"
     assert ctx.dist_status() == 0, "a device-side barrier timed out"
     total_pts = npts  # one global grid, whatever N
-    value = ms_per_step * 1e6 / total_pts
+    value = ms_per_step * 1e6 / total_pts / nsolves_per_step
 
     # ---- per-stage device times (live, CUDA events on the solve's stream) -> roofline of the dominant kernel
     ctx.set_profiling(True)
@@ -456,8 +502,8 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": stage_bytes,
                 "stage_ms": stage_ms,
                 "solve": {"algorithmic_bytes_per_gpu": ALGO_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local,
-                          "achieved": ALGO_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local / (ms_per_step * 1e-3) / 1e9,
-                          "frac": ALGO_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local / (ms_per_step * 1e-3) / 1e9 / peak}}
+                          "achieved": nsolves_per_step * ALGO_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local / (ms_per_step * 1e-3) / 1e9,
+                          "frac": nsolves_per_step * ALGO_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local / (ms_per_step * 1e-3) / 1e9 / peak}}
     if world > 1:
         # two exchanges per solve, each sends (P-1)/P of the local field per GPU per direction
         nvb = 2.0 * (world - 1) / world * npts_local * float(esz)
@@ -474,7 +520,7 @@ def main():
 
     # ---- e2e: the host-memory API (mode A of SURVEY 8b): pinned host p, H2D + solve + D2H per step
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.impdiff:
         nb = int(np.prod(shp)) * esz
         if world == 1:
             ctx.set_host_chunks(args.host_chunks)
@@ -508,7 +554,7 @@ def main():
 
     # ---- N > 1: the distributed result against a single-GPU solve of the same global right-hand side (rank 0)
     parity = None
-    if world > 1 and not args.no_parity:
+    if world > 1 and not args.no_parity and not args.impdiff and args.weak_nz == 0:
         parity = dist_parity(args, ctx, sd, cb, S, dist, torch, np, dev, rank, world, ng, dli, dzc, dzf, cbc, cf, fp32, tdt, ndt, step, p)
 
     cpu = None
@@ -518,7 +564,7 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak" if args.weak_nz > 0 else "strong",
             "vs_baseline": None, "dtype": "f32" if fp32 else "f64", "data": "synthetic",
             "config": bench_config(args.workload, world),   # identical in both arms (driver's same_config)
             "details": {
@@ -526,6 +572,10 @@ def main():
                                  "transposes = peer-mapped stores over NVLink, pipelined over x windows",
                 "solves_per_s": 1e3 / ms_per_step, "thomas_variant": int(sd.arrplan.stats()["thomas_variant"]),
                 **({"dtdma": True} if (args.dtdma and world > 1) else {}),
+                **({"impdiff": "one step = Helmholtz solves of u, v, w (three alternating alpha) + the Poisson solve; value is per solve",
+                    "solves_per_step": 4, "helmholtz_path": "distributed TDMA" if (args.dtdma_helmholtz and world > 1) else "transposes"}
+                   if args.impdiff else {}),
+                **({"weak_nz_per_gpu": args.weak_nz, "grid_solved": ng} if args.weak_nz > 0 else {}),
                 **({"helmholtz_alpha": args.helmholtz} if args.helmholtz != 0.0 else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -64,6 +64,21 @@ struct NvtxRange {
       return fail(CANSB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
   } while (0)
 
+// Host -> device uploads of tables and initial values.  cudaMemcpy from pageable memory may return before the DMA has
+// reached its destination, and it is only ordered against the legacy default stream -- not against the caller's
+// (possibly non-blocking) stream the consuming kernel is launched on a few microseconds later.  Waiting for the legacy
+// stream closes that window (it does not wait for non-blocking streams, so device-side waits of other ranks cannot block it).
+static cudaError_t upload(void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(cudaStreamLegacy);
+}
+static cudaError_t clear_dev(void* dst, size_t bytes) {
+  cudaError_t e = cudaMemset(dst, 0, bytes);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 // ---------------------------------------------------------------------------
 struct DevBuf {
   void* p = nullptr;
@@ -108,6 +123,7 @@ struct cansb200_ctx {
   DevBuf scratch;   // haloless field buffer A (x pencil)
   DevBuf scratch2;  // z-major copy B[j][k][i] of the middle stages (zmajor)
   DevBuf work2;     // third pencil-sized buffer lent to the host (cansb200_get_work)
+  int dtdma_tiled = 1;   // distributed TDMA: slab-local elimination on chip (pipelined kernel) instead of per-column sweeps through HBM
   int dtdma = 0;    // several ranks: keep z decomposed in the tridiagonal stage (gaussel_dtdma) instead of transposing to z pencils
   int zmajor = 1;   // 1: the y transforms write / read B, so that every row stream of the tridiagonal stage is 8 KB-strided
   DevBuf staging;   // haloed p when the caller's p is host memory
@@ -201,6 +217,8 @@ struct cansb200_plan {
   bool sym_checked = false;
   DevBuf zcache, p2cache, dencache, state;
   DevBuf dtdma_big, dtdma_small;   // distributed-TDMA coefficients (Z, AA, CC) and reduced system (cansb200_gaussel_dtdma)
+  const void* zsrc_base = nullptr;  // pivot source of the pipelined kernel when it is not the plan's cache (distributed TDMA: the Z array)
+  long long zsrc_slot = 0;
   DevBuf dtdma_rows;               // ... gathered coefficient rows of all ranks, per cache slot (solve_dist_dtdma)
   unsigned long long solves = 0;
   // TMA descriptors of the pipelined substitution: pivots (per plan) and right-hand sides (per field pointer / shape)
@@ -249,7 +267,7 @@ template <class T> static int get_r2_tables(cansb200_ctx* ctx, int n, int ymode,
           h[(size_t)(r - 1) * L + o] = Cx<T>{(T)cosl(a), (T)sinl(a)};
         }
       CK(cudaMalloc(&t.tw[s], sizeof(Cx<T>) * h.size()));
-      CK(cudaMemcpy(t.tw[s], h.data(), sizeof(Cx<T>) * h.size(), cudaMemcpyHostToDevice));
+      CK(upload(t.tw[s], h.data(), sizeof(Cx<T>) * h.size()));
     }
     Ns = L;
   }
@@ -259,7 +277,7 @@ template <class T> static int get_r2_tables(cansb200_ctx* ctx, int n, int ymode,
     mk[k] = Cx<T>{(T)cosl(a), (T)sinl(a)};
   }
   CK(cudaMalloc(&t.mak, sizeof(Cx<T>) * mk.size()));
-  CK(cudaMemcpy(t.mak, mk.data(), sizeof(Cx<T>) * mk.size(), cudaMemcpyHostToDevice));
+  CK(upload(t.mak, mk.data(), sizeof(Cx<T>) * mk.size()));
   auto res = mp.emplace(key, t);
   *out = &res.first->second;
   return 0;
@@ -281,10 +299,10 @@ template <class T> static int get_tables(cansb200_ctx* ctx, int n, FftTables<T>*
     CK(cudaMalloc(&t.twp, sizeof(C2<T>) * (M / 2 + 1)));
     CK(cudaMalloc(&t.mak, sizeof(C2<T>) * (M + 1)));
     CK(cudaMalloc(&t.rev, sizeof(uint16_t) * (M > 0 ? M : 1)));
-    CK(cudaMemcpy(t.tw, tw.data(), sizeof(C2<T>) * M, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(t.twp, twp.data(), sizeof(C2<T>) * (M / 2 + 1), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(t.mak, mak.data(), sizeof(C2<T>) * (M + 1), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(t.rev, t.H.rev.data(), sizeof(uint16_t) * M, cudaMemcpyHostToDevice));
+    CK(upload(t.tw, tw.data(), sizeof(C2<T>) * M));
+    CK(upload(t.twp, twp.data(), sizeof(C2<T>) * (M / 2 + 1)));
+    CK(upload(t.mak, mak.data(), sizeof(C2<T>) * (M + 1)));
+    CK(upload(t.rev, t.H.rev.data(), sizeof(uint16_t) * M));
   }
   auto res = mp.emplace(n, t);
   *out = &res.first->second;
@@ -302,7 +320,7 @@ template <class T> static int get_direct_tables(cansb200_ctx* ctx, int n, int ki
   const long double pi = 3.14159265358979323846264338327950288L;
   for (long long m = 0; m < 2LL * Q; ++m) cs[m] = {(T)cosl(pi * m / Q), (T)sinl(pi * m / Q)};
   CK(cudaMalloc(&t.cs, sizeof(C2<T>) * cs.size()));
-  CK(cudaMemcpy(t.cs, cs.data(), sizeof(C2<T>) * cs.size(), cudaMemcpyHostToDevice));
+  CK(upload(t.cs, cs.data(), sizeof(C2<T>) * cs.size()));
   auto res = mp.emplace(Q, t);
   *out = &res.first->second;
   return 0;
@@ -447,6 +465,8 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   D.sj = sj; D.sk = sk; D.a = a; D.b = b; D.c = c; D.lam = lam; D.lam_sj = nx;
   D.m = pl->th_m; D.chunk_layout = 2; D.xb = 0; D.xn = nx; D.out_rows = nullptr; D.nopin = 0;
   D.dx = pl->dx; D.dy = pl->dy; D.nxu = pl->nxu; D.nyu = pl->nyu;
+  D.zsj = (long long)D.nn * D.nxu; D.zsk = D.nxu;
+  D.dt_mode = 0; D.dt_z1 = nullptr; D.dt_rp = nullptr; D.dt_slot_small = 0;
   return D;
 }
 
@@ -490,13 +510,16 @@ static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p
                             const CUtensorMap** mp, const CUtensorMap** mz) {
   if (!pl->use_tma || D.nx < box_cols) return false;
   const size_t esz = sizeof(T);
-  const unsigned long long zkey[4] = {(unsigned long long)(uintptr_t)pl->zcache.p, (unsigned long long)D.nxu, (unsigned long long)D.nyu,
-                                      ((unsigned long long)D.nn << 20) | (unsigned long long)box_rows};
+  const void* zb = pl->zsrc_base ? pl->zsrc_base : pl->zcache.p;
+  const long long zslot = pl->zsrc_base ? pl->zsrc_slot : pl->slot_z;
+  const unsigned long long zkey[4] = {(unsigned long long)(uintptr_t)zb, ((unsigned long long)D.nxu << 32) | (unsigned long long)D.nyu,
+                                      ((unsigned long long)D.nn << 20) | (unsigned long long)box_rows,
+                                      (unsigned long long)D.zsk * 1000003ULL + (unsigned long long)D.zsj};
   if (memcmp(zkey, pl->map_z_key, sizeof(zkey)) != 0) {
-    // pivot cache z[slot][j][k][i]: tensor (x, row, y, slot)
+    // pivots: tensor (x, row, y, slot) -- the cache z[slot][j][k][i], or the Z[slot][k][j][i] of the distributed TDMA
     const cuuint64_t dims[4] = {(cuuint64_t)D.nxu, (cuuint64_t)D.nn, (cuuint64_t)D.nyu, (cuuint64_t)pl->nslots};
-    const cuuint64_t st[3] = {(cuuint64_t)D.nxu * esz, (cuuint64_t)D.nxu * D.nn * esz, (cuuint64_t)pl->slot_z * esz};
-    if (!encode_tile_map(&pl->map_z, pl->zcache.p, esz, 4, dims, st, box_rows, box_cols, true)) { pl->use_tma = false; return false; }
+    const cuuint64_t st[3] = {(cuuint64_t)D.zsk * esz, (cuuint64_t)D.zsj * esz, (cuuint64_t)zslot * esz};
+    if (!encode_tile_map(&pl->map_z, zb, esz, 4, dims, st, box_rows, box_cols, true)) { pl->use_tma = false; return false; }
     memcpy(pl->map_z_key, zkey, sizeof(zkey));
   }
   *mz = &pl->map_z;
@@ -557,8 +580,10 @@ static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   static const CUtensorMap dummy = {};
-  CK(cudaLaunchKernelEx(&cfg, kfn, D, (const CacheState*)pl->state.p, (const T*)pl->zcache.p, (const T*)pl->p2cache.p,
-                        (const T*)pl->dencache.p, pl->slot_z, pl->slot_den, p, norm, mp ? *mp : dummy, mz ? *mz : dummy, box_rows));
+  const T* zb = pl->zsrc_base ? (const T*)pl->zsrc_base : (const T*)pl->zcache.p;
+  const long long zslot = pl->zsrc_base ? pl->zsrc_slot : pl->slot_z;
+  CK(cudaLaunchKernelEx(&cfg, kfn, D, (const CacheState*)pl->state.p, zb, (const T*)pl->p2cache.p,
+                        (const T*)pl->dencache.p, zslot, pl->slot_den, p, norm, mp ? *mp : dummy, mz ? *mz : dummy, box_rows));
   ctx->launches++;
   return 0;
 }
@@ -600,7 +625,7 @@ static int plan_cache_alloc(cansb200_plan* pl) {
   CacheState cs;
   memset(&cs, 0, sizeof(cs));
   cs.nslots = pl->nslots;
-  CK(cudaMemcpy(pl->state.p, &cs, sizeof(cs), cudaMemcpyHostToDevice));
+  CK(upload(pl->state.p, &cs, sizeof(cs)));
   return 0;
 }
 
@@ -654,7 +679,8 @@ template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T
     // 16-byte tile copies need every row segment aligned: even (FP64) / multiple-of-4 (FP32) column counts and offsets
     const long long vw = 16 / (long long)sizeof(T);
     const bool vec = (D.nx % vw) == 0 && (D.xb % vw) == 0 && (D.sk % vw) == 0 && (D.sj % vw) == 0 && ((uintptr_t)p % 16) == 0 &&
-                     ((uintptr_t)pl->zcache.p % 16) == 0 && (pl->slot_z % vw) == 0 && (D.xn % vw) == 0;
+                     ((uintptr_t)(pl->zsrc_base ? pl->zsrc_base : pl->zcache.p) % 16) == 0 &&
+                     ((pl->zsrc_base ? pl->zsrc_slot : pl->slot_z) % vw) == 0 && (D.xn % vw) == 0 && (D.zsk % vw) == 0 && (D.zsj % vw) == 0;
     const bool exact = D.m == pl->th_mmax;
     if constexpr (sizeof(T) == 8) {
       if (pl->th_cols == 16 && pl->th_cl == 1) {
@@ -786,7 +812,7 @@ int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ip
     c->off_XB = c->off_C + up(nel_z * c->esz);
     c->region_bytes = c->off_XB + up(nel * c->esz);
     if (cudaMalloc(&c->region, c->region_bytes) != cudaSuccess) { c->scratch.release(); delete c; return fail(CANSB200_ENOMEM, "init: exchange region"); }
-    cudaMemset(c->region, 0, 4096);
+    clear_dev(c->region, 4096);
     // host-mapped: the waiting kernels set it on a time-out, the host reads it without synchronising
     if (cudaHostAlloc((void**)&c->dist_status, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
       cudaFree(c->region); c->scratch.release(); delete c;
@@ -797,7 +823,7 @@ int cansb200_init(cansb200_ctx** out, const int ng[3], const int dims[2], int ip
       cudaFreeHost(c->dist_status); cudaFree(c->region); c->scratch.release(); delete c;
       return fail(CANSB200_ENOMEM, "init: status word");
     }
-    cudaMemset(c->dist_status_dev, 0, sizeof(int));
+    clear_dev(c->dist_status_dev, sizeof(int));
     c->peer.assign(nranks, nullptr);
     c->peer[rank] = c->region;
   }
@@ -848,8 +874,8 @@ template <class T> static int build_dist_tables(cansb200_ctx* c, bool packed) {
   DevBuf& tf = packed ? c->ytab_fwd_pk : c->ytab_fwd;
   DevBuf& tb = packed ? c->ytab_bwd_pk : c->ytab_bwd;
   if (tf.ensure(sizeof(R2Row<T>) * ny) || tb.ensure(sizeof(R2Row<T>) * ny)) return fail(CANSB200_ENOMEM, "dist_connect: tables");
-  CK(cudaMemcpy(tf.p, yf.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(tb.p, yb.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
+  CK(upload(tf.p, yf.data(), sizeof(R2Row<T>) * ny));
+  CK(upload(tb.p, yb.data(), sizeof(R2Row<T>) * ny));
   if (packed) { c->tabs_pk = true; return 0; }
   std::vector<OutRow<T>> zt(nz);
   for (int s = 0; s < P; ++s) {
@@ -861,7 +887,7 @@ template <class T> static int build_dist_tables(cansb200_ctx* c, bool packed) {
     }
   }
   if (c->ztab.ensure(sizeof(OutRow<T>) * nz)) return fail(CANSB200_ENOMEM, "dist_connect: tables");
-  CK(cudaMemcpy(c->ztab.p, zt.data(), sizeof(OutRow<T>) * nz, cudaMemcpyHostToDevice));
+  CK(upload(c->ztab.p, zt.data(), sizeof(OutRow<T>) * nz));
   return 0;
 }
 
@@ -1029,6 +1055,10 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
       c->n_z[1] = c->ys[c->rank + 1] - c->ys[c->rank];
       c->lo_z[1] = c->ys[c->rank] + 1;
     }
+    return 0;
+  }
+  if (what == CANSB200_CTX_DTDMA_TILED) {
+    c->dtdma_tiled = value ? 1 : 0;
     return 0;
   }
   if (what == CANSB200_CTX_ZMAJOR) {
@@ -1399,7 +1429,7 @@ template <class T> static int build_dma_tables(cansb200_ctx* c) {
     }
     DevBuf& tf = packed ? c->ytab_fwd_loc_pk : c->ytab_fwd_loc;
     if (tf.ensure(sizeof(R2Row<T>) * ny)) return fail(CANSB200_ENOMEM, "solve: tables");
-    CK(cudaMemcpy(tf.p, yf.data(), sizeof(R2Row<T>) * ny, cudaMemcpyHostToDevice));
+    CK(upload(tf.p, yf.data(), sizeof(R2Row<T>) * ny));
   }
   std::vector<OutRow<T>> zt(nz);
   for (int s = 0; s < P; ++s) {
@@ -1411,7 +1441,7 @@ template <class T> static int build_dma_tables(cansb200_ctx* c) {
     }
   }
   if (c->ztab_loc.ensure(sizeof(OutRow<T>) * nz)) return fail(CANSB200_ENOMEM, "solve: tables");
-  CK(cudaMemcpy(c->ztab_loc.p, zt.data(), sizeof(OutRow<T>) * nz, cudaMemcpyHostToDevice));
+  CK(upload(c->ztab_loc.p, zt.data(), sizeof(OutRow<T>) * nz));
   int lo = 0, hi = 0;
   CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   c->dist_cs.assign(P, nullptr);
@@ -1661,11 +1691,36 @@ static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double norm
   const unsigned cbk = (unsigned)((ncol + 127) / 128);
   dtdma_coef_kernel<T><<<cbk, 128, 0, st>>>(D);   // returns at once on a cache hit
   prof_mark(ctx, st);
-  dtdma_phase1_kernel<T><<<cbk, 128, 0, st>>>(D, A, (T)normfft);
+  {
+    // slab-local elimination: on chip with the pipelined tridiagonal kernel (tile = one 128-byte row segment of columns x all
+    // rows of the slab: p in, Z in, p out = 24 B/point) whenever the slab fits its chunking, else the one-thread-per-column
+    // sweeps through HBM (48 B/point)
+    const int wide = (int)(128 / sizeof(T)), chunks = CB_TH_THREADS / wide;
+    const int m = (nloc + chunks - 1) / chunks;
+    const int m_lo = ctx->is_fp32 ? 8 : 4, m_hi = ctx->is_fp32 ? 16 : 8;
+    const bool tiled = ctx->dtdma_tiled && m <= m_hi && (nx % wide) == 0 && nx >= wide;
+    if (tiled) {
+      ThomasDev<T> Dt = make_thomas<T>(pl, nx, ny, nx, (long long)ncol, nloc, 0, lam, a, b, c);
+      Dt.m = m; Dt.nopin = 1; Dt.dx = Dt.dy = 0; Dt.nxu = nx; Dt.nyu = ny;
+      Dt.zsj = nx; Dt.zsk = (long long)ncol;
+      Dt.dt_mode = 1; Dt.dt_z1 = D.Z1; Dt.dt_rp = D.rp; Dt.dt_slot_small = (long long)slot_small;
+      // borrow the launcher of the transposed solve with this slab's chunking
+      const int sv_m = pl->th_m, sv_mmax = pl->th_mmax, sv_cols = pl->th_cols, sv_cl = pl->th_cl, sv_var = pl->th_variant;
+      pl->th_m = m; pl->th_mmax = m <= m_lo ? m_lo : m_hi; pl->th_cols = wide; pl->th_cl = 1; pl->th_variant = 1;
+      pl->zsrc_base = big; pl->zsrc_slot = (long long)slot_big;
+      rc = gaussel_apply<T>(pl, Dt, A, (T)normfft, st);
+      pl->zsrc_base = nullptr; pl->zsrc_slot = 0;
+      pl->th_m = sv_m; pl->th_mmax = sv_mmax; pl->th_cols = sv_cols; pl->th_cl = sv_cl; pl->th_variant = sv_var;
+      if (rc) return rc;
+    } else {
+      dtdma_phase1_kernel<T><<<cbk, 128, 0, st>>>(D, A, (T)normfft);
+      ctx->launches++;
+    }
+  }
   DtdmaPeers pp;
   for (int s = 0; s < CB_DTDMA_MAX_RANKS; ++s) pp.dst[s] = s < P ? (void*)((char*)ctx->peer[s] + ctx->off_C) : nullptr;
   dtdma_gather_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(pp, r, P, (long long)ncol, D.ra, D.rc, D.rp, cst, (long long)slot_small);
-  ctx->launches += 3;
+  ctx->launches += 2;
   CK(cudaGetLastError());
   rc = dist_flag(ctx, CB_SLOT_BAR, seq, true, true, st);
   if (rc) return rc;

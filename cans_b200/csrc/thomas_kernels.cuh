@@ -59,6 +59,16 @@ template <class T> struct ThomasDev {
   //           i - nx/2.
   // A quarter of the cache (and of its HBM stream) for a doubly periodic operator.  nxu / nyu = stored extents.
   int dx, dy, nxu, nyu;
+  long long zsj, zsk;  // element strides of the pivot array between y rows and between z rows (cache: nn * nxu and nxu)
+  // Distributed-TDMA mode of the pipelined kernel (dt_mode = 1): the slab-local elimination of gaussel_dtdma
+  // (src/solver.f90:351-391) is the same pair of first-order recurrences as gaussel's two sweeps with
+  //   a_1 := 0 (rows 0 and 1 both start a chain), c_{n-2} := 0 (rows n-2 and n-1 keep their forward value),
+  //   row 0 scaled by Z1 = 1 / (1 - aa_1 cc_0) at the end,
+  // pivots Z[k][j][i] from the coefficient cache of the plan; rows 0 and n-1 also go to the reduced right-hand side dt_rp.
+  int dt_mode;
+  const T* dt_z1;      // [ncol] of the selected slot
+  T* dt_rp;            // [2][ncol]
+  long long dt_slot_small;   // elements between the slots of dt_z1
 };
 
 // ---- exactly-rounded, never-contracted arithmetic ---------------------------
@@ -488,8 +498,14 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
 
   for (int e = tid; e < nrows_tile; e += NT) {
     const int ge = e / m, re = e - ge * m;
-    sa[ge * CSA + re] = (rbase + e < nn) ? D.a[rbase + e] : T(0);
-    sc[ge * CSA + re] = (rbase + e < nn) ? D.c[rbase + e] : T(0);
+    T av = (rbase + e < nn) ? D.a[rbase + e] : T(0);
+    T cv = (rbase + e < nn) ? D.c[rbase + e] : T(0);
+    if (D.dt_mode) {   // distributed TDMA: two chain starts, two untouched last rows (see ThomasDev::dt_mode)
+      if (rbase + e == 1) av = T(0);
+      if (rbase + e >= nn - 2) cv = T(0);
+    }
+    sa[ge * CSA + re] = av;
+    sc[ge * CSA + re] = cv;
   }
 
   if (TMA) {
@@ -547,7 +563,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       }
       return;
     }
-    const T* zrow0 = zsel + (long long)ju * nn * D.nxu;   // stored row ju, k = 0
+    const T* zrow0 = zsel + (long long)ju * D.zsj;   // stored row ju, k = 0
     if (VEC) {
       constexpr int PPR = COLS / VW;                // pieces per row
       for (int q = tid; q < nrows_tile * PPR; q += NT) {
@@ -555,7 +571,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         T* zd = zs + row * COLS + pc;
         T* pd = ps + row * COLS + pc;
         if (rbase + row < nn && pc < ncols) {
-          const T* zr = zrow0 + (long long)(rbase + row) * D.nxu;
+          const T* zr = zrow0 + (long long)(rbase + row) * D.zsk;
           cp_async_16(zd, zr + zx0 + pc);
           cp_async_16(pd, p + (long long)(rbase + row) * sk + col0 + pshift + pc);
         } else {
@@ -567,7 +583,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
       for (int q = tid; q < nrows_tile * COLS; q += NT) {
         const int row = q / COLS, pc = q - row * COLS;
         if (rbase + row < nn && pc < ncols) {
-          cp_async_elem(zs + q, zrow0 + (long long)(rbase + row) * D.nxu + zx0 + pc);
+          cp_async_elem(zs + q, zrow0 + (long long)(rbase + row) * D.zsk + zx0 + pc);
           cp_async_elem(ps + q, p + (long long)(rbase + row) * sk + col0 + pshift + pc);
         } else {
           zs[q] = T(0);
@@ -734,6 +750,19 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
 #pragma unroll
       for (int r = 0; r < MMAX; ++r)
         if (r < nrow) y[r] = fma(p2c[(long long)r * D.nxu], pcl, y[r]);
+    }
+    if (D.dt_mode && live) {
+      // first row of the slab: (y_0 - cc_0 x_1) * Z1; first and last row are this rank's rows of the reduced system
+      const long long ncolg = (long long)D.nx * D.ny;
+      if (k0 == 0) {
+        y[0] = y[0] * D.dt_z1[(long long)sel * D.dt_slot_small + col];
+        D.dt_rp[col] = y[0];
+      }
+      if (nn - 1 >= k0 && nn - 1 < k0 + m) {
+#pragma unroll
+        for (int r = 0; r < MMAX; ++r)
+          if (k0 + r == nn - 1) D.dt_rp[ncolg + col] = y[r];
+      }
     }
     if (D.out_rows) {
       const OutRow<T>* rows = D.out_rows + k0;

@@ -170,6 +170,10 @@ class Context:
         check(lib.cansb200_get_extents(self._h, n, lo, nz, loz), "get_extents")
         self.n, self.lo, self.n_z, self.lo_z = list(n), list(lo), list(nz), list(loz)
 
+    def set_dtdma_tiled(self, on: bool = True):
+        """Distributed TDMA: slab-local elimination on chip (pipelined kernel) or per-column sweeps in the reference's order."""
+        check(lib.cansb200_ctx_set(self._h, 15, int(on)), "ctx_set")
+
     def set_zmajor(self, on: bool = True):
         """One-GPU solves: z-major intermediate between the y transforms and the tridiagonal stage."""
         check(lib.cansb200_ctx_set(self._h, 8, int(on)), "ctx_set")
@@ -487,7 +491,16 @@ def solve_helmholtz(n, ng, hi, arrplan, normfft, alpha, lambdaxy, a, b, c, rhsbx
     updt_rhs_b(c_or_f, cbc, n, is_bound, rhsbx, rhsby, rhsbz, p, alpha, ctx=arrplan.ctx if arrplan is not None else None, stream=stream)
     ty = p.dtype.type if isinstance(p, np.ndarray) else (np.float32 if p.dtype == torch.float32 else np.float64)
     alphai = ty(1.0) / ty(alpha)
-    bb = b + alphai if not _is_torch(b) else b + float(alphai)
+    if _is_torch(b):
+        # `bb(k) = b(k) + alphai` runs on the solve's stream (the reference does it on the same OpenACC queue): on any other
+        # stream the solve's kernels could read bb before it is written
+        if stream is not None and b.is_cuda:
+            with torch.cuda.stream(stream if hasattr(stream, "cuda_stream") else torch.cuda.ExternalStream(int(stream))):
+                bb = b + float(alphai)
+        else:
+            bb = b + float(alphai)
+    else:
+        bb = b + alphai
     if is_impdiff_1d:
         return solver_gaussel_z(n, ng, hi, a, bb, c, cbc[2], c_or_f, alphai, p, arrplan=arrplan, stream=stream)
     return solver(n, ng, arrplan, ty(normfft) * alphai, lambdaxy, a, bb, c, cbc, c_or_f, p, stream)

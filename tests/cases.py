@@ -64,6 +64,11 @@ DIST_CASES = {
     "tma_32x64x256": ([32, 64, 256], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # full chunks: TMA tile path
     "cluster_32x64x1024": ([32, 64, 1024], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # CTA-pair Thomas + peer stores
     "fp32_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float32, False),
+    # chunk lengths that are not powers of two (m = 3 and m = 5 rows per thread of the pipelined tridiagonal kernel)
+    "m3_32x64x160": ([32, 64, 160], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),
+    "m5_32x64x300": ([32, 64, 300], [1.0, 1.0, 2.0], [P, P, D], C3, 1.0, np.float64, False),
+    # regular operator with 256-row slabs on 2 ranks: full chunks of the pipelined kernel (TMA tiles) in distributed-TDMA mode
+    "reg_32x64x512": ([32, 64, 512], [1.0, 1.0, 2.0], [P, P, D], C3, 1.0, np.float64, False),
 }
 
 HELMHOLTZ = {"helm_u_face_x", "helm_v_face_y", "helm_w_face_z", "helm_w_face_z_nn"}

@@ -142,8 +142,10 @@ def test_virtual_ranks_copy_engines_shapes(cb, windows, chunks):
     _run_virtual_ranks(cb, "uneven_64x64x70", 2, windows, mode=2, chunks=chunks)
 
 
-@pytest.mark.parametrize("name,P", [("helm_w_64x64x64", 2), ("uneven_64x64x70", 2), ("helm_w_64x64x64", 3)])
-def test_virtual_ranks_distributed_tdma(cb, name, P):
+@pytest.mark.parametrize("tiled", [True, False])
+@pytest.mark.parametrize("name,P", [("helm_w_64x64x64", 2), ("uneven_64x64x70", 2), ("helm_w_64x64x64", 3), ("reg_32x64x512", 2),
+                                    ("reg_32x64x512", 3), ("m5_32x64x300", 2), ("m3_32x64x160", 2)])
+def test_virtual_ranks_distributed_tdma(cb, name, P, tiled):
     """CANSB200_CTX_DTDMA (the reference's is_poisson_dtdma): z stays decomposed, only the reduced system travels; the
     coefficient arrays are cached per coefficient set (the reference's is_dtdma_update / aa_z_save, src/solver_gpu.f90:571-591):
     three solves with two different alpha must run the coefficient kernel twice, not three times."""
@@ -158,6 +160,7 @@ def test_virtual_ranks_distributed_tdma(cb, name, P):
     cb.Context.connect_local(ctxs)
     for c in ctxs:
         c.set_dtdma(True)
+        c.set_dtdma_tiled(tiled)   # slab-local elimination on chip (pipelined kernel) / per-column sweeps in the reference's order
     sds = [cb.initsolver(c, ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], cf, device=dev, cache_slots=2) for c in ctxs]
     streams = [torch.cuda.Stream() for _ in range(P)]
     slabs_h, slabs_d = [], []
