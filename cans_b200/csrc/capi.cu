@@ -656,6 +656,7 @@ template <class T> static int gaussel_prepare(cansb200_plan* pl, ThomasDev<T>& D
         if (rc) return rc;
         memset(pl->map_z_key, 0, sizeof(pl->map_z_key));
         D.dx = D.dy = 0; D.nxu = pl->nxu; D.nyu = pl->nyu;
+        D.zsj = (long long)D.nn * D.nxu; D.zsk = D.nxu;
         continue;   // hash again without the flags
       }
     }
@@ -1253,6 +1254,15 @@ static int dist_check(cansb200_ctx* c, const char* who) {
   return 0;
 }
 
+// can the y transforms of this plan store / load their rows through the peer row tables themselves (two-for-one kernels)?
+template <class T> static bool dist_y_fast(cansb200_plan* pl) {
+  cansb200_ctx* ctx = pl->ctx;
+  if (ctx->force_generic || !kind_is_fast(pl->kind[1][0]) || !kind_is_fast(pl->kind[1][1])) return false;
+  if ((ctx->ng[0] % (int)(16 / sizeof(T))) != 0) return false;   // column pairs move as 16-byte vectors
+  int radix[4];
+  return (sizeof(T) == 4 ? r2r2_query<true, true>(pl->nt[1], 0, radix) : r2r2_query<true, false>(pl->nt[1], 0, radix)) > 0;
+}
+
 // the z-slab decomposed solve: x and y transforms on my slab, tridiagonal stage on my z pencil.
 //
 // The two exchanges are the stores of the producing kernels (forward y transform -> z pencils of the owners,
@@ -1279,10 +1289,14 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
   T* pin = p + (px * py + px + 1);
   if (pl->th_n != nz - pl->q) return fail(CANSB200_EINVAL, "solve: plan / grid mismatch");
   const bool pipelined = thomas_is_pipelined(pl);
+  // Any y length / kind the single-GPU solve can transform also works here: when the two-for-one kernels do not serve it
+  // (odd or prime n, REDFT00 / 11, RODFT00 / 11), the transform runs in place on the slab with the generic engine and a copy
+  // kernel moves the rows through the same peer row tables (one extra pass; FFTW plans any n, src/fft.f90:148-162)
+  const bool yfast = dist_y_fast<T>(pl);
   // windows: whole 128-byte row segments, as many as asked for (auto: 4) that divide nx
   const int wide = (int)(128 / sizeof(T));
   int W = 1;
-  if (pipelined && !ctx->profiling) {
+  if (pipelined && !ctx->profiling && yfast) {
     // auto: measured on C3 (profiles/r2b_exchange_schedules.md) the windows pay on 2 ranks (2.82 -> 2.73 ms) and cost a
     // little on 4 and 8 (the kernels that store to the peers hold every SM while NVLink drains, whatever the schedule)
     const int want = ctx->dist_windows > 0 ? ctx->dist_windows : (ctx->nranks == 2 ? 4 : 1);
@@ -1323,10 +1337,17 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     const int xb = w * ww;
     // ---- stage F: forward y transform of the window; rows go straight to the z pencils of their owners
     R2RGeom gyf{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, ww, nzl, ny, 1};
-    gyf.row_tab = ytab_fwd;
-    gyf.x0 = xb;
+    if (yfast) {
+      gyf.row_tab = ytab_fwd;
+      gyf.x0 = xb;
+    }
     rc = run_r2r<T>(ctx, pl->kind[1][0], pl->nt[1], A + xb, A + xb, gyf, pl->opt.fft_y_lines, sF);
     if (rc) return rc;
+    if (!yfast) {
+      slab_rows_copy_kernel<T><<<(unsigned)(ctx->num_sms * 8), 256, 0, sF>>>(A, nx, (long long)nx * ny, (const DistRow<T>*)ytab_fwd, nx, ny, nzl, 1);
+      ctx->launches++;
+      CK(cudaGetLastError());
+    }
     if (W > 1) {
       rc = dist_flag(ctx, CB_SLOT_FWD + w, seq, true, false, sF);
       if (rc) return rc;
@@ -1374,9 +1395,16 @@ static int solve_dist(cansb200_plan* pl, T* p, const int n[3], double normfft, c
     if (W == 1) prof_mark(ctx, st);
     // ---- stage B: backward y transform of the window; gathers its rows from the way-back buffer
     R2RGeom gyb{nx, nx, 1, 1, (long long)nx * ny, (long long)nx * ny, ww, nzl, ny, 1};
-    gyb.row_tab = ytab_bwd;
-    gyb.x0 = xb;
-    rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], XB, A + xb, gyb, pl->opt.fft_y_lines, sB);
+    if (yfast) {
+      gyb.row_tab = ytab_bwd;
+      gyb.x0 = xb;
+      rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], XB, A + xb, gyb, pl->opt.fft_y_lines, sB);
+    } else {
+      slab_rows_copy_kernel<T><<<(unsigned)(ctx->num_sms * 8), 256, 0, sB>>>(A, nx, (long long)nx * ny, (const DistRow<T>*)ytab_bwd, nx, ny, nzl, 0);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      rc = run_r2r<T>(ctx, pl->kind[1][1], pl->nt[1], A, A, gyb, pl->opt.fft_y_lines, sB);
+    }
     if (rc) return rc;
   }
   if (W > 1) {
@@ -1868,7 +1896,7 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   }
   if (ctx->nranks > 1) {
     const int rcd = ctx->dtdma ? solve_dist_dtdma<T>(pl, p, n, normfft, lam, a, b, c, st)
-                               : (ctx->dist_mode >= 1 ? solve_dist2<T>(pl, p, n, normfft, lam, a, b, c, pky, ctx->dist_mode == 1, st)
+                               : ((ctx->dist_mode >= 1 && dist_y_fast<T>(pl)) ? solve_dist2<T>(pl, p, n, normfft, lam, a, b, c, pky, ctx->dist_mode == 1, st)
                                                       : solve_dist<T>(pl, p, n, normfft, lam, a, b, c, pky, st));
     if (rcd) return rcd;
     if (mem_kind == CANSB200_MEM_HOST) {

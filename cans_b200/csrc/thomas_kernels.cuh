@@ -99,8 +99,9 @@ template <class T> __device__ __forceinline__ long long zden(const ThomasDev<T>&
 // ---- factorisation cache bookkeeping (device resident) ----------------------
 #define CB_MAX_SLOTS 8
 struct CacheState {
-  unsigned long long key_new;
+  unsigned long long key_new, key2_new;   // two independent content hashes of the coefficient set being solved
   unsigned long long keys[CB_MAX_SLOTS];
+  unsigned long long keys2[CB_MAX_SLOTS];
   unsigned long long stamp[CB_MAX_SLOTS];
   unsigned long long clock;
   unsigned long long nfactor;  // how many factorisations ran (diagnostic)
@@ -114,6 +115,14 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   return z ^ (z >> 31);
 }
+// second, independent mixer (murmur3 finaliser with a different stream constant): a slot is reused only if BOTH 64-bit
+// hashes match, so a silent reuse of the wrong factorisation needs a simultaneous collision of two unrelated sums
+__device__ __forceinline__ unsigned long long mix64b(unsigned long long z) {
+  z ^= 0xC2B2AE3D27D4EB4FULL;
+  z = (z ^ (z >> 33)) * 0xFF51AFD7ED558CCDULL;
+  z = (z ^ (z >> 33)) * 0xC4CEB9FE1A85EC53ULL;
+  return z ^ (z >> 33);
+}
 __device__ __forceinline__ unsigned long long bits_of(double v) { return (unsigned long long)__double_as_longlong(v); }
 __device__ __forceinline__ unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
 
@@ -123,7 +132,7 @@ __global__ void thomas_hash_kernel(const ThomasDev<T> D, CacheState* st) {
   const long long ncoef = D.n;
   const long long nlam = (long long)D.nx * D.ny;
   const long long total = 3 * ncoef + nlam;
-  unsigned long long h = 0;
+  unsigned long long h = 0, h2 = 0;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     T v;
     if (e < ncoef) v = D.a[e];
@@ -144,19 +153,21 @@ __global__ void thomas_hash_kernel(const ThomasDev<T> D, CacheState* st) {
       }
     }
     h += mix64(mix64((unsigned long long)e) ^ bits_of(v));
+    h2 += mix64b(mix64b(bits_of(v)) + 0x9E3779B97F4A7C15ULL * (unsigned long long)(e + 1));
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) h += mix64(0x5EEDULL + (unsigned long long)D.nopin + 2ULL * D.dx + 4ULL * D.dy);
-  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&st->key_new, h);
+  for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, o); h2 += __shfl_xor_sync(0xffffffffu, h2, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&st->key_new, h); atomicAdd(&st->key2_new, h2); }
 }
 
 __global__ void thomas_select_kernel(CacheState* st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   unsigned long long key = st->key_new | 1ULL;  // never 0 (0 = empty slot)
+  const unsigned long long key2 = st->key2_new;
   st->clock += 1;
   int sel = -1;
   for (int s = 0; s < st->nslots; ++s)
-    if (st->keys[s] == key) sel = s;
+    if (st->keys[s] == key && st->keys2[s] == key2) sel = s;
   if (sel >= 0) {
     st->hit = 1;
   } else {
@@ -165,11 +176,13 @@ __global__ void thomas_select_kernel(CacheState* st) {
     for (int s = 1; s < st->nslots; ++s)
       if (st->stamp[s] < st->stamp[sel]) sel = s;
     st->keys[sel] = key;
+    st->keys2[sel] = key2;
     st->nfactor += 1;
   }
   st->stamp[sel] = st->clock;
   st->sel = sel;
   st->key_new = 0;
+  st->key2_new = 0;
 }
 
 // ---- factorisation: reference operation order, one thread per column --------

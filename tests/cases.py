@@ -64,6 +64,11 @@ DIST_CASES = {
     "tma_32x64x256": ([32, 64, 256], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # full chunks: TMA tile path
     "cluster_32x64x1024": ([32, 64, 1024], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),   # CTA-pair Thomas + peer stores
     "fp32_64x64x64": ([64, 64, 64], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float32, False),
+    # y lengths / kinds the two-for-one kernels do not serve (odd, prime, small, REDFT00 / RODFT11): generic engine + row copies
+    "geny_64x30x48": ([64, 30, 48], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),
+    "geny_40x17x36": ([40, 17, 36], [1.0, 1.0, 1.0], [N, P, ["D", "D"]], C3, 1.0, np.float64, False),
+    "geny_face_48x33x40": ([48, 33, 40], [1.0, 1.0, 1.0], [P, N, ["D", "D"]], ["c", "f", "c"], 1.5, np.float64, False),
+    "geny_mixed_32x20x24": ([32, 20, 24], [1.0, 1.0, 1.0], [P, ["D", "N"], ["D", "D"]], C3, 0.5, np.float64, False),
     # chunk lengths that are not powers of two (m = 3 and m = 5 rows per thread of the pipelined tridiagonal kernel)
     "m3_32x64x160": ([32, 64, 160], [6.0, 3.0, 2.0], [P, P, N], C3, 2.0, np.float64, False),
     "m5_32x64x300": ([32, 64, 300], [1.0, 1.0, 2.0], [P, P, D], C3, 1.0, np.float64, False),
