@@ -1059,7 +1059,8 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
     return 0;
   }
   if (what == CANSB200_CTX_DTDMA_TILED) {
-    c->dtdma_tiled = value ? 1 : 0;
+    if (value < -1 || value > 2) return fail(CANSB200_EINVAL, "ctx_set: dtdma_tiled must be -1 / 1 (auto), 0 (never) or 2 (always)");
+    c->dtdma_tiled = value < 0 ? 1 : value;
     return 0;
   }
   if (what == CANSB200_CTX_ZMAJOR) {
@@ -1726,7 +1727,11 @@ static int solve_dist_dtdma(cansb200_plan* pl, T* p, const int n[3], double norm
     const int wide = (int)(128 / sizeof(T)), chunks = CB_TH_THREADS / wide;
     const int m = (nloc + chunks - 1) / chunks;
     const int m_lo = ctx->is_fp32 ? 8 : 4, m_hi = ctx->is_fp32 ? 16 : 8;
-    const bool tiled = ctx->dtdma_tiled && m <= m_hi && (nx % wide) == 0 && nx >= wide;
+    // ... when it pays: a tile is one 128-byte row segment x the slab's rows, and below ~4 rows per thread (slabs under 256
+    // rows in FP64) the per-tile overhead of the chunked scan exceeds the traffic it saves (measured on 8 B200: C3 with 64-row
+    // slabs 1.57 ms per solve tiled against 1.1 ms with the per-column sweeps; C5 with 128-row slabs 9.7 against 8.4 ms)
+    const bool pays = m >= m_lo || ctx->dtdma_tiled == 2;
+    const bool tiled = ctx->dtdma_tiled && pays && m <= m_hi && (nx % wide) == 0 && nx >= wide;
     if (tiled) {
       ThomasDev<T> Dt = make_thomas<T>(pl, nx, ny, nx, (long long)ncol, nloc, 0, lam, a, b, c);
       Dt.m = m; Dt.nopin = 1; Dt.dx = Dt.dy = 0; Dt.nxu = nx; Dt.nyu = ny;

@@ -170,9 +170,10 @@ class Context:
         check(lib.cansb200_get_extents(self._h, n, lo, nz, loz), "get_extents")
         self.n, self.lo, self.n_z, self.lo_z = list(n), list(lo), list(nz), list(loz)
 
-    def set_dtdma_tiled(self, on: bool = True):
-        """Distributed TDMA: slab-local elimination on chip (pipelined kernel) or per-column sweeps in the reference's order."""
-        check(lib.cansb200_ctx_set(self._h, 15, int(on)), "ctx_set")
+    def set_dtdma_tiled(self, on=None):
+        """Distributed TDMA, slab-local elimination: True = always on chip (pipelined kernel), False = per-column sweeps in the
+        reference's operation order, None = automatic (on chip for slabs of at least 193 rows in FP64)."""
+        check(lib.cansb200_ctx_set(self._h, 15, 1 if on is None else (2 if on else 0)), "ctx_set")
 
     def set_zmajor(self, on: bool = True):
         """One-GPU solves: z-major intermediate between the y transforms and the tridiagonal stage."""

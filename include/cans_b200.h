@@ -237,8 +237,9 @@ enum {
                                     the wire); -1 = auto */
   CANSB200_CTX_DIST_SPLIT_PAD = 14, /* z-chunked forward half: KB of shared-memory padding per CTA of the y transforms that store to the peers,
                                     so that they leave room on every SM for the x transform of the next chunk; -1 = auto, 0 = none */
-  CANSB200_CTX_DTDMA_TILED = 15,  /* distributed TDMA: 1 (default) = the slab-local elimination runs on chip in the pipelined tridiagonal kernel
-                                    (24 B/point), 0 = one thread per column sweeping through HBM in the reference's operation order (48 B/point) */
+  CANSB200_CTX_DTDMA_TILED = 15,  /* distributed TDMA, slab-local elimination: 2 = on chip in the pipelined tridiagonal kernel (24 B/point),
+                                    0 = one thread per column sweeping through HBM in the reference's operation order (48 B/point),
+                                    -1 / 1 (default) = on chip when the slab has at least 4 rows per thread of a tile (>= 193 rows in FP64) */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
                                     bit 2 = force the maximum shared-memory carveout (default: the driver picks, which leaves L1 to the twiddles) */
 };
