@@ -289,6 +289,7 @@ def main():
     ap.add_argument("--fp32", action="store_true", help="the -D_SINGLE_PRECISION build of CaNS (not the headline; FP64 is)")
     ap.add_argument("--host-chunks", type=int, default=16)
     ap.add_argument("--zmajor", type=int, default=-1)
+    ap.add_argument("--pivot-dedup", type=int, default=-1, help="0 = full pivot cache, -1 = library default (deduplicated where lambda is symmetric)")
     ap.add_argument("--dtdma", action="store_true",
                     help="N > 1: the distributed-TDMA path (CANSB200_CTX_DTDMA); use it with --helmholtz (it has no singular-pivot pin)")
     ap.add_argument("--dist-windows", type=int, default=-1, help="N > 1: x windows of the pipelined exchange (-1 auto, 1 = two barriers)")
@@ -352,7 +353,8 @@ def main():
     if args.zmajor >= 0:
         ctx.set_zmajor(bool(args.zmajor))
     sd = cb.initsolver(ctx, ng, dli, 1.0 / dzc, 1.0 / dzf, cbc, [[0.0, 0.0]] * 3, cf, device=dev,
-                       thomas_variant=args.thomas, fft_x_lines=args.fft_x_lines, fft_y_lines=args.fft_y_lines)
+                       thomas_variant=args.thomas, fft_x_lines=args.fft_x_lines, fft_y_lines=args.fft_y_lines,
+                       pivot_dedup=args.pivot_dedup)
     nl = ctx.n                      # local x pencil (nx, ny, nz / N)
     shp = (nl[2] + 2, nl[1] + 2, nl[0] + 2)
     npts = ng[0] * ng[1] * ng[2]    # global points

@@ -1939,9 +1939,10 @@ static int solve_impl(cansb200_plan* pl, void* p_any, const int n[3], double nor
   const R2RGeom gyb{(long long)nx * nz, nx, 1, 1, nx, (long long)nx * ny, nx, nz, ny, 1};
   // auto: two half-width windows on two streams; the windows' kernels overlap each other's ramp-up / ramp-down
   // (measured -3 % on C3; windows small enough to stay in L2 lose more to launch tails than they gain)
-  // ... and with the deduplicated pivot cache one full-width tridiagonal launch is better: the tiles that share pivots run
-  // side by side and the sharing happens in L2 (C3: 3.90 ms against 3.97 with the two windows)
-  const int W = ctx->chain_cols >= 0 ? ctx->chain_cols : ((nx >= 1024 && (nx / 2) % 16 == 0 && !(pl->dx | pl->dy)) ? nx / 2 : 0);
+  // ... and with the pivot cache deduplicated in x AND y one full-width tridiagonal launch is better: the four tiles that
+  // share pivots run side by side and the sharing happens in L2 (C3: 3.92 ms against 3.97 with the two windows; C4, x only:
+  // 9.86 with the windows against 9.95 without)
+  const int W = ctx->chain_cols >= 0 ? ctx->chain_cols : ((nx >= 1024 && (nx / 2) % 16 == 0 && !(pl->dx && pl->dy)) ? nx / 2 : 0);
   if (W > 0 && W < nx && thomas_is_pipelined(pl) && !ctx->profiling) {
     // ---- L2-resident chain over x windows, round-robin on auxiliary streams
     ThomasDev<T> D = make_thomas<T>(pl, nx, ny, zm ? (long long)nx * nz : (long long)nx, zm ? (long long)nx : (long long)nx * ny,
