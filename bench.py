@@ -509,7 +509,7 @@ def main():
     if world > 1:
         # two exchanges per solve, each sends (P-1)/P of the local field per GPU per direction
         nvb = 2.0 * (world - 1) / world * npts_local * float(esz)
-        ach = nvb / (ms_per_step * 1e-3) / 1e9
+        ach = nsolves_per_step * nvb / (ms_per_step * 1e-3) / 1e9   # (a distributed-TDMA solve moves far less: upper bound then)
         roofline["nvlink"] = {"bytes_per_gpu_per_direction_per_solve": nvb, "achieved_GBs_over_whole_solve": ach,
                               "peak_GBs": 900.0, "frac": ach / 900.0, "measured_peer_copy_GBs": 770.0, "frac_of_measured": ach / 770.0,
                               "floor_ms_at_900": nvb / 900e9 * 1e3,
