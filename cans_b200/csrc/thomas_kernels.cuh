@@ -628,12 +628,14 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   }
   for (; tile < ntiles; tile += tstride) {
     if (TMA) {
-      mbar_wait(&tile_bar, tile_phase);
+      mbar_wait(&tile_bar, tile_phase);   // every thread waits itself: the tile is visible to it without a CTA barrier
       tile_phase ^= 1u;
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();   // this tile has landed (copies of all threads); also orders the previous tile's sY reads
+    // cp.async paths: the copies of ALL threads must have landed.  TMA path: the barrier is only needed where threads read
+    // fold slots other than their own after the last barrier of the previous tile (periodic closure, CTA pairs).
+    if (!TMA || CL > 1 || D.periodic) __syncthreads();
     T y[MMAX], z[MMAX];
 #pragma unroll
     for (int r = 0; r < MMAX; ++r)
