@@ -97,6 +97,10 @@ struct DevBuf {
     p = nullptr;
     bytes = 0;
   }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }   // error paths of plan / context creation must not leak device memory
 };
 
 template <class T> struct FftTables {
@@ -178,6 +182,11 @@ struct cansb200_ctx {
   std::vector<cudaEvent_t> aux_done;
   cudaEvent_t fork_ev = nullptr;
   unsigned long long launches = 0;
+  // One solve at a time per context: scratch, staging and the exchange region are shared by its plans.  The device side
+  // is made safe here: a solve enqueued on another stream than the previous one first waits for that one's end.
+  cudaStream_t last_stream = nullptr;
+  cudaEvent_t last_done = nullptr;
+  bool have_last = false;
   int cur_xsplit = 0;                           // set for the duration of a solve whose plan keeps x in split order (CB_R2_XSPLIT)
   int cta_cap = 0;                              // > 0: the persistent tridiagonal kernel uses at most this many CTAs (pipelined exchange)
   int nplans = 0;                               // live plans (some switches are only legal before the first one)
@@ -544,9 +553,13 @@ static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_
                        const CUtensorMap* mz, int box_rows, cudaStream_t st) {
   auto kfn = thomas_pipe_kernel<T, MMAX, EXACT, LDM, COLS, CL>;
   const size_t smem = thomas_pipe_smem<T, MMAX, COLS>();
-  static bool attr = false;
-  static int max_clusters = 0;
-  if (!attr) {
+  // per device: the shared-memory opt-in and the cluster occupancy belong to the device the context lives on
+  static std::map<int, int> per_dev;   // device -> max resident clusters (0 for CL = 1)
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  auto itd = per_dev.find(dev);
+  int max_clusters = itd != per_dev.end() ? itd->second : 0;
+  if (itd == per_dev.end()) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CL > 1) {
       // how many CTA pairs can be resident at once (GPCs with an odd SM count leave one SM out)
@@ -559,7 +572,7 @@ static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_
       CK(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &q));
       if (max_clusters < 1) return fail(CANSB200_ECUDA, "gaussel: no room for a CTA cluster");
     }
-    attr = true;
+    per_dev[dev] = max_clusters;
   }
   const long long tiles = (long long)((D.xn + COLS - 1) / COLS) * D.ny;
   cudaLaunchConfig_t cfg = {};
@@ -965,6 +978,7 @@ int cansb200_finalize(cansb200_ctx* c) {
   if (c->dist_status_dev) cudaFree(c->dist_status_dev);
   c->sendb.release(); c->ytab_fwd_loc.release(); c->ytab_fwd_loc_pk.release(); c->ztab_loc.release();
   for (cudaStream_t q : c->dist_cs) if (q) cudaStreamDestroy(q);
+  if (c->last_done) cudaEventDestroy(c->last_done);
   if (c->dist_sF) cudaStreamDestroy(c->dist_sF);
   if (c->dist_sT) cudaStreamDestroy(c->dist_sT);
   if (c->dist_sB) cudaStreamDestroy(c->dist_sB);
@@ -1237,6 +1251,19 @@ int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
 
 // ---------------------------------------------------------------------------
 // device-side flags over the ranks of the box, stream ordered (dist_kernels.cuh): announce and / or wait for slot `slot`
+// serialise the solves of one context on the device, whatever streams the caller uses
+static int ctx_enter(cansb200_ctx* c, cudaStream_t st) {
+  if (c->have_last && c->last_stream != st) CK(cudaStreamWaitEvent(st, c->last_done, 0));
+  return 0;
+}
+static int ctx_leave(cansb200_ctx* c, cudaStream_t st) {
+  if (!c->last_done) CK(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->last_done, st));
+  c->last_stream = st;
+  c->have_last = true;
+  return 0;
+}
+
 static int dist_flag(cansb200_ctx* c, int slot, unsigned long long seq, bool signal, bool wait, cudaStream_t st, int target = -1,
                      bool skip_self = false) {
   DistPeers pp;
@@ -2159,8 +2186,12 @@ int cansb200_solve_z(cansb200_plan* pl, void* p, const int n[3], int nhalo, doub
     if (n[d] != ctx->n[d]) return fail(CANSB200_EINVAL, "solve_z: n differs from the context's local extents");
   if (mem_kind != CANSB200_MEM_HOST && mem_kind != CANSB200_MEM_DEVICE) return fail(CANSB200_EINVAL, "solve_z: bad mem_kind");
   cudaStream_t st = (cudaStream_t)stream;
-  return ctx->is_fp32 ? solve_z_impl<float>(pl, p, n, norm, a, b, c, mem_kind, st)
-                      : solve_z_impl<double>(pl, p, n, norm, a, b, c, mem_kind, st);
+  int rc = ctx_enter(ctx, st);
+  if (rc) return rc;
+  rc = ctx->is_fp32 ? solve_z_impl<float>(pl, p, n, norm, a, b, c, mem_kind, st)
+                    : solve_z_impl<double>(pl, p, n, norm, a, b, c, mem_kind, st);
+  const int rl = ctx_leave(ctx, st);
+  return rc ? rc : rl;
 }
 
 int cansb200_plan_id(cansb200_plan* pl) {
@@ -2294,8 +2325,12 @@ int cansb200_solve(cansb200_plan* pl, void* p, const int n[3], int nhalo, double
     if (n[d] != ctx->n[d]) return fail(CANSB200_EINVAL, "solve: n differs from the context's local extents");
   if (mem_kind != CANSB200_MEM_HOST && mem_kind != CANSB200_MEM_DEVICE) return fail(CANSB200_EINVAL, "solve: bad mem_kind");
   cudaStream_t st = (cudaStream_t)stream;
-  return ctx->is_fp32 ? solve_impl<float>(pl, p, n, normfft, lambdaxy, a, b, c, mem_kind, st)
-                      : solve_impl<double>(pl, p, n, normfft, lambdaxy, a, b, c, mem_kind, st);
+  int rc = ctx_enter(ctx, st);
+  if (rc) return rc;
+  rc = ctx->is_fp32 ? solve_impl<float>(pl, p, n, normfft, lambdaxy, a, b, c, mem_kind, st)
+                    : solve_impl<double>(pl, p, n, normfft, lambdaxy, a, b, c, mem_kind, st);
+  const int rl = ctx_leave(ctx, st);
+  return rc ? rc : rl;
 }
 
 int cansb200_r2r(cansb200_ctx* ctx, int kind, int nt, int axis, void* arr, const int d3[3], void* stream) {

@@ -17,6 +17,8 @@
  *  - all work is stream-ordered on the caller's CUDA stream (the reference
  *    enqueues everything on OpenACC queue 1: src/workspaces.f90:101-106);
  *    no host synchronisation happens inside cansb200_solve in device mode;
+ *  - one solve at a time per context (its plans share scratch, staging and the exchange region): one host thread issues
+ *    work, as in the reference; solves enqueued on different streams are ordered against each other by the library;
  *  - precision is fixed per context: FP64, or FP32 when CaNS is built with
  *    -D_SINGLE_PRECISION (src/types.f90:12-18).
  */
