@@ -196,6 +196,32 @@ def test_virtual_ranks_distributed_tdma(cb, name, P, tiled):
         assert sd.arrplan.stats()["factorisations"] == 2, sd.arrplan.stats()
 
 
+def test_dtdma_context_guards(cb):
+    """on a CANSB200_CTX_DTDMA context the pivot-cache entry points have nothing to work with (solve_z, gaussel
+    -> CANSB200_EUNSUPPORTED instead of a null-pointer write), and the switch is refused once a plan exists."""
+    ng, l, cbc, cf, gr, dt, helm = cases.DIST_CASES["helm_w_64x64x64"]
+    dev = torch.device("cuda:0")
+    cs = O.make_case(ng, l, cbc, c_or_f=cf, gr=gr, dtype=dt)
+    ctxs = [cb.Context(ng, rank=r, nranks=2) for r in range(2)]
+    cb.Context.connect_local(ctxs)
+    ctxs[0].set_dtdma(True)
+    sd = cb.initsolver(ctxs[0], ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], cf, device=dev)
+    pd = torch.zeros((ctxs[0].n[2] + 2, ng[1] + 2, ng[0] + 2), dtype=torch.float64, device=dev)
+    with pytest.raises(Exception, match="(?i)dtdma"):
+        cb.solver_gaussel_z(ctxs[0].n, ng, ctxs[0].hi(), sd.a, sd.b, sd.c, cbc[2], cf, 1.0, pd, arrplan=sd.arrplan)
+    import sys
+    S = sys.modules["cans_b200.solver"]   # (`cans_b200.solver` the attribute is the function of that name)
+    pz = torch.zeros((ctxs[0].n_z[2], ng[1], ng[0]), dtype=torch.float64, device=dev)
+    with pytest.raises(Exception, match="(?i)dtdma"):
+        S.gaussel(sd.arrplan, ctxs[0].n_z[2], sd.a, sd.b, sd.c, False, 1.0, pz, sd.lambdaxy)
+    with pytest.raises(Exception, match="before any plan"):
+        ctxs[0].set_dtdma(False)
+    sd1 = cb.initsolver(ctxs[1], ng, cs["dli"], cs["dzci"], cs["dzfi"], cbc, cs["bc"], cf, device=dev)
+    with pytest.raises(Exception, match="before any plan"):
+        ctxs[1].set_dtdma(True)
+    del sd1
+
+
 def test_missing_rank_is_reported(cb):
     """A rank that never calls the collective solve: the device-side wait gives up (no GPU hang), the solve of the
     rank that did call returns normally in device mode (stream ordered, nothing is read back), and the NEXT call on
