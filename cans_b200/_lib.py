@@ -17,13 +17,13 @@ MEM_HOST, MEM_DEVICE = 0, 1
 class Options(C.Structure):
     _fields_ = [("thomas_variant", C.c_int), ("cache_slots", C.c_int), ("fft_x_lines", C.c_int),
                 ("fft_y_lines", C.c_int), ("exchange", C.c_int), ("lambda_order", C.c_int), ("pivot_dedup", C.c_int),
-                ("reserved", C.c_int * 9)]
+                ("tall_tiles", C.c_int), ("reserved", C.c_int * 8)]
 
     def __init__(self, **kw):
         super().__init__()
         for name, _ in self._fields_[:-1]:
             setattr(self, name, kw.pop(name, -1))
-        for i in range(9):
+        for i in range(8):
             self.reserved[i] = -1
         if kw:
             raise TypeError(f"unknown option(s): {sorted(kw)}")

@@ -222,6 +222,7 @@ struct cansb200_plan {
   // thomas
   int th_n, th_nn, th_m, th_variant, th_mmax, th_cols, th_cl, nslots;
   long long slot_z, slot_den;
+  int jb = 1, th_m_b = 0, th_mmax_b = 0;  // shallow grids: y rows per tall tile of the z-major one-GPU solve, and its chunking
   int dx = 0, dy = 0, nxu = 0, nyu = 0;   // pivot-cache deduplication (ThomasDev::dx ..): decided at plan creation, verified at the first solve
   bool sym_checked = false;
   DevBuf zcache, p2cache, dencache, state;
@@ -476,6 +477,12 @@ template <class T> static ThomasDev<T> make_thomas(const cansb200_plan* pl, int 
   D.dx = pl->dx; D.dy = pl->dy; D.nxu = pl->nxu; D.nyu = pl->nyu;
   D.zsj = (long long)D.nn * D.nxu; D.zsk = D.nxu;
   D.dt_mode = 0; D.dt_z1 = nullptr; D.dt_rp = nullptr; D.dt_slot_small = 0;
+  D.jb = 1;
+  // tall tiles: only where (j, k) rows form one uniform run -- the z-major field of the one-GPU solve
+  if (pl->jb > 1 && sj == (long long)D.nn * sk && !periodic && n_rows == pl->th_n && (ny % pl->jb) == 0) {
+    D.jb = pl->jb;
+    D.m = pl->th_m_b;
+  }
   return D;
 }
 
@@ -521,25 +528,27 @@ static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p
   const size_t esz = sizeof(T);
   const void* zb = pl->zsrc_base ? pl->zsrc_base : pl->zcache.p;
   const long long zslot = pl->zsrc_base ? pl->zsrc_slot : pl->slot_z;
+  const bool tall = D.jb > 1;   // (j, k) rows as one run: (x, j nn + k, 0, slot) and (x, 0, j nn + k)
   const unsigned long long zkey[4] = {(unsigned long long)(uintptr_t)zb, ((unsigned long long)D.nxu << 32) | (unsigned long long)D.nyu,
-                                      ((unsigned long long)D.nn << 20) | (unsigned long long)box_rows,
+                                      ((unsigned long long)D.nn << 20) | (unsigned long long)box_rows | (tall ? (1ULL << 60) : 0ULL),
                                       (unsigned long long)D.zsk * 1000003ULL + (unsigned long long)D.zsj};
   if (memcmp(zkey, pl->map_z_key, sizeof(zkey)) != 0) {
     // pivots: tensor (x, row, y, slot) -- the cache z[slot][j][k][i], or the Z[slot][k][j][i] of the distributed TDMA
-    const cuuint64_t dims[4] = {(cuuint64_t)D.nxu, (cuuint64_t)D.nn, (cuuint64_t)D.nyu, (cuuint64_t)pl->nslots};
+    const cuuint64_t dims[4] = {(cuuint64_t)D.nxu, (cuuint64_t)D.nn * (tall ? D.nyu : 1), (cuuint64_t)(tall ? 1 : D.nyu), (cuuint64_t)pl->nslots};
     const cuuint64_t st[3] = {(cuuint64_t)D.zsk * esz, (cuuint64_t)D.zsj * esz, (cuuint64_t)zslot * esz};
     if (!encode_tile_map(&pl->map_z, zb, esz, 4, dims, st, box_rows, box_cols, true)) { pl->use_tma = false; return false; }
     memcpy(pl->map_z_key, zkey, sizeof(zkey));
   }
   *mz = &pl->map_z;
+  const int ny_key = tall ? -D.ny : D.ny;   // tall and per-row maps of the same field are different descriptors
   for (auto& e : pl->map_p)
-    if (e.p == p && e.sj == D.sj && e.sk == D.sk && e.nx == D.nx && e.ny == D.ny && e.nn == D.nn && e.box_rows == box_rows) {
+    if (e.p == p && e.sj == D.sj && e.sk == D.sk && e.nx == D.nx && e.ny == ny_key && e.nn == D.nn && e.box_rows == box_rows) {
       *mp = &e.m;
       return true;
     }
   cansb200_plan::PMap e;
-  e.p = p; e.sj = D.sj; e.sk = D.sk; e.nx = D.nx; e.ny = D.ny; e.nn = D.nn; e.box_rows = box_rows;
-  const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)D.ny, (cuuint64_t)D.nn, 1};
+  e.p = p; e.sj = D.sj; e.sk = D.sk; e.nx = D.nx; e.ny = ny_key; e.nn = D.nn; e.box_rows = box_rows;
+  const cuuint64_t dims[4] = {(cuuint64_t)D.nx, (cuuint64_t)(tall ? 1 : D.ny), (cuuint64_t)D.nn * (tall ? D.ny : 1), 1};
   const cuuint64_t st[3] = {(cuuint64_t)D.sj * esz, (cuuint64_t)D.sk * esz, 0};
   if (!encode_tile_map(&e.m, p, esz, 3, dims, st, box_rows, box_cols, false)) return false;
   if (pl->map_p.size() >= 16) pl->map_p.erase(pl->map_p.begin());
@@ -574,7 +583,7 @@ static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_
     }
     per_dev[dev] = max_clusters;
   }
-  const long long tiles = (long long)((D.xn + COLS - 1) / COLS) * D.ny;
+  const long long tiles = (long long)((D.xn + COLS - 1) / COLS) * (D.ny / (D.jb > 1 ? D.jb : 1));
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute la[1];
   if (CL > 1) {
@@ -695,11 +704,12 @@ template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T
     const bool vec = (D.nx % vw) == 0 && (D.xb % vw) == 0 && (D.sk % vw) == 0 && (D.sj % vw) == 0 && ((uintptr_t)p % 16) == 0 &&
                      ((uintptr_t)(pl->zsrc_base ? pl->zsrc_base : pl->zcache.p) % 16) == 0 &&
                      ((pl->zsrc_base ? pl->zsrc_slot : pl->slot_z) % vw) == 0 && (D.xn % vw) == 0 && (D.zsk % vw) == 0 && (D.zsj % vw) == 0;
-    const bool exact = D.m == pl->th_mmax;
+    const int mmax_eff = D.jb > 1 ? pl->th_mmax_b : pl->th_mmax;
+    const bool exact = D.m == mmax_eff;
     if constexpr (sizeof(T) == 8) {
       if (pl->th_cols == 16 && pl->th_cl == 1) {
-        if (pl->th_mmax == 4) return launch_pipe_sel<T, 4, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
-        if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
+        if (mmax_eff == 4) return launch_pipe_sel<T, 4, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
+        if (mmax_eff == 8) return launch_pipe_sel<T, 8, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
       } else if (pl->th_cols == 16 && pl->th_cl == 2) {
         if (pl->th_mmax == 6) return launch_pipe_sel<T, 6, 16, 2>(ctx, D, pl, p, norm, exact, vec, st);
         if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 16, 2>(ctx, D, pl, p, norm, exact, vec, st);
@@ -710,8 +720,8 @@ template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T
     } else {
       // FP32: 32 columns make the 128-byte row segment (32 chunks of up to 16 rows per column)
       if (pl->th_cols == 32 && pl->th_cl == 1) {
-        if (pl->th_mmax == 8) return launch_pipe_sel<T, 8, 32, 1>(ctx, D, pl, p, norm, exact, vec, st);
-        if (pl->th_mmax == 16) return launch_pipe_sel<T, 16, 32, 1>(ctx, D, pl, p, norm, exact, vec, st);
+        if (mmax_eff == 8) return launch_pipe_sel<T, 8, 32, 1>(ctx, D, pl, p, norm, exact, vec, st);
+        if (mmax_eff == 16) return launch_pipe_sel<T, 16, 32, 1>(ctx, D, pl, p, norm, exact, vec, st);
       } else if (pl->th_cols == 32 && pl->th_cl == 2) {
         if (pl->th_mmax == 12) return launch_pipe_sel<T, 12, 32, 2>(ctx, D, pl, p, norm, exact, vec, st);
         if (pl->th_mmax == 16) return launch_pipe_sel<T, 16, 32, 2>(ctx, D, pl, p, norm, exact, vec, st);
@@ -1169,6 +1179,21 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
   else pl->th_mmax = pl->th_cols == 16 ? 16 : (pl->th_cl == 1 ? (pl->th_m <= 8 ? 8 : 16) : (pl->th_m <= 12 ? 12 : 16));
   pl->nslots = o.cache_slots >= 1 ? (o.cache_slots > CB_MAX_SLOTS ? CB_MAX_SLOTS : o.cache_slots) : 1;
   {
+    // shallow grids: tall tiles of jb y rows for the z-major one-GPU solve, so that a tile keeps ~512 rows
+    const int chunks = CB_TH_THREADS / wide, nyz = ctx->n_z[1];
+    if (ctx->nranks == 1 && (variant == 1 || variant == 3) && pl->th_cl == 1 && pl->th_cols == wide && !pl->periodic_z && pl->q == 0 &&
+        pl->th_nn <= 256 && o.tall_tiles != 0) {
+      int jb = 1;
+      while (jb * 2 * pl->th_nn <= 512 && (nyz % (jb * 2)) == 0) jb *= 2;
+      if (jb > 1) {
+        pl->jb = jb;
+        pl->th_m_b = (jb * pl->th_nn + chunks - 1) / chunks;
+        if (!ctx->is_fp32) pl->th_mmax_b = pl->th_m_b <= 4 ? 4 : 8;
+        else pl->th_mmax_b = pl->th_m_b <= 8 ? 8 : 16;
+      }
+    }
+  }
+  {
     // pivot-cache deduplication: a periodic direction whose length is a whole number of tile pairs (x), an even number of
     // rows held in full by this rank (y).  Off in distributed-TDMA mode (no pivot cache at all).
     const int nxz = ctx->n_z[0], nyz = ctx->n_z[1];
@@ -1178,7 +1203,7 @@ int cansb200_plan_create(cansb200_ctx* ctx, cansb200_plan** out, const char bc[6
     int radix[4];
     const bool fastx = !ctx->force_generic && (ctx->is_fp32 ? r2r2_query<false, true>(nxz, 0, radix) : r2r2_query<false, false>(nxz, 0, radix)) > 0;
     pl->dx = on && fastx && bc[0] == 'P' && bc[1] == 'P' && nxz >= 4 * wide && (nxz % (2 * wide)) == 0;
-    pl->dy = on && bc[2] == 'P' && bc[3] == 'P' && nyz == ctx->ng[1] && nyz >= 4 && (nyz % 2) == 0;
+    pl->dy = on && pl->jb == 1 && bc[2] == 'P' && bc[3] == 'P' && nyz == ctx->ng[1] && nyz >= 4 && (nyz % 2) == 0;   // (tall tiles need consecutive stored rows)
   }
   {
     const int rc = plan_cache_alloc(pl.get());

@@ -65,6 +65,10 @@ template <class T> struct ThomasDev {
   //   a_1 := 0 (rows 0 and 1 both start a chain), c_{n-2} := 0 (rows n-2 and n-1 keep their forward value),
   //   row 0 scaled by Z1 = 1 / (1 - aa_1 cc_0) at the end,
   // pivots Z[k][j][i] from the coefficient cache of the plan; rows 0 and n-1 also go to the reduced right-hand side dt_rp.
+  // Shallow grids: jb > 1 solves jb consecutive y rows as ONE tall tile of jb * nn rows (the z-major field and the pivot cache
+  // are contiguous in (j, k), so the tile is still a uniform run of rows); the recurrences are cut at the seams by a_0 := 0
+  // and c_{nn-1} := 0.  Keeps 512 rows per tile when nz is small (nz = 128: 2.8 -> ~1 ms on 2048 x 1024 x 128).
+  int jb;
   int dt_mode;
   const T* dt_z1;      // [ncol] of the selected slot
   T* dt_rp;            // [2][ncol]
@@ -497,12 +501,15 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   __shared__ __align__(8) unsigned long long tile_bar;   // TMA: completion barrier of the tile in flight
   const unsigned rank = CL > 1 ? cluster_ctarank() : 0u;
   const int tid = threadIdx.x, c = tid & (COLS - 1), g = tid / COLS;
-  const int m = EXACT ? MMAX : D.m, nn = D.nn;
+  const int jb = D.jb > 1 ? D.jb : 1;
+  const int nn1 = D.nn;                      // rows of one system
+  const int m = EXACT ? MMAX : D.m, nn = nn1 * jb;   // rows of one tile
   const int nrows_tile = CHUNKS * m;
   const long long ncol = (long long)D.nx * D.ny;
   const long long sk = D.sk;
   const int tiles_x = (D.xn + COLS - 1) / COLS;
-  const int ntiles = tiles_x * D.ny;
+  const int nyt = D.ny / jb;                 // tiles along y
+  const int ntiles = tiles_x * nyt;
   const int sel = st->sel;
   const int rbase = (int)rank * nrows_tile;         // first row of this CTA
   const int k0 = rbase + g * m;
@@ -511,8 +518,13 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
 
   for (int e = tid; e < nrows_tile; e += NT) {
     const int ge = e / m, re = e - ge * m;
-    T av = (rbase + e < nn) ? D.a[rbase + e] : T(0);
-    T cv = (rbase + e < nn) ? D.c[rbase + e] : T(0);
+    const int kk = jb > 1 ? (rbase + e) % nn1 : rbase + e;   // row inside its own system
+    T av = (rbase + e < nn) ? D.a[kk] : T(0);
+    T cv = (rbase + e < nn) ? D.c[kk] : T(0);
+    if (jb > 1) {      // seams between the systems of a tall tile
+      if (kk == 0) av = T(0);
+      if (kk == nn1 - 1) cv = T(0);
+    }
     if (D.dt_mode) {   // distributed TDMA: two chain starts, two untouched last rows (see ThomasDev::dt_mode)
       if (rbase + e == 1) av = T(0);
       if (rbase + e >= nn - 2) cv = T(0);
@@ -534,15 +546,15 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   // share their pivots get consecutive tile numbers, so that neighbouring CTAs of the persistent grid fetch the same pivot
   // tile at the same time -- one HBM read, the others hit L2.  y pairs in the order (0, ny/2), (1, ny-1), (2, ny-2), ...
   const bool grouped = (D.dx | D.dy) && D.xb == 0 && D.xn == D.nx && (tiles_x & 1) == 0 && (!D.dy || (D.ny & 1) == 0);
-  auto decode = [&](int t, int& tj, int& ti) {
-    if (!grouped) { tj = t / tiles_x; ti = t - tj * tiles_x; return; }
+  auto decode = [&](int t, int& tj, int& ti) {   // tj = FIRST y row of the tile
+    if (!grouped) { tj = t / tiles_x; ti = t - tj * tiles_x; tj *= jb; return; }
     int mx = 0, my = 0;
     if (D.dx) { mx = t & 1; t >>= 1; }
     if (D.dy) { my = t & 1; t >>= 1; }
     const int ntu = D.dx ? tiles_x / 2 : tiles_x;
     const int qy = t / ntu, tu = t - qy * ntu;
     ti = mx ? tu + tiles_x / 2 : tu;
-    tj = !D.dy ? qy : (qy == 0 ? (my ? D.ny / 2 : 0) : (my ? D.ny - qy : qy));
+    tj = !D.dy ? qy * jb : (qy == 0 ? (my ? D.ny / 2 : 0) : (my ? D.ny - qy : qy));   // (the host never combines dy with jb > 1)
   };
   // (flat column of the tile's first thread, live columns); the field itself may have a row pitch sj != nx
   // (the haloed array of solver_gaussel_z): its columns sit at pcol = col + tj (sj - nx)
@@ -570,8 +582,13 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         fence_proxy_async();   // the generic-proxy reads of the previous tile are ordered before the async writes
         mbar_expect_tx(&tile_bar, (unsigned)(2u * nrows_tile * COLS * sizeof(T)));
         for (int r0 = 0; r0 < nrows_tile; r0 += box_rows) {
-          tma_load_3d(ps + r0 * COLS, &map_p, &tile_bar, x0, tj, rbase + r0);
-          tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, zx0, rbase + r0, ju, sel);
+          if (jb > 1) {   // maps of a tall tile describe the (j, k) rows as one run: (x, 0, j nn + k) / (x, j nn + k, 0, slot)
+            tma_load_3d(ps + r0 * COLS, &map_p, &tile_bar, x0, 0, tj * nn1 + rbase + r0);
+            tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, zx0, ju * nn1 + rbase + r0, 0, sel);
+          } else {
+            tma_load_3d(ps + r0 * COLS, &map_p, &tile_bar, x0, tj, rbase + r0);
+            tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, zx0, rbase + r0, ju, sel);
+          }
         }
       }
       return;

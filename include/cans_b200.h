@@ -64,7 +64,9 @@ typedef struct cansb200_options {
                            two halves agree to rounding (<= 2e-11 relative), which moves the pressure by <= 1e-14 in relative L2; the
                            symmetry of the caller's lambdaxy is verified on the device to 1e-10 (the first solve falls back to the
                            full cache if it does not hold);  0 = always the full cache */
-  int reserved[9];
+  int tall_tiles;       /* one-GPU solves of shallow grids (nz <= 256): -1 / 1 (default) = the tridiagonal stage solves several y rows per
+                           tile (the z-major field is contiguous in (j, k)), which keeps ~512 rows per tile; 0 = one y row per tile */
+  int reserved[8];
 } cansb200_options;
 
 /* -- context: replaces initmpi's cuDecomp setup (src/initmpi.f90:84-146), common_cudecomp.f90
