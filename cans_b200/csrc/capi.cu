@@ -557,10 +557,10 @@ static bool thomas_tma_maps(cansb200_plan* pl, const ThomasDev<T>& D, const T* p
   return true;
 }
 
-template <class T, int MMAX, bool EXACT, int LDM, int COLS, int CL>
+template <class T, int MMAX, bool EXACT, int LDM, int COLS, int CL, bool TALL = false>
 static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_plan* pl, T* p, T norm, const CUtensorMap* mp,
                        const CUtensorMap* mz, int box_rows, cudaStream_t st) {
-  auto kfn = thomas_pipe_kernel<T, MMAX, EXACT, LDM, COLS, CL>;
+  auto kfn = thomas_pipe_kernel<T, MMAX, EXACT, LDM, COLS, CL, TALL>;
   const size_t smem = thomas_pipe_smem<T, MMAX, COLS>();
   // per device: the shared-memory opt-in and the cluster occupancy belong to the device the context lives on
   static std::map<int, int> per_dev;   // device -> max resident clusters (0 for CL = 1)
@@ -610,7 +610,7 @@ static int launch_pipe(cansb200_ctx* ctx, const ThomasDev<T>& D, const cansb200_
   return 0;
 }
 
-template <class T, int MMAX, int COLS, int CL>
+template <class T, int MMAX, int COLS, int CL, bool TALL = false>
 static int launch_pipe_sel(cansb200_ctx* ctx, const ThomasDev<T>& D, cansb200_plan* pl, T* p, T norm, bool exact, bool vec,
                            cudaStream_t st) {
   if (exact && vec && COLS * sizeof(T) == 128 && pl->th_variant != 3) {
@@ -619,11 +619,11 @@ static int launch_pipe_sel(cansb200_ctx* ctx, const ThomasDev<T>& D, cansb200_pl
     const int box_rows = rows % 256 == 0 ? 256 : (rows % 128 == 0 ? 128 : 64);
     const CUtensorMap *mp = nullptr, *mz = nullptr;
     if (thomas_tma_maps<T>(pl, D, p, box_rows, COLS, &mp, &mz))
-      return launch_pipe<T, MMAX, true, CB_TH_LD_TMA, COLS, CL>(ctx, D, pl, p, norm, mp, mz, box_rows, st);
+      return launch_pipe<T, MMAX, true, CB_TH_LD_TMA, COLS, CL, TALL>(ctx, D, pl, p, norm, mp, mz, box_rows, st);
   }
-  if (exact && vec) return launch_pipe<T, MMAX, true, CB_TH_LD_VEC, COLS, CL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
-  if (vec) return launch_pipe<T, MMAX, false, CB_TH_LD_VEC, COLS, CL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
-  return launch_pipe<T, MMAX, false, CB_TH_LD_ELEM, COLS, CL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
+  if (exact && vec) return launch_pipe<T, MMAX, true, CB_TH_LD_VEC, COLS, CL, TALL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
+  if (vec) return launch_pipe<T, MMAX, false, CB_TH_LD_VEC, COLS, CL, TALL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
+  return launch_pipe<T, MMAX, false, CB_TH_LD_ELEM, COLS, CL, TALL>(ctx, D, pl, p, norm, nullptr, nullptr, 0, st);
 }
 
 // sizes of the pivot cache for the plan's deduplication flags
@@ -707,7 +707,10 @@ template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T
     const int mmax_eff = D.jb > 1 ? pl->th_mmax_b : pl->th_mmax;
     const bool exact = D.m == mmax_eff;
     if constexpr (sizeof(T) == 8) {
-      if (pl->th_cols == 16 && pl->th_cl == 1) {
+      if (pl->th_cols == 16 && pl->th_cl == 1 && D.jb > 1) {
+        if (mmax_eff == 4) return launch_pipe_sel<T, 4, 16, 1, true>(ctx, D, pl, p, norm, exact, vec, st);
+        if (mmax_eff == 8) return launch_pipe_sel<T, 8, 16, 1, true>(ctx, D, pl, p, norm, exact, vec, st);
+      } else if (pl->th_cols == 16 && pl->th_cl == 1) {
         if (mmax_eff == 4) return launch_pipe_sel<T, 4, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
         if (mmax_eff == 8) return launch_pipe_sel<T, 8, 16, 1>(ctx, D, pl, p, norm, exact, vec, st);
       } else if (pl->th_cols == 16 && pl->th_cl == 2) {
@@ -719,7 +722,10 @@ template <class T> static int gaussel_apply(cansb200_plan* pl, const ThomasDev<T
       }
     } else {
       // FP32: 32 columns make the 128-byte row segment (32 chunks of up to 16 rows per column)
-      if (pl->th_cols == 32 && pl->th_cl == 1) {
+      if (pl->th_cols == 32 && pl->th_cl == 1 && D.jb > 1) {
+        if (mmax_eff == 8) return launch_pipe_sel<T, 8, 32, 1, true>(ctx, D, pl, p, norm, exact, vec, st);
+        if (mmax_eff == 16) return launch_pipe_sel<T, 16, 32, 1, true>(ctx, D, pl, p, norm, exact, vec, st);
+      } else if (pl->th_cols == 32 && pl->th_cl == 1) {
         if (mmax_eff == 8) return launch_pipe_sel<T, 8, 32, 1>(ctx, D, pl, p, norm, exact, vec, st);
         if (mmax_eff == 16) return launch_pipe_sel<T, 16, 32, 1>(ctx, D, pl, p, norm, exact, vec, st);
       } else if (pl->th_cols == 32 && pl->th_cl == 2) {

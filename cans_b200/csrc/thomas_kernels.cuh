@@ -477,7 +477,9 @@ __device__ __forceinline__ void thomas_fold(T* sY, T* sP, int tid, const T* cin,
 #define CB_TH_LD_ELEM 0
 #define CB_TH_LD_VEC 1
 #define CB_TH_LD_TMA 2
-template <class T, int MMAX, bool EXACT, int LDM, int COLS, int CL>
+// TALL: tiles of several y rows (ThomasDev::jb) -- a compile-time switch, so that the one-row-per-tile instantiations keep their
+// register budget (the run-time version spilled 24 bytes at the 64-register cap: C3 0.95 -> 1.02 ms).
+template <class T, int MMAX, bool EXACT, int LDM, int COLS, int CL, bool TALL = false>
 __global__ void __launch_bounds__(CB_TH_THREADS, 1)
 thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, const T* p2base, const T* denbase,
                    long long slot_z, long long slot_den, T* p, T norm, const __grid_constant__ CUtensorMap map_p,
@@ -501,7 +503,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
   __shared__ __align__(8) unsigned long long tile_bar;   // TMA: completion barrier of the tile in flight
   const unsigned rank = CL > 1 ? cluster_ctarank() : 0u;
   const int tid = threadIdx.x, c = tid & (COLS - 1), g = tid / COLS;
-  const int jb = D.jb > 1 ? D.jb : 1;
+  const int jb = TALL ? D.jb : 1;
   const int nn1 = D.nn;                      // rows of one system
   const int m = EXACT ? MMAX : D.m, nn = nn1 * jb;   // rows of one tile
   const int nrows_tile = CHUNKS * m;
@@ -518,10 +520,10 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
 
   for (int e = tid; e < nrows_tile; e += NT) {
     const int ge = e / m, re = e - ge * m;
-    const int kk = jb > 1 ? (rbase + e) % nn1 : rbase + e;   // row inside its own system
+    const int kk = TALL ? (rbase + e) % nn1 : rbase + e;   // row inside its own system
     T av = (rbase + e < nn) ? D.a[kk] : T(0);
     T cv = (rbase + e < nn) ? D.c[kk] : T(0);
-    if (jb > 1) {      // seams between the systems of a tall tile
+    if (TALL) {        // seams between the systems of a tall tile
       if (kk == 0) av = T(0);
       if (kk == nn1 - 1) cv = T(0);
     }
@@ -582,7 +584,7 @@ thomas_pipe_kernel(const ThomasDev<T> D, const CacheState* st, const T* zbase, c
         fence_proxy_async();   // the generic-proxy reads of the previous tile are ordered before the async writes
         mbar_expect_tx(&tile_bar, (unsigned)(2u * nrows_tile * COLS * sizeof(T)));
         for (int r0 = 0; r0 < nrows_tile; r0 += box_rows) {
-          if (jb > 1) {   // maps of a tall tile describe the (j, k) rows as one run: (x, 0, j nn + k) / (x, j nn + k, 0, slot)
+          if (TALL) {     // maps of a tall tile describe the (j, k) rows as one run: (x, 0, j nn + k) / (x, j nn + k, 0, slot)
             tma_load_3d(ps + r0 * COLS, &map_p, &tile_bar, x0, 0, tj * nn1 + rbase + r0);
             tma_load_4d(zs + r0 * COLS, &map_z, &tile_bar, zx0, ju * nn1 + rbase + r0, 0, sel);
           } else {
