@@ -2,15 +2,20 @@
 """bench.py -- Poisson-solve ns per grid point on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path, full grid, all host cores
 
-One "step" = one `solver(...)` call (FFT x, FFT y, tridiagonal z, iFFT y, iFFT x)
-on the workload named in `config.workload`: the channel grid of BASELINE.json's
-target (1024x512x512, periodic x/y, stretched Neumann-Neumann z, FP64), which
-fits one GPU (2.15 GB per field).  Inputs are resident in HBM for `value`; `e2e`
-runs the same solve through the public host-memory API (pinned host buffers,
-H2D + D2H inside the timed region).  The field (2.15 GB) is >> L2 (126 MB), so
-no explicit L2 flush is needed between steps.
+One "step" = one `solver(...)` call (FFT x, FFT y, tridiagonal z, iFFT y, iFFT x) on the workload named in
+`config.workload`: the channel grid of BASELINE.json's target (1024x512x512, periodic x/y, stretched Neumann-Neumann z,
+FP64), which fits one GPU (2.15 GB per field).  Inputs are resident in HBM for `value`; `e2e` runs the same solve through the
+public host-memory API (pinned host buffers, H2D + D2H inside the timed region).  The field (2.15 GB) is >> L2 (126 MB), so
+no explicit L2 flush is needed between steps.  N > 1: ONE global grid as z slabs over the N GPUs (strong scaling); after the
+timed region the distributed result is compared with a single-GPU solve of the same right-hand side (`parity`, exit != 0
+on failure).
+
+Other lines: `--impdiff` (one step = one RK substage of an is_impdiff run: Helmholtz solves of u, v, w + the Poisson solve;
+`--dtdma-helmholtz` runs the three on the distributed TDMA), `--weak-nz K` (weak scaling: K planes per GPU), `--fp32`,
+`--workload` (C2 / C4 / C5 ...), and the tuning switches of the library (`--dist-mode`, `--dist-windows`, `--chain-cols`,
+`--pivot-dedup` ...).
 
 Prints ONE JSON line (rank 0).
 """
