@@ -1274,7 +1274,8 @@ int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
   if (!pl || !stats) return fail(CANSB200_EINVAL, "null argument");
   CacheState cs;
   CK(cudaMemcpy(&cs, pl->state.p, sizeof(cs), cudaMemcpyDeviceToHost));
-  stats[0] = pl->solves; stats[1] = cs.nfactor; stats[2] = pl->ctx->launches; stats[3] = (unsigned long long)pl->th_variant | ((unsigned long long)pl->dx << 4) | ((unsigned long long)pl->dy << 5);
+  stats[0] = pl->solves; stats[1] = cs.nfactor; stats[2] = pl->ctx->launches; stats[3] = (unsigned long long)pl->th_variant | ((unsigned long long)pl->dx << 4) | ((unsigned long long)pl->dy << 5) |
+             ((unsigned long long)(((pl->dx | pl->dy) && cs.sym_bad) ? 1 : 0) << 6) | ((unsigned long long)pl->jb << 8);
   return 0;
 }
 

@@ -244,7 +244,10 @@ class Plan:
         s = (C.c_ulonglong * 4)()
         check(lib.cansb200_plan_stats(self._h, s), "plan_stats")
         return {"solves": s[0], "factorisations": s[1], "launches": s[2], "thomas_variant": s[3] & 15,
-                "pivot_dedup_x": (s[3] >> 4) & 1, "pivot_dedup_y": (s[3] >> 5) & 1}
+                "pivot_dedup_x": (s[3] >> 4) & 1, "pivot_dedup_y": (s[3] >> 5) & 1,
+                # set if a lambdaxy WITHOUT the mirror symmetry reached a plan whose cache is deduplicated after its first solve
+                # (the first solve checks and falls back; later solves only record the violation here)
+                "pivot_dedup_violation": (s[3] >> 6) & 1, "tall_tile_rows": (s[3] >> 8) & 0xFFFF}
 
     def destroy(self):
         if self._h:

@@ -199,7 +199,8 @@ int cansb200_fill_hash(cansb200_ctx* ctx, void* p, const int n[3], const int lo[
 const char* cansb200_last_error(void);
 int cansb200_version(void);
 /* counters since plan creation: [0] solves, [1] factorisations run, [2] kernels launched (context-wide),
- * [3] bits 0-3 tridiagonal variant in use, bit 4 / 5 pivot cache deduplicated in x / y (after the first solve's check) */
+ * [3] bits 0-3 tridiagonal variant in use, bit 4 / 5 pivot cache deduplicated in x / y (after the first solve's check),
+ *     bit 6 a later lambdaxy violated the symmetry the deduplicated cache relies on, bits 8-23 y rows per tall tile */
 int cansb200_plan_stats(cansb200_plan* plan, unsigned long long stats[4]);
 /* per-stage device timing with CUDA events on the solve's stream (the role of the reference's
  * unused timer_tic/toc CUDA-event pool, src/timer.f90:113-216).  Stages of one solve:
