@@ -559,3 +559,26 @@ def test_pivot_dedup_falls_back_on_asymmetric_lambda(cb, S, name):
             pd = torch.from_numpy(pz.copy()).to(_dev())
             S.gaussel(sd.arrplan, ng[2], sd.a, sd.b, sd.c, per, sd.normfft, pd, lam_d)
             assert cases.rel_l2(pd.cpu().numpy(), ref) < 1e-13
+
+
+@pytest.mark.parametrize("name,cols", [("dedup_x_128x24x40", 32), ("dedup_xy_64x32x48", 16), ("dedup_tma_96x8x256", 48),
+                                       ("C3s_channel", 16), ("dedup_cluster_64x8x1024", 32), ("fp32_dedup_128x16x256", 64)])
+def test_x_windows_of_the_middle_stages(cb, name, cols):
+    """The one-GPU solve runs fft-y -> tridiagonal -> ifft-y per window of x columns on auxiliary streams when nx >= 1024
+    (CANSB200_CTX_CHAIN_COLS; default: two half-width windows).  Here the windows are forced on small grids so that they
+    meet the deduplicated pivot cache (tiles of the mirrored half in another window), the tall tiles of shallow grids, the
+    CTA-pair kernel and FP32."""
+    cs = cases.build_case(name)
+    ng = cs["ng"]
+    p = cases.make_rhs(cs)
+    ref = cases.oracle_solve(name, cs, p)
+    ctx = cb.Context(ng, is_fp32=cs["dtype"] == np.float32)
+    ctx.set_chain(cols, 2)
+    sd = cb.initsolver(ctx, ng, cs["dli"], cs["dzci"], cs["dzfi"], cs["cbc"], cs["bc"], cs["c_or_f"], device=_dev())
+    pd = torch.from_numpy(p.copy()).to(_dev())
+    for _ in range(2):
+        pd.copy_(torch.from_numpy(p))
+        cb.solver(ng, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cs["cbc"], cs["c_or_f"], pd)
+    torch.cuda.synchronize()
+    err = cases.parity_error(cs, pd.cpu().numpy()[1:-1, 1:-1, 1:-1], ref[1:-1, 1:-1, 1:-1])
+    assert err < TOL[cs["dtype"]], err
