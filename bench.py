@@ -312,6 +312,10 @@ def main():
     ap.add_argument("--weak-nz", type=int, default=0, help="weak scaling: nz = this many planes per GPU (the workload's nx, ny are kept)")
     ap.add_argument("--helmholtz", type=float, default=0.0,
                     help="alpha != 0: time the implicit-diffusion Helmholtz solve p/alpha + lap p = rhs (regular operator) instead")
+    ap.add_argument("--fillps", action="store_true",
+                    help="one step = the pressure-correction right-hand side + its solve (src/main.f90:465-467: fillps, updt_rhs_b, solver) "
+                         "as ONE call, the forward x transform evaluating fillps at load time (cansb200_solve_fillps); the split sequence "
+                         "(fillps kernel, then solver) is timed beside it.  One GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -408,6 +412,35 @@ def main():
                 cb.solve_helmholtz(ctx_h.n, ng, ctx_h.hi(), sdv.arrplan, sdv.normfft, al, sdv.lambdaxy, sdv.a, sdv.b, sdv.c, None, None,
                                    None, ctx_h.is_bound(), cbcv, cfv, f)
             cb.solver(nl, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, p)
+    elif args.fillps:
+        if world > 1:
+            raise SystemExit("bench.py --fillps: one GPU (the z halos of u, v, w would need the host's halo exchange)")
+        # a prediction velocity with consistent halos: periodic directions wrap, no flow through Neumann (pressure) walls
+        uvw = []
+        for d in range(3):
+            f = torch.empty(shp, dtype=tdt, device=dev)
+            S.fill_hash(ctx, f, nl, ctx.lo, 1, 2000 + d)
+            uvw.append(f)
+        for d, ax in ((0, 2), (1, 1), (2, 0)):      # direction d of the grid is tensor axis ax
+            for f in uvw:
+                lo_h, hi_h = [slice(None)] * 3, [slice(None)] * 3
+                lo_i, hi_i = [slice(None)] * 3, [slice(None)] * 3
+                lo_h[ax], hi_h[ax], lo_i[ax], hi_i[ax] = 0, -1, 1, -2
+                if cbc[d] == ["P", "P"]:
+                    f[tuple(lo_h)] = f[tuple(hi_i)]
+                    f[tuple(hi_h)] = f[tuple(lo_i)]
+            if cbc[d] != ["P", "P"]:
+                f = uvw[d]                           # the wall-normal component vanishes on both walls
+                lo_h, hi_i = [slice(None)] * 3, [slice(None)] * 3
+                lo_h[ax], hi_i[ax] = 0, -2
+                f[tuple(lo_h)] = 0.0
+                f[tuple(hi_i)] = 0.0
+        dzfi_d = torch.from_numpy((1.0 / dzf).astype(ndt)).to(dev)
+        dti_f = 1.0e3
+
+        def step():
+            S.solver_fillps(nl, ng, sd.arrplan, sd.normfft, sd.lambdaxy, sd.a, sd.b, sd.c, cbc, cf, dli, dzfi_d, dti_f,
+                            uvw[0], uvw[1], uvw[2], p)
     elif args.helmholtz != 0.0:
         alphai = 1.0 / args.helmholtz
         b_h, norm_h = sd.b + alphai, float(sd.normfft) * alphai   # src/solve_helmholtz.f90:63-71
@@ -525,9 +558,30 @@ def main():
                                  "(no x windows / second stream, N > 1: one window with two whole-field barriers); `value` is the "
                                  "default overlapped schedule")
 
+    # ---- --fillps: the same step as three separate launches sequences (fillps kernel, then the solve reading p back)
+    fillps_info = None
+    if args.fillps:
+        fused_flag = int(sd.arrplan.stats()["fillps_fused"])
+        ctx.set_fuse_fillps(False)
+        for _ in range(3):
+            step()
+        sync_all()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            step()
+        b1.record()
+        sync_all()
+        ctx.set_fuse_fillps(True)
+        split_ms = b0.elapsed_time(b1) / args.steps
+        fillps_info = {"fused": fused_flag, "fused_ms_per_step": ms_per_step, "split_ms_per_step": split_ms,
+                       "algorithmic_bytes_per_point": {"fused": 96.0 * esz / 8.0, "split": 112.0 * esz / 8.0},
+                       "note": "step = fillps + solver of the pressure correction (src/main.f90:465-467); fused: the forward x "
+                               "transform reads u, v, w (24 B/pt) instead of p (8), and the fillps kernel (24 read + 8 written) is gone"}
+
     # ---- e2e: the host-memory API (mode A of SURVEY 8b): pinned host p, H2D + solve + D2H per step
     e2e = None
-    if not args.no_e2e and not args.impdiff:
+    if not args.no_e2e and not args.impdiff and not args.fillps:
         nb = int(np.prod(shp)) * esz
         if world == 1:
             ctx.set_host_chunks(args.host_chunks)
@@ -565,7 +619,7 @@ def main():
         parity = dist_parity(args, ctx, sd, cb, S, dist, torch, np, dev, rank, world, ng, dli, dzc, dzf, cbc, cf, fp32, tdt, ndt, step, p)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not fp32:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not fp32 and not args.fillps:
         cpu = cpu_baseline_leg(args.workload)
 
     if rank == 0:
@@ -583,6 +637,7 @@ def main():
                     "solves_per_step": 4, "helmholtz_path": "distributed TDMA" if (args.dtdma_helmholtz and world > 1) else "transposes"}
                    if args.impdiff else {}),
                 **({"weak_nz_per_gpu": args.weak_nz, "grid_solved": ng} if args.weak_nz > 0 else {}),
+                **({"fillps": fillps_info} if fillps_info is not None else {}),
                 **({"helmholtz_alpha": args.helmholtz} if args.helmholtz != 0.0 else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -51,6 +51,10 @@ SYMBOLS = {
     "cansb200_fftend": (C.c_int, [_VP, C.c_int]),
     "cansb200_solver": (C.c_int, [_VP, C.c_int, C.c_char_p, C.c_char_p, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, _VP, C.c_int,
                                   C.c_int, _VP]),
+    "cansb200_solve_fillps": (C.c_int, [_VP, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, _VP, _D3, _VP, C.c_double, _VP, _VP, _VP,
+                                        _I3, _I3, _D3, _VP]),
+    "cansb200_solver_fillps": (C.c_int, [_VP, C.c_int, C.c_char_p, C.c_char_p, _VP, _I3, C.c_int, C.c_double, _VP, _VP, _VP, _VP,
+                                         C.c_int, _D3, _VP, C.c_double, _VP, _VP, _VP, _I3, _I3, _D3, _VP]),
     "cansb200_plan_id": (C.c_int, [_VP]),
     "cansb200_plan_from_id": (_VP, [C.c_int]),
     "cansb200_updt_rhs_b": (C.c_int, [_VP, C.c_char_p, C.c_char_p, _I3, _I3, _I3, _D3, C.c_double, _VP, _VP]),

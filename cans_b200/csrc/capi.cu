@@ -34,6 +34,10 @@ extern template int r2r2_run<float, false, false>(const R2Args<float>&, int, int
 extern template int r2r2_run<float, true, false>(const R2Args<float>&, int, int, bool, cudaStream_t);
 extern template int r2r2_run<double, true, true>(const R2Args<double>&, int, int, bool, cudaStream_t);
 extern template int r2r2_run<float, true, true>(const R2Args<float>&, int, int, bool, cudaStream_t);
+// forward x transform fed by the fused fillps source (r2r2_xf{64,32}.cu)
+template <class T> int r2r2_run_fillps(const R2Args<T>& A, const R2Fill<T>& F, int n, cudaStream_t st);
+extern template int r2r2_run_fillps<double>(const R2Args<double>&, const R2Fill<double>&, int, cudaStream_t);
+extern template int r2r2_run_fillps<float>(const R2Args<float>&, const R2Fill<float>&, int, cudaStream_t);
 extern int g_r2_default_carveout;   // 1: do not force the maximum shared-memory carveout (capi.cu owns it)
 extern template int r2r2_query<false, false>(int, int, int[4]);
 extern template int r2r2_query<true, false>(int, int, int[4]);
@@ -188,6 +192,16 @@ struct cansb200_ctx {
   cudaEvent_t last_done = nullptr;
   bool have_last = false;
   int cur_xsplit = 0;                           // set for the duration of a solve whose plan keeps x in split order (CB_R2_XSPLIT)
+  // cansb200_solve_fillps: for the duration of that solve the forward x transform evaluates its samples from u, v, w
+  struct FuseSrc {
+    const void *u, *v, *w, *dzfi;               // device pointers; u, v, w haloed like p
+    const void* pin;                            // p(1,1,1) of the solve: launches on z chunks are located relative to it
+    double dti, dxi, dyi;
+    RhsbPlanes B;                               // wall terms of updt_rhs_b (idx = 0: none)
+    int any_rhsb;
+  };
+  const FuseSrc* fuse = nullptr;
+  int fuse_fillps = 1;                          // CANSB200_CTX_FUSE_FILLPS
   int cta_cap = 0;                              // > 0: the persistent tridiagonal kernel uses at most this many CTAs (pipelined exchange)
   int nplans = 0;                               // live plans (some switches are only legal before the first one)
   // host-memory mode: the z planes travel in chunks on two copy streams so that the x / y transforms of a chunk
@@ -231,6 +245,7 @@ struct cansb200_plan {
   long long zsrc_slot = 0;
   DevBuf dtdma_rows;               // ... gathered coefficient rows of all ranks, per cache slot (solve_dist_dtdma)
   unsigned long long solves = 0;
+  int last_fused = 0;              // did the last cansb200_solve_fillps on this plan run the fused forward x transform?
   // TMA descriptors of the pipelined substitution: pivots (per plan) and right-hand sides (per field pointer / shape)
   bool use_tma = true;
   CUtensorMap map_z;
@@ -374,6 +389,9 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
     R2Tables<T>* rt = nullptr;
     int var = ctx->r2_variant[g.ymode ? 1 : 0];
     if (var < 0) var = r2_auto_variant(nt, g.ymode, kind, sizeof(T) == 4);
+    // cansb200_solve_fillps: the forward x transform of that solve reads u, v, w instead of p (variant 0 kernels)
+    const bool fused = !g.ymode && ctx->fuse && kind_is_forward(kind);
+    if (fused) var = 0;
     if (ok) {
       int rc = get_r2_tables<T>(ctx, nt, g.ymode, var, &rt);
       if (rc) return rc;
@@ -389,6 +407,27 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
       A.x0 = g.x0; A.g0 = g.g0; A.smem_pad = g.smem_pad;
       A.flags = (ctx->r2_flags & 3) | ((!g.ymode && ctx->cur_xsplit) ? CB_R2_XSPLIT : 0);
       cb::g_r2_default_carveout = (ctx->r2_flags & 4) ? 0 : 1;
+      if (fused) {
+        const cansb200_ctx::FuseSrc& fs = *ctx->fuse;
+        const long long delta = in - (const T*)fs.pin;   // this launch starts `delta / plane` planes into the slab
+        if (delta < 0 || g.in_gs <= 0 || delta % g.in_gs != 0 || g.line_len != nt)
+          return fail(CANSB200_EINVAL, "r2r: fused fillps source on a launch that is not a run of whole planes");
+        R2Fill<T> F;
+        F.u = (const T*)fs.u + delta; F.v = (const T*)fs.v + delta; F.w = (const T*)fs.w + delta;
+        F.dzfi = (const T*)fs.dzfi;
+        // fillps.f90:35-36: dtidxi = dti*dli(1), dtidyi = dti*dli(2), in the working precision
+        F.dti = (T)fs.dti; F.dtidxi = (T)fs.dti * (T)fs.dxi; F.dtidyi = (T)fs.dti * (T)fs.dyi;
+        F.sj = g.in_ls; F.sk = g.in_gs;
+        F.k0 = (int)(delta / g.in_gs);
+        F.any_rhsb = fs.any_rhsb;
+        for (int d = 0; d < 3; ++d)
+          for (int sd = 0; sd < 2; ++sd) { F.idx[d][sd] = fs.B.idx[d][sd]; F.val[d][sd] = (T)fs.B.val[d][sd]; }
+        const int rcf = r2r2_run_fillps<T>(A, F, nt, st);
+        if (rcf != 0) return fail(rcf < 0 ? CANSB200_ECUDA : CANSB200_EUNSUPPORTED, "r2r: fused fillps launch failed");
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
+      }
       const int rc = !g.ymode ? r2r2_run<T, false, false>(A, nt, var, kind_is_forward(kind), st)
                      : g.row_tab ? r2r2_run<T, true, true>(A, nt, var, kind_is_forward(kind), st)
                                  : r2r2_run<T, true, false>(A, nt, var, kind_is_forward(kind), st);
@@ -400,6 +439,8 @@ static int run_r2r(cansb200_ctx* ctx, int kind, int nt, const T* in, T* out, con
       }
     }
   }
+  if (!g.ymode && ctx->fuse && kind_is_forward(kind))
+    return fail(CANSB200_EUNSUPPORTED, "r2r: the fused fillps source needs a fast-path x length");
   if (g.row_tab) return fail(CANSB200_EUNSUPPORTED, "r2r: the distributed solve needs a fast-path y length (64..2048, 2^k or 3*2^k)");
   if (!g.ymode && ctx->cur_xsplit)
     return fail(CANSB200_EINVAL, "r2r: the plan keeps x in split order (pivot_dedup), which only the fast x transforms write; "
@@ -1106,6 +1147,10 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
     c->host_chunks = value;
     return 0;
   }
+  if (what == CANSB200_CTX_FUSE_FILLPS) {
+    c->fuse_fillps = value ? 1 : 0;
+    return 0;
+  }
   if (what == CANSB200_CTX_R2_FLAGS) {
     if (value < 0 || value > 7) return fail(CANSB200_EINVAL, "ctx_set: r2 flags must be 0..7");
     c->r2_flags = value;
@@ -1275,7 +1320,8 @@ int cansb200_plan_stats(cansb200_plan* pl, unsigned long long stats[4]) {
   CacheState cs;
   CK(cudaMemcpy(&cs, pl->state.p, sizeof(cs), cudaMemcpyDeviceToHost));
   stats[0] = pl->solves; stats[1] = cs.nfactor; stats[2] = pl->ctx->launches; stats[3] = (unsigned long long)pl->th_variant | ((unsigned long long)pl->dx << 4) | ((unsigned long long)pl->dy << 5) |
-             ((unsigned long long)(((pl->dx | pl->dy) && cs.sym_bad) ? 1 : 0) << 6) | ((unsigned long long)pl->jb << 8);
+             ((unsigned long long)(((pl->dx | pl->dy) && cs.sym_bad) ? 1 : 0) << 6) | ((unsigned long long)(pl->last_fused ? 1 : 0) << 7) |
+             ((unsigned long long)pl->jb << 8);
   return 0;
 }
 
@@ -1321,6 +1367,14 @@ template <class T> static bool dist_y_fast(cansb200_plan* pl) {
   if ((ctx->ng[0] % (int)(16 / sizeof(T))) != 0) return false;   // column pairs move as 16-byte vectors
   int radix[4];
   return (sizeof(T) == 4 ? r2r2_query<true, true>(pl->nt[1], 0, radix) : r2r2_query<true, false>(pl->nt[1], 0, radix)) > 0;
+}
+
+// can the forward x transform of this plan take the fused fillps source?  (a two-for-one length over whole lines)
+template <class T> static bool can_fuse_fillps(const cansb200_plan* pl) {
+  const cansb200_ctx* ctx = pl->ctx;
+  if (!ctx->fuse_fillps || ctx->force_generic || !kind_is_fast(pl->kind[0][0]) || pl->nt[0] != ctx->n[0]) return false;
+  int radix[4];
+  return r2r2_query<false, sizeof(T) == 4>(pl->nt[0], 0, radix) > 0;
 }
 
 // the z-slab decomposed solve: x and y transforms on my slab, tridiagonal stage on my z pencil.
@@ -2298,9 +2352,8 @@ int cansb200_fftend(cansb200_ctx* ctx, int id) {
   return 0;
 }
 
-int cansb200_solver(cansb200_ctx* ctx, int id, const char bc[6], const char c_or_f[3], void* p, const int n[3], int nhalo,
-                    double normfft, const void* lambdaxy, const void* a, const void* b, const void* c, int lambda_order,
-                    int mem_kind, void* stream) {
+// the plan behind (fftini id, z boundary conditions, c_or_f(3), eigenvalue order), created on first use
+static int solver_plan(cansb200_ctx* ctx, int id, const char bc[6], const char c_or_f[3], int lambda_order, cansb200_plan** out) {
   if (!ctx || !bc || !c_or_f) return fail(CANSB200_EINVAL, "solver: null argument");
   if (id < 1 || id > (int)ctx->fftini_recs.size() || !ctx->fftini_recs[id - 1].live) return fail(CANSB200_EINVAL, "solver: unknown fftini id");
   auto& rec = ctx->fftini_recs[id - 1];
@@ -2318,13 +2371,32 @@ int cansb200_solver(cansb200_ctx* ctx, int id, const char bc[6], const char c_or
     if (rc) return rc;
     it = rec.byz.emplace(key, pl).first;
   }
-  return cansb200_solve(it->second, p, n, nhalo, normfft, lambdaxy, a, b, c, mem_kind, stream);
+  *out = it->second;
+  return 0;
 }
 
-int cansb200_updt_rhs_b(cansb200_ctx* ctx, const char cf[3], const char bc[6], const int n[3], const int is_bound[6],
-                        const int have[3], const double rhsb[6], double norm, void* p, void* stream) {
-  if (!ctx || !cf || !bc || !n || !is_bound || !have || !rhsb || !p) return fail(CANSB200_EINVAL, "updt_rhs_b: null argument");
-  RhsbPlanes B;
+int cansb200_solver(cansb200_ctx* ctx, int id, const char bc[6], const char c_or_f[3], void* p, const int n[3], int nhalo,
+                    double normfft, const void* lambdaxy, const void* a, const void* b, const void* c, int lambda_order,
+                    int mem_kind, void* stream) {
+  cansb200_plan* pl = nullptr;
+  const int rc = solver_plan(ctx, id, bc, c_or_f, lambda_order, &pl);
+  if (rc) return rc;
+  return cansb200_solve(pl, p, n, nhalo, normfft, lambdaxy, a, b, c, mem_kind, stream);
+}
+
+int cansb200_solver_fillps(cansb200_ctx* ctx, int id, const char bc[6], const char c_or_f[3], void* p, const int n[3], int nhalo,
+                           double normfft, const void* lambdaxy, const void* a, const void* b, const void* c, int lambda_order,
+                           const double dli[3], const void* dzfi, double dti, const void* u, const void* v, const void* w,
+                           const int is_bound[6], const int have[3], const double rhsb[6], void* stream) {
+  cansb200_plan* pl = nullptr;
+  const int rc = solver_plan(ctx, id, bc, c_or_f, lambda_order, &pl);
+  if (rc) return rc;
+  return cansb200_solve_fillps(pl, p, n, nhalo, normfft, lambdaxy, a, b, c, dli, dzfi, dti, u, v, w, is_bound, have, rhsb, stream);
+}
+
+// planes and values of updt_rhs_b's six wall terms (src/bound.f90:514-598)
+static int rhsb_planes(const cansb200_ctx* ctx, const char cf[3], const char bc[6], const int n[3], const int is_bound[6],
+                       const int have[3], const double rhsb[6], double norm, RhsbPlanes& B) {
   for (int d = 0; d < 3; ++d) {
     const int q = (cf[d] == 'f' && bc[2 * d + 1] == 'D') ? 1 : 0;   // src/bound.f90:528-530
     for (int sd = 0; sd < 2; ++sd) {
@@ -2335,6 +2407,15 @@ int cansb200_updt_rhs_b(cansb200_ctx* ctx, const char cf[3], const char bc[6], c
       if (on && B.idx[d][sd] < 1) return fail(CANSB200_EINVAL, "updt_rhs_b: empty direction");
     }
   }
+  return 0;
+}
+
+int cansb200_updt_rhs_b(cansb200_ctx* ctx, const char cf[3], const char bc[6], const int n[3], const int is_bound[6],
+                        const int have[3], const double rhsb[6], double norm, void* p, void* stream) {
+  if (!ctx || !cf || !bc || !n || !is_bound || !have || !rhsb || !p) return fail(CANSB200_EINVAL, "updt_rhs_b: null argument");
+  RhsbPlanes B;
+  const int rcb = rhsb_planes(ctx, cf, bc, n, is_bound, have, rhsb, norm, B);
+  if (rcb) return rcb;
   cudaStream_t st = (cudaStream_t)stream;
   for (int d = 0; d < 3; ++d) {
     if (!B.idx[d][0] && !B.idx[d][1]) continue;
@@ -2361,6 +2442,57 @@ int cansb200_solve(cansb200_plan* pl, void* p, const int n[3], int nhalo, double
   if (rc) return rc;
   rc = ctx->is_fp32 ? solve_impl<float>(pl, p, n, normfft, lambdaxy, a, b, c, mem_kind, st)
                     : solve_impl<double>(pl, p, n, normfft, lambdaxy, a, b, c, mem_kind, st);
+  const int rl = ctx_leave(ctx, st);
+  return rc ? rc : rl;
+}
+
+int cansb200_solve_fillps(cansb200_plan* pl, void* p, const int n[3], int nhalo, double normfft, const void* lambdaxy,
+                          const void* a, const void* b, const void* c, const double dli[3], const void* dzfi, double dti,
+                          const void* u, const void* v, const void* w, const int is_bound[6], const int have[3],
+                          const double rhsb[6], void* stream) {
+  if (!pl || !p || !n || !lambdaxy || !a || !b || !c || !dli || !dzfi || !u || !v || !w)
+    return fail(CANSB200_EINVAL, "solve_fillps: null argument");
+  if (nhalo != 1) return fail(CANSB200_EINVAL, "solve_fillps: nhalo must be 1");
+  cansb200_ctx* ctx = pl->ctx;
+  for (int d = 0; d < 3; ++d)
+    if (n[d] != ctx->n[d]) return fail(CANSB200_EINVAL, "solve_fillps: n differs from the context's local extents");
+  const bool walls = is_bound && have && rhsb;
+  if (!walls && (is_bound || have || rhsb)) return fail(CANSB200_EINVAL, "solve_fillps: is_bound, have and rhsb come together or not at all");
+  cansb200_ctx::FuseSrc fs;
+  fs.u = u; fs.v = v; fs.w = w; fs.dzfi = dzfi;
+  fs.dti = dti; fs.dxi = dli[0]; fs.dyi = dli[1];
+  fs.any_rhsb = 0;
+  for (int d = 0; d < 3; ++d)
+    for (int sd = 0; sd < 2; ++sd) { fs.B.idx[d][sd] = 0; fs.B.val[d][sd] = 0.0; }
+  if (walls) {
+    const int rcb = rhsb_planes(ctx, pl->cf, pl->bc, n, is_bound, have, rhsb, 1.0, fs.B);
+    if (rcb) return rcb;
+    for (int d = 0; d < 3; ++d) fs.any_rhsb |= (fs.B.idx[d][0] | fs.B.idx[d][1]) ? 1 : 0;
+  }
+  const bool fuse = ctx->is_fp32 ? can_fuse_fillps<float>(pl) : can_fuse_fillps<double>(pl);
+  pl->last_fused = fuse ? 1 : 0;
+  if (!fuse) {
+    // lengths / kinds the two-for-one x kernels do not serve: the three steps one after the other (all of them CUDA)
+    int rc = cansb200_fillps(ctx, n, dli, dzfi, dti, u, v, w, p, stream);
+    if (rc) return rc;
+    if (walls && fs.any_rhsb) {
+      rc = cansb200_updt_rhs_b(ctx, pl->cf, pl->bc, n, is_bound, have, rhsb, 1.0, p, stream);
+      if (rc) return rc;
+    }
+    return cansb200_solve(pl, p, n, nhalo, normfft, lambdaxy, a, b, c, CANSB200_MEM_DEVICE, stream);
+  }
+  const size_t esz = ctx->esz;
+  fs.pin = (const char*)p + ((size_t)(n[0] + 2) * (n[1] + 2) + (size_t)(n[0] + 2) + 1) * esz;   // p(1,1,1)
+  // u, v, w as the kernel addresses them: element (1,1,1) of arrays shaped like p
+  const size_t o111 = ((size_t)(n[0] + 2) * (n[1] + 2) + (size_t)(n[0] + 2) + 1) * esz;
+  fs.u = (const char*)u + o111; fs.v = (const char*)v + o111; fs.w = (const char*)w + o111;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ctx_enter(ctx, st);
+  if (rc) return rc;
+  ctx->fuse = &fs;
+  rc = ctx->is_fp32 ? solve_impl<float>(pl, p, n, normfft, lambdaxy, a, b, c, CANSB200_MEM_DEVICE, st)
+                    : solve_impl<double>(pl, p, n, normfft, lambdaxy, a, b, c, CANSB200_MEM_DEVICE, st);
+  ctx->fuse = nullptr;
   const int rl = ctx_leave(ctx, st);
   return rc ? rc : rl;
 }

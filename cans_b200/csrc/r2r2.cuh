@@ -32,6 +32,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "fft_engine.cuh"  // Kind constants
 
 namespace cb {
@@ -420,6 +421,54 @@ __device__ __forceinline__ R2Rows<T, YMODE, SPLIT, FULL> r2_rows(const T* p, lon
   return R;
 }
 
+// ---- fused source of the forward x transform: fillps (+ updt_rhs_b) evaluated at load time ----------------------
+// The right-hand side of the pressure Poisson equation is the scaled divergence of the prediction velocity
+// (/root/reference/src/fillps.f90:38-50) plus the wall terms of updt_rhs_b (src/bound.f90:514-598), and the first thing
+// `solver` does with it is the forward x transform.  With this source the transform's loads evaluate
+//     p(i,j,k) = (w(i,j,k)-w(i,j,k-1))*dti*dzfi(k) + (v(i,j,k)-v(i,j-1,k))*dtidyi + (u(i,j,k)-u(i-1,j,k))*dtidxi
+// (same expression, same operation order as the stand-alone fillps kernel) straight from u, v, w: p is never written and
+// re-read (-16 B/point of HBM traffic on the two steps).  u, v, w are haloed like p and point at element (1,1,1).
+template <class T> struct R2Fill {
+  const T *u, *v, *w;
+  const T* dzfi;        // dzfi(0:n3+1) of the local slab
+  T dti, dtidxi, dtidyi;
+  long long sj, sk;     // strides of j and k in the haloed arrays
+  int k0;               // 0-based interior plane of group 0 of this launch (launches on z chunks)
+  int any_rhsb;         // updt_rhs_b: any wall term at all?
+  int idx[3][2];        // 1-based interior index of the plane that takes the wall term of (direction, side), 0 = none
+  T val[3][2];          // rhsb * norm
+};
+// one line (j, k) of the fused source
+template <class T> struct R2FillLine {
+  const T *u, *v, *vm, *w, *wm;   // x = 0 of u(:,j,k), v(:,j,k), v(:,j-1,k), w(:,j,k), w(:,j,k-1)
+  T dz;                           // dzfi(k)
+  bool y0, y1, z0, z1;            // the line lies in the plane that takes the wall term of (y | z, lower | upper)
+  __device__ __forceinline__ R2FillLine(const R2Fill<T>& F, long long off, int g, int j) {
+    u = F.u + off; v = F.v + off; w = F.w + off;
+    vm = v - F.sj; wm = w - F.sk;
+    const int k = F.k0 + g;       // 0-based interior plane
+    dz = __ldg(F.dzfi + k + 1);
+    y0 = j + 1 == F.idx[1][0]; y1 = j + 1 == F.idx[1][1];
+    z0 = k + 1 == F.idx[2][0]; z1 = k + 1 == F.idx[2][1];
+  }
+  // sample i (0-based) of the line
+  __device__ __forceinline__ T at(const R2Fill<T>& F, int i) const {
+    T r = (w[i] - wm[i]) * F.dti * dz + (v[i] - vm[i]) * F.dtidyi + (u[i] - u[i - 1]) * F.dtidxi;
+    if (F.any_rhsb) {   // uniform branch; the six terms are added one after the other as the reference's six loops do
+      if (i + 1 == F.idx[0][0]) r += F.val[0][0];
+      if (i + 1 == F.idx[0][1]) r += F.val[0][1];
+      if (y0) r += F.val[1][0];
+      if (y1) r += F.val[1][1];
+      if (z0) r += F.val[2][0];
+      if (z1) r += F.val[2][1];
+    }
+    return r;
+  }
+};
+
+// kernel arguments of the fused variant: the transform's own arguments followed by the source
+template <class T> struct R2ArgsFill : R2Args<T> { R2Fill<T> F; };
+
 // thread part of the positions a thread touches in stage S (the part that does not depend on the unrolled
 // indices m, q), and the compile-time remainder; their bit sets are disjoint for power-of-two plans
 template <class Cfg, int S> __device__ __forceinline__ int r2_stage_tpos(int t) {
@@ -535,9 +584,18 @@ template <class T, class Cfg, bool YMODE> struct R2Pair {
 };
 
 // ---- forward kinds: R2HC, REDFT10, RODFT10 ---------------------------------------------------------
-template <class T, class Cfg, bool YMODE, bool SPLIT, int KIND, bool FULL>
-__global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(const R2Args<T> A) {
+// ARGS = R2Args<T>: samples come from A.in;  ARGS = R2ArgsFill<T>: x mode only, samples are evaluated from u, v, w (fused
+// fillps, A.F).  Five row pointers per line come on top of the samples there: a quarter fewer CTAs per SM than the plain
+// kernel keeps the register allocation free of spills (ptxas -v).
+template <class ARGS, class T> __host__ __device__ constexpr bool r2_fused() { return !std::is_same<ARGS, R2Args<T>>::value; }
+template <class Cfg, bool FUSED> __host__ __device__ constexpr int r2_fwd_minb() {
+  return FUSED ? Cfg::MINB - (Cfg::MINB >= 4 ? Cfg::MINB / 4 : 0) : Cfg::MINB;
+}
+template <class T, class Cfg, bool YMODE, bool SPLIT, int KIND, bool FULL, class ARGS = R2Args<T>>
+__global__ void __launch_bounds__(Cfg::TPL* Cfg::G, r2_fwd_minb<Cfg, r2_fused<ARGS, T>()>()) r2r2_fwd_kernel(const ARGS A) {
   static_assert(KIND == K_R2HC || KIND == K_REDFT10 || KIND == K_RODFT10, "forward kinds");
+  constexpr bool FUSED = r2_fused<ARGS, T>();
+  static_assert(!FUSED || (!YMODE && !SPLIT && FULL), "the fused source feeds the contiguous (x) transforms");
   static_assert(YMODE || r2_group_local<Cfg>(), "x mode relies on per-transform barriers");
   static_assert(!SPLIT || YMODE, "split rows exist only for the strided (y) transforms");
   using C = Cx<T>;
@@ -557,7 +615,33 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
   using RowsOut = R2Rows<T, YMODE, SPLIT, FULL>;
 
   C v[E];
-  {
+  if constexpr (FUSED) {
+    // the same samples, evaluated from the velocity field (R2Fill); x index of a sample = base + compile-time offset
+    constexpr int R0 = Cfg::R(0), L0 = N / R0;
+    const R2Fill<T>& S = A.F;
+    // (plane, row) of my two lines, as r2_locate finds them
+    const unsigned lpg = (unsigned)A.lines_per_group;
+    const unsigned l0 = (blockIdx.x * (unsigned)G + (unsigned)c) * 2u;
+    const unsigned ga = l0 / lpg, ja = l0 - ga * lpg;
+    const bool wrap = ja + 1u == lpg;
+    const unsigned gb = !loc.has_b ? ga : (wrap ? ga + 1u : ga), jb = !loc.has_b ? ja : (wrap ? 0u : ja + 1u);
+    const R2FillLine<T> la(S, loc.ia, (int)ga, (int)ja), lb(S, loc.ib, (int)gb, (int)jb);
+    const int b_up = trig ? 2 * t : t, b_dn = -2 * t;
+#pragma unroll
+    for (int m = 0; m < E / R0; ++m)
+#pragma unroll
+      for (int q = 0; q < R0; ++q) {
+        const int cj = q * L0 + TPL * m;
+        C x;
+        if (!trig) x = C{la.at(S, b_up + cj), lb.at(S, b_up + cj)};
+        else if (cj < N / 2) x = C{la.at(S, b_up + 2 * cj), lb.at(S, b_up + 2 * cj)};
+        else {
+          x = C{la.at(S, b_dn + 2 * N - 1 - 2 * cj), lb.at(S, b_dn + 2 * N - 1 - 2 * cj)};
+          if (neg_odd) x = {-x.x, -x.y};   // odd input rows
+        }
+        v[m * R0 + q] = x;
+      }
+  } else {
     // natural-order samples j = t + cj; Makhoul: input row 2 j (cj < N/2) or 2 (N - 1 - j) + 1
     constexpr int R0 = Cfg::R(0), L0 = N / R0;
     const RowsIn in_up = r2_rows<T, YMODE, false, FULL>(A.in, loc.ia, loc.ib, A.in_es, nullptr, loc, trig ? 2 * t : t);
@@ -579,8 +663,8 @@ __global__ void __launch_bounds__(Cfg::TPL* Cfg::G, Cfg::MINB) r2r2_fwd_kernel(c
   }
   const RowsOut out_up = r2_rows<T, YMODE, SPLIT, FULL>(A.out, loc.oa, loc.ob, A.out_es, A.row_tab, loc, t);
   const RowsOut out_dn = r2_rows<T, YMODE, SPLIT, FULL>(A.out, loc.oa, loc.ob, A.out_es, A.row_tab, loc, TPL - t);
-  // copy the untransformed tail when the result goes to another array
-  if (A.line_len > N && (SPLIT || A.in != A.out)) {
+  // copy the untransformed tail when the result goes to another array (never with the fused source: line_len == N there)
+  if (!FUSED && A.line_len > N && (SPLIT || A.in != A.out)) {
     const RowsIn in_t = r2_rows<T, YMODE, false, FULL>(A.in, loc.ia, loc.ib, A.in_es, nullptr, loc, t);
     for (int i = N; i + t < A.line_len; i += TPL) {
       const C x = in_t.load(i);

@@ -130,6 +130,44 @@ template <class T, bool YMODE, bool SPLIT> int r2r2_run(const R2Args<T>& A, int 
 #undef CB_R2_CASE
 }
 
+// forward x transform fed by the fused fillps source (R2Fill): variant 0 of every instantiated length.
+// 0 = launched, 1 = no instantiation for this length, < 0 = error
+template <class T, class Cfg> static int r2r2_launch_fill(const R2Args<T>& A0, const R2Fill<T>& F, cudaStream_t st) {
+  R2ArgsFill<T> A;
+  static_cast<R2Args<T>&>(A) = A0;
+  A.F = F;
+  using Lay = R2Lay<T, Cfg, false>;
+  const size_t smem = Lay::smem_bytes();
+  const long long npairs = ((long long)A.lines_per_group * A.ngroups + 1) / 2;
+  const long long grid = (npairs + Cfg::G - 1) / Cfg::G;
+  if (grid < 1) return 0;
+  if (grid > 0x7fffffffLL || (long long)A.lines_per_group * A.ngroups > 0x7ffffff0LL) return -2;
+  if (A.line_len != Cfg::N) return 1;   // the fused source has no untransformed tail
+  auto launch = [&](auto k) -> int {
+    static std::set<const void*> done;
+    if (!done.count((const void*)k)) {
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+      done.insert((const void*)k);
+    }
+    void* kargs[1] = {&A};
+    return cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(Cfg::TPL * Cfg::G), kargs, smem, st) == cudaSuccess ? 0 : -4;
+  };
+  switch (A.kind) {
+    case K_R2HC: return launch(r2r2_fwd_kernel<T, Cfg, false, false, K_R2HC, true, R2ArgsFill<T>>);
+    case K_REDFT10: return launch(r2r2_fwd_kernel<T, Cfg, false, false, K_REDFT10, true, R2ArgsFill<T>>);
+    case K_RODFT10: return launch(r2r2_fwd_kernel<T, Cfg, false, false, K_RODFT10, true, R2ArgsFill<T>>);
+    default: return -5;
+  }
+}
+template <class T> int r2r2_run_fillps(const R2Args<T>& A, const R2Fill<T>& F, int n, cudaStream_t st) {
+#define CB_R2_CASE(N_, V_, TPL_, G_, MB_, R0_, R1_, R2_, R3_) \
+  case N_ * 4 + V_:                                           \
+    if constexpr (V_ == 0) return r2r2_launch_fill<T, R2Cfg<N_, TPL_, G_, MB_, R0_, R1_, R2_, R3_>>(A, F, st); \
+    else return 1;
+  switch (n * 4) { CB_R2_X_CONFIGS(CB_R2_CASE) default: return 1; }
+#undef CB_R2_CASE
+}
+
 // radices of variant `var` for length n (host-side table construction); returns the stage count or 0
 template <bool YMODE, bool F32> int r2r2_query(int n, int var, int radix[4]) {
 #define CB_R2_CASE(N_, V_, TPL_, G_, MB_, R0_, R1_, R2_, R3_) \

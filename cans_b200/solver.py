@@ -175,6 +175,11 @@ class Context:
         reference's operation order, None = automatic (on chip for slabs of at least 193 rows in FP64)."""
         check(lib.cansb200_ctx_set(self._h, 15, 1 if on is None else (2 if on else 0)), "ctx_set")
 
+    def set_fuse_fillps(self, on: bool = True):
+        """`solver_fillps`: evaluate fillps (+ updt_rhs_b) inside the forward x transform (default) or run the three steps
+        one after the other."""
+        check(lib.cansb200_ctx_set(self._h, 16, int(on)), "ctx_set")
+
     def set_zmajor(self, on: bool = True):
         """One-GPU solves: z-major intermediate between the y transforms and the tridiagonal stage."""
         check(lib.cansb200_ctx_set(self._h, 8, int(on)), "ctx_set")
@@ -247,7 +252,7 @@ class Plan:
                 "pivot_dedup_x": (s[3] >> 4) & 1, "pivot_dedup_y": (s[3] >> 5) & 1,
                 # set if a lambdaxy WITHOUT the mirror symmetry reached a plan whose cache is deduplicated after its first solve
                 # (the first solve checks and falls back; later solves only record the violation here)
-                "pivot_dedup_violation": (s[3] >> 6) & 1, "tall_tile_rows": (s[3] >> 8) & 0xFFFF}
+                "pivot_dedup_violation": (s[3] >> 6) & 1, "fillps_fused": (s[3] >> 7) & 1, "tall_tile_rows": (s[3] >> 8) & 0xFFFF}
 
     def destroy(self):
         if self._h:
@@ -422,6 +427,38 @@ def solver(n, ng, arrplan: Plan, normfft, lambdaxy, a, b, c, bc, c_or_f, p, stre
         raise ValueError(f"solver: p has shape {tuple(p.shape)}, expected {want}")
     check(lib.cansb200_solve(arrplan.handle, _ptr(p), i3(n), 1, float(normfft), _ptr(lambdaxy), _ptr(a), _ptr(b), _ptr(c),
                              MEM_DEVICE if dev else MEM_HOST, _stream_ptr(stream)), "cansb200_solve")
+    return p
+
+
+def solver_fillps(n, ng, arrplan: Plan, normfft, lambdaxy, a, b, c, bc, c_or_f, dli, dzfi, dti, u, v, w, p,
+                  is_bound=None, rhsbx=None, rhsby=None, rhsbz=None, stream=None):
+    """`fillps` + `updt_rhs_b` + `solver` of the pressure-correction step (src/main.f90:465-467) as ONE call on device
+    arrays: the forward x transform evaluates the right-hand side from u, v, w at load time (`cansb200_solve_fillps`), p only
+    receives the solution.  The first ten arguments are `solver`'s, `dli, dzfi, dti, u, v, w` are `fillps`'s, `is_bound,
+    rhsbx, rhsby, rhsbz` are `updt_rhs_b`'s ([lower, upper] wall values or None)."""
+    if list(c_or_f) != arrplan.c_or_f or [list(x) for x in bc] != arrplan.cbc:
+        raise ValueError("solver_fillps: bc / c_or_f differ from the ones the plan (arrplan) was created with")
+    for name, arr in (("p", p), ("u", u), ("v", v), ("w", w), ("dzfi", dzfi), ("lambdaxy", lambdaxy), ("a", a), ("b", b), ("c", c)):
+        if not (_is_torch(arr) and arr.is_cuda):
+            raise ValueError(f"solver_fillps: {name} must be a CUDA tensor (device arrays only)")
+    want = (n[2] + 2, n[1] + 2, n[0] + 2)
+    for name, arr in (("p", p), ("u", u), ("v", v), ("w", w)):
+        if tuple(arr.shape) != want:
+            raise ValueError(f"solver_fillps: {name} has shape {tuple(arr.shape)}, expected {want}")
+    if tuple(dzfi.shape) != (n[2] + 2,):
+        raise ValueError("solver_fillps: dzfi must have n(3)+2 entries (0:n3+1)")
+    walls = any(r is not None for r in (rhsbx, rhsby, rhsbz))
+    isb = have = vals = None
+    if walls:
+        if is_bound is None:
+            raise ValueError("solver_fillps: is_bound is needed with rhsbx / rhsby / rhsbz")
+        rh = [r if r is not None else [0.0, 0.0] for r in (rhsbx, rhsby, rhsbz)]
+        have = (C.c_int * 3)(*[int(r is not None) for r in (rhsbx, rhsby, rhsbz)])
+        isb = (C.c_int * 6)(*[int(bool(is_bound[d][sd])) for d in range(3) for sd in range(2)])
+        vals = (C.c_double * 6)(*[float(rh[d][sd]) for d in range(3) for sd in range(2)])
+    check(lib.cansb200_solve_fillps(arrplan.handle, _ptr(p), i3(n), 1, float(normfft), _ptr(lambdaxy), _ptr(a), _ptr(b), _ptr(c),
+                                    d3(dli), _ptr(dzfi), float(dti), _ptr(u), _ptr(v), _ptr(w), isb, have, vals,
+                                    _stream_ptr(stream)), "cansb200_solve_fillps")
     return p
 
 

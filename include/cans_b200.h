@@ -190,6 +190,26 @@ int cansb200_chkdiv(cansb200_ctx* ctx, const int n[3], const double dli[3], cons
                     const void* u, const void* v, const void* w, double* divtot_sum, double* divmax,
                     void* stream);
 
+/* -- the pressure-correction right-hand side fused into the solve (device pointers): one call for
+ *      call fillps(n,dli,dzfi,dtrki,u,v,w,pp)                                          src/main.f90:465, src/fillps.f90:13-51
+ *      call updt_rhs_b(['c','c','c'],cbcpre,n,is_bound,rhsbp%x,rhsbp%y,rhsbp%z,pp)     src/main.f90:466, src/bound.f90:514-598
+ *      call solver(n,ng,arrplanp,normfftp,lambdaxyp,ap,bp,cp,cbcpre,['c','c','c'],pp)  src/main.f90:467
+ *    The forward x transform evaluates its samples from u, v, w at load time, so the right-hand side is never written to
+ *    p and read back (16 B/point less HBM traffic on the two steps); p receives the solution only.  is_bound / have / rhsb
+ *    as in cansb200_updt_rhs_b (norm = 1; boundary conditions and c_or_f are the plan's), all three NULL = no wall terms.
+ *    Same result as the three separate calls to rounding (the divergence is evaluated by the same expression).  x lengths /
+ *    kinds the two-for-one kernels do not serve, and a context with CANSB200_CTX_FUSE_FILLPS = 0, run the three steps one
+ *    after the other instead; bit 7 of cansb200_plan_stats()[3] tells which.  Works on one rank and on z slabs (dzfi, u, v, w
+ *    are the rank's own slab, as in the reference).  cansb200_solver_fillps is the same through an fftini id. */
+int cansb200_solve_fillps(cansb200_plan* plan, void* p, const int n[3], int nhalo, double normfft, const void* lambdaxy,
+                          const void* a, const void* b, const void* c, const double dli[3], const void* dzfi, double dti,
+                          const void* u, const void* v, const void* w, const int is_bound[6], const int have[3],
+                          const double rhsb[6], void* stream);
+int cansb200_solver_fillps(cansb200_ctx* ctx, int id, const char bc[6], const char c_or_f[3], void* p, const int n[3], int nhalo,
+                           double normfft, const void* lambdaxy, const void* a, const void* b, const void* c, int lambda_order,
+                           const double dli[3], const void* dzfi, double dti, const void* u, const void* v, const void* w,
+                           const int is_bound[6], const int have[3], const double rhsb[6], void* stream);
+
 /* -- synthetic input: counter-based uniform(-1,1) field indexed by the GLOBAL (i,j,k)
  *    (SURVEY.md 8d); fills the interior of a haloed device array, halo set to 0. */
 int cansb200_fill_hash(cansb200_ctx* ctx, void* p, const int n[3], const int lo[3], int nhalo,
@@ -200,7 +220,8 @@ const char* cansb200_last_error(void);
 int cansb200_version(void);
 /* counters since plan creation: [0] solves, [1] factorisations run, [2] kernels launched (context-wide),
  * [3] bits 0-3 tridiagonal variant in use, bit 4 / 5 pivot cache deduplicated in x / y (after the first solve's check),
- *     bit 6 a later lambdaxy violated the symmetry the deduplicated cache relies on, bits 8-23 y rows per tall tile */
+ *     bit 6 a later lambdaxy violated the symmetry the deduplicated cache relies on, bit 7 the last cansb200_solve_fillps ran
+ *     the fused forward x transform, bits 8-23 y rows per tall tile */
 int cansb200_plan_stats(cansb200_plan* plan, unsigned long long stats[4]);
 /* per-stage device timing with CUDA events on the solve's stream (the role of the reference's
  * unused timer_tic/toc CUDA-event pool, src/timer.f90:113-216).  Stages of one solve:
@@ -245,6 +266,8 @@ enum {
   CANSB200_CTX_DTDMA_TILED = 15,  /* distributed TDMA, slab-local elimination: 2 = on chip in the pipelined tridiagonal kernel (24 B/point),
                                     0 = one thread per column sweeping through HBM in the reference's operation order (48 B/point),
                                     -1 / 1 (default) = on chip when the slab has at least 4 rows per thread of a tile (>= 193 rows in FP64) */
+  CANSB200_CTX_FUSE_FILLPS = 16,  /* cansb200_solve_fillps: 1 (default) = the forward x transform evaluates fillps (+ updt_rhs_b) at load time,
+                                    0 = fillps, updt_rhs_b and the solve run one after the other */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
                                     bit 2 = force the maximum shared-memory carveout (default: the driver picks, which leaves L1 to the twiddles) */
 };
