@@ -202,6 +202,7 @@ struct cansb200_ctx {
   };
   const FuseSrc* fuse = nullptr;
   int fuse_fillps = 1;                          // CANSB200_CTX_FUSE_FILLPS
+  int aux_3d = 1;                               // CANSB200_CTX_AUX_3D: fillps / correc with the 3-D launch geometry
   int cta_cap = 0;                              // > 0: the persistent tridiagonal kernel uses at most this many CTAs (pipelined exchange)
   int nplans = 0;                               // live plans (some switches are only legal before the first one)
   // host-memory mode: the z planes travel in chunks on two copy streams so that the x / y transforms of a chunk
@@ -1145,6 +1146,10 @@ int cansb200_ctx_set(cansb200_ctx* c, int what, int value) {
   if (what == CANSB200_CTX_HOST_CHUNKS) {
     if (value < 1 || value > 64) return fail(CANSB200_EINVAL, "ctx_set: host_chunks must be 1..64");
     c->host_chunks = value;
+    return 0;
+  }
+  if (what == CANSB200_CTX_AUX_3D) {
+    c->aux_3d = value ? 1 : 0;
     return 0;
   }
   if (what == CANSB200_CTX_FUSE_FILLPS) {
@@ -2525,6 +2530,18 @@ int cansb200_gaussel(cansb200_plan* pl, void* pz, const int d3[3], int n_rows, i
                                    (const double*)lam, (const double*)a, (const double*)b, (const double*)c, st);
 }
 
+// launch geometry of the 3-D step kernels: 256 threads, x first; false when an extent exceeds the grid limits
+static bool aux_geom(int ex, int ey, int ez, dim3& grid, dim3& block) {
+  int bx = 32;
+  while (bx < 256 && bx < ex) bx *= 2;
+  const int by = 256 / bx;
+  const long long gy = ((long long)ey + by - 1) / by;
+  if (ex < 1 || ey < 1 || ez < 1 || gy > 65535 || ez > 65535) return false;
+  block = dim3((unsigned)bx, (unsigned)by, 1);
+  grid = dim3((unsigned)((ex + bx - 1) / bx), (unsigned)gy, (unsigned)ez);
+  return true;
+}
+
 int cansb200_fill_hash(cansb200_ctx* ctx, void* p, const int n[3], const int lo[3], int nhalo, unsigned long long seed,
                        void* stream) {
   if (!ctx || !p || !n || !lo) return fail(CANSB200_EINVAL, "fill_hash: null argument");
@@ -2545,6 +2562,18 @@ int cansb200_fillps(cansb200_ctx* ctx, const int n[3], const double dli[3], cons
                     const void* v, const void* w, void* p, void* stream) {
   if (!ctx || !n || !dli || !dzfi || !u || !v || !w || !p) return fail(CANSB200_EINVAL, "fillps: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  dim3 g3, b3;
+  if (ctx->aux_3d && aux_geom(n[0], n[1], n[2], g3, b3)) {
+    if (ctx->is_fp32)
+      fillps3d_kernel<float><<<g3, b3, 0, st>>>(n[0], n[1], (float)dli[0], (float)dli[1], (const float*)dzfi, (float)dti, (const float*)u,
+                                                (const float*)v, (const float*)w, (float*)p);
+    else
+      fillps3d_kernel<double><<<g3, b3, 0, st>>>(n[0], n[1], dli[0], dli[1], (const double*)dzfi, dti, (const double*)u, (const double*)v,
+                                                 (const double*)w, (double*)p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
   const long long tot = (long long)n[0] * n[1] * n[2];
   const unsigned blocks = (unsigned)((tot + 255) / 256);
   if (ctx->is_fp32)
@@ -2562,6 +2591,18 @@ int cansb200_correc(cansb200_ctx* ctx, const int n[3], const double dli[3], cons
                     void* v, void* w, void* stream) {
   if (!ctx || !n || !dli || !dzci || !u || !v || !w || !p) return fail(CANSB200_EINVAL, "correc: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  dim3 g3, b3;
+  if (ctx->aux_3d && aux_geom(n[0] + 2, n[1] + 2, n[2] + 2, g3, b3)) {
+    if (ctx->is_fp32)
+      correc3d_kernel<float><<<g3, b3, 0, st>>>(n[0], n[1], n[2], (float)dli[0], (float)dli[1], (const float*)dzci, (float)dt, (const float*)p,
+                                                (float*)u, (float*)v, (float*)w);
+    else
+      correc3d_kernel<double><<<g3, b3, 0, st>>>(n[0], n[1], n[2], dli[0], dli[1], (const double*)dzci, dt, (const double*)p, (double*)u,
+                                                 (double*)v, (double*)w);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
   const long long tot = (long long)(n[0] + 2) * (n[1] + 2) * (n[2] + 2);
   const unsigned blocks = (unsigned)((tot + 255) / 256);
   if (ctx->is_fp32)

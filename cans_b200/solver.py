@@ -180,6 +180,10 @@ class Context:
         one after the other."""
         check(lib.cansb200_ctx_set(self._h, 16, int(on)), "ctx_set")
 
+    def set_aux_3d(self, on: bool = True):
+        """`fillps` / `correc`: kernels with the 3-D launch geometry (default) or the flat-index ones."""
+        check(lib.cansb200_ctx_set(self._h, 17, int(on)), "ctx_set")
+
     def set_zmajor(self, on: bool = True):
         """One-GPU solves: z-major intermediate between the y transforms and the tridiagonal stage."""
         check(lib.cansb200_ctx_set(self._h, 8, int(on)), "ctx_set")

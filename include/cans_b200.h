@@ -268,6 +268,8 @@ enum {
                                     -1 / 1 (default) = on chip when the slab has at least 4 rows per thread of a tile (>= 193 rows in FP64) */
   CANSB200_CTX_FUSE_FILLPS = 16,  /* cansb200_solve_fillps: 1 (default) = the forward x transform evaluates fillps (+ updt_rhs_b) at load time,
                                     0 = fillps, updt_rhs_b and the solve run one after the other */
+  CANSB200_CTX_AUX_3D = 17,       /* cansb200_fillps / _correc: 1 (default) = kernels with a 3-D launch geometry (no index division per
+                                    point), 0 = the flat-index kernels (also the fallback for extents beyond the grid limits) */
   CANSB200_CTX_R2_FLAGS = 5      /* cache hints of the fast transforms: bit 0 = field loads bypass L1 allocation, bit 1 = streaming stores,
                                     bit 2 = force the maximum shared-memory carveout (default: the driver picks, which leaves L1 to the twiddles) */
 };
