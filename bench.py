@@ -530,12 +530,15 @@ def main():
         heavy = {k: v for k, v in stage_ms.items() if k != "pivot_cache"}
         dom = max(heavy, key=heavy.get)
     stage_bytes = STAGE_BYTES_PER_POINT_FP64 * (esz / 8.0) * npts_local   # per GPU: each rank's launch covers its local points
+    fused_x = args.fillps and dom == "fft_x_fwd"
+    if fused_x:   # the fused forward x transform reads u, v, w (24 B/point) and writes the field (8)
+        stage_bytes = 32.0 * (esz / 8.0) * npts_local
     achieved = stage_bytes / (stage_ms[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = None if fp32 else json.load(open(tpath)).get(args.workload, {}).get(dom)
+            traffic = None if fp32 else json.load(open(tpath)).get(args.workload, {}).get("fft_x_fwd_fillps" if fused_x else dom)
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
