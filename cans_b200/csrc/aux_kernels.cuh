@@ -103,6 +103,18 @@ __global__ void chkdiv_kernel(int n1, int n2, int n3, T dxi, T dyi, const T* __r
 // same operation order.  Used whenever the extents fit the grid limits.  Measured on C3 (profiles/r2_bench_steps.json):
 // fillps 1.84 -> 1.34 ms (6.4 TB/s), correc 3.33 -> 2.89 ms (5.2 TB/s).  chkdiv keeps its capped grid-stride kernel: with one
 // CTA per 256 points the two atomics per CTA made it slower (3.9 against 2.8 ms), so that variant is not kept.
+// launch geometry of these kernels: 256 threads, x first; false when an extent exceeds the grid limits (flat kernels then)
+inline bool aux_geom(int ex, int ey, int ez, dim3& grid, dim3& block) {
+  int bx = 32;
+  while (bx < 256 && bx < ex) bx *= 2;
+  const int by = 256 / bx;
+  const long long gy = ((long long)ey + by - 1) / by;
+  if (ex < 1 || ey < 1 || ez < 1 || gy > 65535 || ez > 65535) return false;
+  block = dim3((unsigned)bx, (unsigned)by, 1);
+  grid = dim3((unsigned)((ex + bx - 1) / bx), (unsigned)gy, (unsigned)ez);
+  return true;
+}
+
 template <class T>
 __global__ void fillps3d_kernel(int n1, int n2, T dxi, T dyi, const T* __restrict__ dzfi, T dti, const T* __restrict__ u,
                                 const T* __restrict__ v, const T* __restrict__ w, T* __restrict__ p) {

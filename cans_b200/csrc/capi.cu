@@ -2530,18 +2530,6 @@ int cansb200_gaussel(cansb200_plan* pl, void* pz, const int d3[3], int n_rows, i
                                    (const double*)lam, (const double*)a, (const double*)b, (const double*)c, st);
 }
 
-// launch geometry of the 3-D step kernels: 256 threads, x first; false when an extent exceeds the grid limits
-static bool aux_geom(int ex, int ey, int ez, dim3& grid, dim3& block) {
-  int bx = 32;
-  while (bx < 256 && bx < ex) bx *= 2;
-  const int by = 256 / bx;
-  const long long gy = ((long long)ey + by - 1) / by;
-  if (ex < 1 || ey < 1 || ez < 1 || gy > 65535 || ez > 65535) return false;
-  block = dim3((unsigned)bx, (unsigned)by, 1);
-  grid = dim3((unsigned)((ex + bx - 1) / bx), (unsigned)gy, (unsigned)ez);
-  return true;
-}
-
 int cansb200_fill_hash(cansb200_ctx* ctx, void* p, const int n[3], const int lo[3], int nhalo, unsigned long long seed,
                        void* stream) {
   if (!ctx || !p || !n || !lo) return fail(CANSB200_EINVAL, "fill_hash: null argument");
