@@ -233,7 +233,7 @@ contains
     id = arrplan(1,1)
 #endif
     isb = merge(1,0,[is_bound(0,1),is_bound(1,1),is_bound(0,2),is_bound(1,2),is_bound(0,3),is_bound(1,3)]); have = 1
-    !$acc update self(rhsbx(1,1,0:1),rhsby(1,1,0:1),rhsbz(1,1,0:1))
+    ! rhsb* are filled on the host by initsolver and only copied to the device afterwards: the host copies are current
     rh = real([rhsbx(1,1,0),rhsbx(1,1,1),rhsby(1,1,0),rhsby(1,1,1),rhsbz(1,1,0),rhsbz(1,1,1)],c_double); dl3 = real(dli,c_double)
     !$acc host_data use_device(p,lambdaxy,a,b,c,dzfi,u,v,w)
     istat = cansb200_solver_fillps(ctx,id,b6,cf,c_loc(p),n,1,real(normfft,c_double),c_loc(lambdaxy),c_loc(a),c_loc(b),c_loc(c), &
