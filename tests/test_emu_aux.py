@@ -16,6 +16,8 @@ IDS = [f"{s[0][0]}x{s[0][1]}x{s[0][2]}_{np.dtype(s[1]).name}" for s in SHAPES]
 
 
 def _emu(dt, op, ng, d, *params):
+    if not os.path.exists(EMU):   # built by __graft_entry__.build() (conftest's session fixture)
+        pytest.skip("tests/_build/emu_aux was not built (g++ or the CUDA headers are missing)")
     prec = "f32" if dt == np.float32 else "f64"
     r = subprocess.run([EMU, prec, op, str(ng[0]), str(ng[1]), str(ng[2]), str(d)] + [repr(float(p)) if not isinstance(p, (int, np.integer)) else str(int(p)) for p in params],
                        capture_output=True, text=True)
