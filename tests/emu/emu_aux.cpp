@@ -8,6 +8,9 @@
 //   updt_rhs_b               idx(6) val(6)            p               -> p_out
 //   lambda_unpack            px py sx                 lam (n1 x n2)   -> lam_out
 //   fill_hash                o1 o2 o3 ng1 ng2 nh seed                 -> p_out
+//   fill_source              dxi dyi dti idx(6) val(6) kc   u v w dzfi -> p_out   (R2Fill / R2FillLine of r2_fill.cuh: the loads of
+//                            the fused forward x transform, evaluated for every interior point as two launches on the z
+//                            chunks [0, kc) and [kc, n3), set up the way capi.cu's run_r2r sets them up)
 // TEST INFRASTRUCTURE (the product launches the same kernels through capi.cu).
 #include <cmath>
 #include <cstdio>
@@ -31,7 +34,10 @@ static inline unsigned long long atomicCAS(unsigned long long* a, unsigned long 
 static inline double atomicAdd(double* a, double v) { const double o = *a; *a += v; return o; }
 static inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
 
+template <class T> static T __ldg(const T* p) { return *p; }
+
 #include "../../cans_b200/csrc/aux_kernels.cuh"
+#include "../../cans_b200/csrc/r2_fill.cuh"
 
 using namespace cb;
 
@@ -109,6 +115,34 @@ template <class T> static int run(const std::string& op, int n1, int n2, int n3,
     std::vector<T> out((size_t)n1 * n2);
     launch(dim3(3), dim3(64), [&] { lambda_unpack_kernel<T>(lam.data(), out.data(), n1, n2, (int)num(0), (int)num(1), (int)num(2)); });
     wr(dir, "lam_out", out);
+  } else if (op == "fill_source") {
+    auto u = rd<T>(dir, "u", nh), v = rd<T>(dir, "v", nh), w = rd<T>(dir, "w", nh);
+    auto dzfi = rd<T>(dir, "dzfi", n3 + 2);
+    std::vector<T> p(nh, (T)3.25);
+    const long long px = n1 + 2, plane = px * (n2 + 2), o111 = plane + px + 1;
+    const int kc = (int)num(15);
+    for (int chunk = 0; chunk < 2; ++chunk) {
+      const int k0 = chunk ? kc : 0, nk = chunk ? n3 - kc : kc;
+      const long long delta = (long long)k0 * plane;   // `in - fs.pin` of the launch
+      R2Fill<T> F;
+      F.u = u.data() + o111 + delta; F.v = v.data() + o111 + delta; F.w = w.data() + o111 + delta;
+      F.dzfi = dzfi.data();
+      F.dti = (T)num(2); F.dtidxi = (T)num(2) * (T)num(0); F.dtidyi = (T)num(2) * (T)num(1);
+      F.sj = px; F.sk = plane; F.k0 = k0;
+      F.any_rhsb = 0;
+      for (int d = 0; d < 3; ++d)
+        for (int sd = 0; sd < 2; ++sd) {
+          F.idx[d][sd] = (int)num(3 + 2 * d + sd); F.val[d][sd] = (T)num(9 + 2 * d + sd);
+          F.any_rhsb |= F.idx[d][sd] ? 1 : 0;
+        }
+      for (int g = 0; g < nk; ++g)
+        for (int j = 0; j < n2; ++j) {
+          const long long off = (long long)g * plane + (long long)j * px;   // R2Loc::ia of line (g, j)
+          const R2FillLine<T> L(F, off, g, j);
+          for (int i = 0; i < n1; ++i) p[o111 + delta + off + i] = L.at(F, i);
+        }
+    }
+    wr(dir, "p_out", p);
   } else if (op == "fill_hash") {
     const int nhalo = (int)num(5);
     std::vector<T> p((size_t)(n1 + 2 * nhalo) * (n2 + 2 * nhalo) * (n3 + 2 * nhalo), (T)7);

@@ -112,3 +112,26 @@ def test_fill_hash_kernel(tmp_path, nhalo):
     inner = (slice(nhalo, shp[0] - nhalo), slice(nhalo, shp[1] - nhalo), slice(nhalo, shp[2] - nhalo))
     ref[inner] = O.hash_field(ngl, 4242, lo=lo, n=n)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("walls", [False, True])
+@pytest.mark.parametrize("ng,dt", SHAPES, ids=IDS)
+def test_fused_fill_source(tmp_path, ng, dt, walls):
+    """R2Fill / R2FillLine (cans_b200/csrc/r2_fill.cuh): what the loads of the fused forward x transform evaluate
+    (`cansb200_solve_fillps`) == fillps followed by updt_rhs_b, on two z chunks of the slab, with a face-centred wall."""
+    cf, cbc = ["c", "c", "f"], [["D", "D"], ["N", "N"], ["N", "D"]]
+    cs = O.make_case(ng, [2.0, 1.0, 1.5], [["P", "P"], ["N", "N"], ["D", "D"]], gr=1.0, dtype=dt)
+    f = _fields(ng, dt, tmp_path, "uvw")
+    cs["dzfi"].tofile(os.path.join(tmp_path, "dzfi.bin"))
+    dti = dt(1.0 / 0.37)
+    ref = np.full(f["u"].shape, 3.25, dtype=dt)
+    O.fillps(ng, cs["dli"], cs["dzfi"], dti, f["u"], f["v"], f["w"], ref)
+    idx, vals = [0] * 6, [0.0] * 6
+    if walls:
+        rh = [[0.3, -0.7], [0.11, 0.05], [-0.4, 0.9]]
+        O.updt_rhs_b(cf, cbc, ng, rh[0], rh[1], rh[2], ref)
+        q = [1 if (cf[d] == "f" and cbc[d][1] == "D") else 0 for d in range(3)]
+        idx = [v for d in range(3) for v in (1, ng[d] - q[d])]
+        vals = [float(dt(rh[d][s])) for d in range(3) for s in range(2)]
+    _emu(dt, "fill_source", ng, tmp_path, cs["dli"][0], cs["dli"][1], dti, *idx, *vals, max(1, ng[2] // 3))
+    assert np.array_equal(_read(tmp_path, "p_out", ref.shape, dt), ref)
