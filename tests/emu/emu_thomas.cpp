@@ -7,6 +7,8 @@
 //
 // usage: emu_thomas <f64|f32> nx ny nz n_rows periodic nopin dedup_x dedup_y norm dir
 //        reads p.bin [nz][ny][nx], lam.bin [ny][nx], a.bin b.bin c.bin [>= n_rows]; writes p_out.bin
+//        emu_thomas dtdma <f64|f32> nx ny nz n_rows periodic has_lam norm dir nsplit start_0 .. start_nsplit
+//        the same files through the four kernels of dtdma_kernels.cuh (gaussel_dtdma, src/solver.f90:309-517)
 // TEST INFRASTRUCTURE.
 #include <cmath>
 #include <cstdio>
@@ -49,6 +51,7 @@ template <class T> static T __ldg(const T* p) { return *p; }
 #define __launch_bounds__(...)
 
 #include "../../cans_b200/csrc/thomas_kernels.cuh"
+#include "../../cans_b200/csrc/dtdma_kernels.cuh"
 
 using namespace cb;
 
@@ -101,7 +104,45 @@ template <class T> static int run(int nx, int ny, int nz, int n_rows, int period
   return 0;
 }
 
+// gaussel_dtdma (src/solver.f90:309-517) with the z slabs of `nsplit` ranks in one address space: the four kernels of
+// dtdma_kernels.cuh driven as capi.cu's gaussel_dtdma_impl drives them (cansb200_gaussel_dtdma, no coefficient cache)
+template <class T> static int run_dtdma(int nx, int ny, int nz, int n_rows, int periodic, int has_lam, double norm, const std::string& dir,
+                                        int nsplit, char** sv) {
+  auto p = rd<T>(dir, "p", (size_t)nx * ny * nz);
+  std::vector<T> lam;
+  if (has_lam) lam = rd<T>(dir, "lam", (size_t)nx * ny);
+  auto a = rd<T>(dir, "a", n_rows), b = rd<T>(dir, "b", n_rows), c = rd<T>(dir, "c", n_rows);
+  const size_t ncol = (size_t)nx * ny;
+  std::vector<T> big(3 * ncol * n_rows, (T)NAN), sm((size_t)(11 * nsplit) * ncol, (T)NAN);
+  DtdmaDev<T> D;
+  D.nx = nx; D.ny = ny; D.n = n_rows; D.nranks = nsplit; D.periodic = periodic;
+  for (int r = 0; r <= nsplit; ++r) D.starts[r] = atoi(sv[r]);
+  D.a = a.data(); D.b = b.data(); D.c = c.data(); D.lam = has_lam ? lam.data() : nullptr;
+  D.st = nullptr; D.slot_big = 0; D.slot_small = 0;
+  D.Z = big.data(); D.AA = big.data() + ncol * n_rows; D.CC = big.data() + 2 * ncol * n_rows;
+  D.Z1 = sm.data();
+  D.ra = sm.data() + ncol * nsplit; D.rc = D.ra + 2 * ncol * nsplit; D.rcw = D.rc + 2 * ncol * nsplit;
+  D.rp = D.rcw + 2 * ncol * nsplit; D.rp2 = D.rp + 2 * ncol * nsplit;
+  const unsigned cbk = (unsigned)((ncol + 127) / 128);
+  launch(cbk, 128, [&] { dtdma_coef_kernel<T>(D); });
+  launch(cbk, 128, [&] { dtdma_phase1_kernel<T>(D, p.data(), (T)norm); });
+  launch(cbk, 128, [&] { dtdma_reduced_kernel<T>(D); });
+  launch(7, 256, [&] { dtdma_phase3_kernel<T>(D, p.data()); });
+  FILE* f = fopen((dir + "/p_out.bin").c_str(), "wb");
+  if (!f || fwrite(p.data(), sizeof(T), p.size(), f) != p.size()) return 2;
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 13 && std::string(argv[1]) == "dtdma") {
+    // emu_thomas dtdma <f64|f32> nx ny nz n_rows periodic has_lam norm dir nsplit start_0 .. start_nsplit
+    const int nsplit = atoi(argv[11]);
+    if (argc < 13 + nsplit) { fprintf(stderr, "emu_thomas dtdma: missing split starts\n"); return 2; }
+    const int v[6] = {atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8])};
+    return std::string(argv[2]) == "f32" ? run_dtdma<float>(v[0], v[1], v[2], v[3], v[4], v[5], atof(argv[9]), argv[10], nsplit, argv + 12)
+                                         : run_dtdma<double>(v[0], v[1], v[2], v[3], v[4], v[5], atof(argv[9]), argv[10], nsplit, argv + 12);
+  }
   if (argc < 12) { fprintf(stderr, "usage: emu_thomas <f64|f32> nx ny nz n_rows periodic nopin dedup_x dedup_y norm dir\n"); return 2; }
   const int v[8] = {atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]), atoi(argv[9])};
   const double norm = atof(argv[10]);

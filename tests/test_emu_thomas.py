@@ -85,3 +85,38 @@ def test_deduplicated_pivot_cache(tmp_path, dedx, dedy, per):
     _emu(np.float64, nx, ny, nz, nz, per, 0, dedx, dedy, cs["normfft"], tmp_path)
     got = np.fromfile(os.path.join(tmp_path, "p_out.bin"), dtype=np.float64).reshape(pz.shape)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("name,nsplit", [("C3s_channel", 2), ("C3s_channel", 4), ("C4s_duct", 3), ("periodic_z_odd", 3),
+                                         ("C2s_triperiodic", 4), ("helm_w_face_z", 2), ("fp32_channel", 4), ("C1_ldc_2x64x64", 1)])
+def test_distributed_tdma_kernels_are_bit_identical_to_gaussel_dtdma(tmp_path, name, nsplit):
+    """The four kernels of dtdma_kernels.cuh, driven as `cansb200_gaussel_dtdma` drives them, against the oracle's
+    `gaussel_dtdma` (src/solver.f90:309-517): slab-wise elimination, reduced 2-rows-per-rank system (periodic closure
+    included), update -- even and uneven z splits, with and without lambdaxy."""
+    from cans_b200.decomp import split_starts
+    if not os.path.exists(EMU):
+        pytest.skip("tests/_build/emu_thomas was not built")
+    cs = cases.build_case(name)
+    ng, dt = cs["ng"], cs["dtype"]
+    helm = name in cases.HELMHOLTZ
+    a, c = cs["a"], cs["c"]
+    b = (cs["b"] + dt(1.0 / cases.ALPHA if helm else 0.0)).astype(dt)
+    lam = (cs["lambdaxy"] - dt(0.0 if helm or not cases.is_singular(cs) else 0.37)).astype(dt)   # regular columns
+    per = cs["cbc"][2] == cases.P
+    q = 1 if (cs["c_or_f"][2] == "f" and cs["cbc"][2][1] == "D") else 0
+    n = ng[2] - q
+    starts = split_starts(ng[2], nsplit)
+    rng = np.random.default_rng(29)
+    pz = rng.uniform(-1, 1, (ng[2], ng[1], ng[0])).astype(dt)
+    norm = 0.61
+    for use_lam, bb in ((True, b), (False, (b - dt(3.0)).astype(dt))):
+        ref = pz.copy()
+        O.gaussel_dtdma(starts, n, a, bb, c, per, norm, ref, lam if use_lam else None)
+        for nm, arr in (("p", pz), ("lam", lam), ("a", a), ("b", bb), ("c", c)):
+            np.ascontiguousarray(arr).tofile(os.path.join(tmp_path, nm + ".bin"))
+        r = subprocess.run([EMU, "dtdma", "f32" if dt == np.float32 else "f64", str(ng[0]), str(ng[1]), str(ng[2]), str(n),
+                            str(int(per)), str(int(use_lam)), repr(norm), str(tmp_path), str(nsplit)] + [str(v) for v in starts],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        got = np.fromfile(os.path.join(tmp_path, "p_out.bin"), dtype=dt).reshape(pz.shape)
+        assert np.array_equal(got, ref), f"{name} lam={use_lam}: rel L2 {cases.rel_l2(got, ref):.2e}"
