@@ -274,7 +274,11 @@ template <class T, class Cfg, bool YMODE> struct R2Lay {
 };
 
 template <int ID, int CNT> __device__ __forceinline__ void r2_named_bar() {
+#if defined(CB_EMU_HOST)   // tests/emu/emu_r2r2.cpp: the kernels' source under g++, CUDA threads as host threads
+  cb_emu_named_bar(ID, CNT);
+#else
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(CNT) : "memory");
+#endif
 }
 // barrier among the TPL threads of one transform.  Barrier ids are compile-time constants so that
 // ptxas reserves G + 1 hardware barriers per CTA, not all 16 (which would cap the CTAs per SM at 4).
