@@ -70,7 +70,7 @@ def test_x_plans(tmp_path, n, var):
     _check(np.float64, "x", n, var, shape, tmp_path)
 
 
-@pytest.mark.parametrize("n,var,nx", [(n, v, 20) for n, v in Y_PLANS] + [(n, v, 32) for n, v in Y_PLANS if v in (0, 3)])
+@pytest.mark.parametrize("n,var,nx", [(n, v, 20 if n < 1024 else 12) for n, v in Y_PLANS] + [(n, v, 32) for n, v in Y_PLANS if v in (0, 3) and n < 1024])
 def test_y_plans(tmp_path, n, var, nx):
     """strided lines; 20 columns = a ragged last tile (predicated kernels), 32 = whole tiles (unpredicated kernels)"""
     shape = (1, n, nx)
@@ -81,7 +81,7 @@ def test_y_plans(tmp_path, n, var, nx):
 
 @pytest.mark.parametrize("n,var", Y32_PLANS)
 def test_y_plans_fp32(tmp_path, n, var):
-    shape = (1, n, 40)
+    shape = (1, n, 40 if n < 1024 else 24)
     _input(np.float32, shape, tmp_path, n + var)
     _emu(np.float32, "y", n, var, shape, tmp_path)
     _check(np.float32, "y", n, var, shape, tmp_path)
@@ -120,7 +120,7 @@ def test_y_plans_through_a_row_table(tmp_path, n, var):
     """SPLIT kernels (the exchange of the distributed solve): forward kinds store result row j of plane g at
     table[j].ptr + g * table[j].gs, backward kinds load their input rows from there.  The far side here is laid out like the
     way-back buffer, [row][plane][x], with the rows dealt out in a scrambled order."""
-    nx, nz = 24, 2
+    nx, nz = (24 if n < 1024 else 8), 2
     shape = (nz, n, nx)
     _input(np.float64, shape, tmp_path, 11 * n + var)
     perm = np.random.default_rng(n).permutation(n)
