@@ -115,7 +115,7 @@ def test_x_split_order(tmp_path, n, var):
     _check(np.float64, "x", n, var, shape, tmp_path, ref_of=ref_of)
 
 
-@pytest.mark.parametrize("n,var", Y_PLANS)
+@pytest.mark.parametrize("n,var", [p for p in Y_PLANS if p[1] in (0, 3)])   # the plans run_r2r picks by default
 def test_y_plans_through_a_row_table(tmp_path, n, var):
     """SPLIT kernels (the exchange of the distributed solve): forward kinds store result row j of plane g at
     table[j].ptr + g * table[j].gs, backward kinds load their input rows from there.  The far side here is laid out like the
