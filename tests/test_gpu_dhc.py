@@ -1,7 +1,5 @@
-#!/usr/bin/env python
-"""GPU check (a script, NOT collected by pytest: it has not been run on a B200 yet -- the round's GPU budget ran out):
-the reference's differentially-heated-cavity case replayed with the CUDA solver as the Poisson solve.
-Run on a GPU box: python tests/gpu_dhc_check.py
+"""GPU, opt-in (CANSB200_LONG_TESTS=1; written after the round's GPU budget was spent, so it has not run on a B200 yet and is
+skipped by default): the reference's differentially-heated-cavity case replayed with the CUDA solver as the Poisson solve.
 
 Same loop as tests/test_dhc_golden.py (oracle/dhc_replay.py restates the CaNS time step with one scalar and Boussinesq
 buoyancy); every pressure solve goes through `cansb200_solve` (C ABI, device pointers).  On the solver path this case has
@@ -9,19 +7,22 @@ REDFT10 / REDFT01 along x (n = 128) -- the lid-driven cavity has them along y on
 Nusselt number) take ten minutes of host time; here the first steps are held to the oracle's own replay, tightly."""
 import importlib
 
-import numpy as np
 import os
-import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
+import numpy as np
+import pytest
 
 from oracle import cans_oracle as O
 from oracle import dhc_replay as D
 
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("CANSB200_LONG_TESTS") != "1", reason="opt-in: set CANSB200_LONG_TESTS=1")]
+torch = pytest.importorskip("torch")
 
-def main():
-    assert torch.cuda.is_available(), "needs a CUDA device; the product path has no CPU fallback"
+
+def test_cuda_solver_follows_the_oracle_on_the_dhc_case():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device; the product path has no CPU fallback")
     cb = importlib.import_module("cans_b200")
     cfg = D.DHC
     dev = torch.device("cuda:0")
@@ -43,8 +44,3 @@ def main():
     np.testing.assert_allclose(nu_g, nu_c, rtol=1e-11)
     for k in ("s", "u", "w"):
         np.testing.assert_allclose(st_g[k], st_c[k], rtol=1e-9, atol=1e-13)
-    print(f"dhc: {nstep} steps, Nusselt CUDA = {nu_g!r}, oracle = {nu_c!r}: ok")
-
-
-if __name__ == "__main__":
-    main()
