@@ -2,12 +2,14 @@
 // WHICH factorisation a solve uses -- `thomas_hash_kernel` (two independent content hashes of (a, b, c, lambdaxy), mirror-
 // symmetry check of lambdaxy for the deduplicated cache) and `thomas_select_kernel` (slot look-up, LRU eviction) of
 // cans_b200/csrc/thomas_kernels.cuh -- and of `chkdiv_kernel` (aux_kernels.cuh: the acceptance metric, warp-shuffle
-// reduction + atomics).  The kernels' own source under g++, launched as capi.cu launches them.
+// reduction + atomics), and of `r2r_direct_kernel` (fft_kernels.cuh: the O(n^2) transform of lengths / kinds no fast kernel
+// serves).  The kernels' own source under g++, launched as capi.cu launches them.
 //
 // usage: emu_cache cache nx ny n nslots nsets dir flags...   set_<s>_{a,b,c,lam}.bin, one line "hit sel nfactor sym_bad key key2"
 //                                                            per entry of the sequence given as the trailing arguments
 //                                                            (each: "<set>:<nopin><dx><dy>", e.g. 0:000)
 //        emu_cache chkdiv <f64|f32> n1 n2 n3 dxi dyi dir     u v w dzfi -> prints "sum max"
+//        emu_cache direct <f64|f32> kind n axis nx ny nz dir arr.bin -> out.bin
 // TEST INFRASTRUCTURE.
 #include "emu_threads.hpp"
 static inline double __dmul_rn(double a, double b) { return a * b; }
@@ -25,6 +27,8 @@ static inline void __trap() {}
 #include <cuda.h>
 #include "../../cans_b200/csrc/aux_kernels.cuh"
 #include "../../cans_b200/csrc/thomas_kernels.cuh"
+#include "../../cans_b200/csrc/fft_kernels.cuh"
+#include "../../cans_b200/csrc/fft_plan.hpp"
 
 using namespace cb;
 
@@ -78,7 +82,31 @@ template <class T> static int run_chkdiv(int n1, int n2, int n3, double dxi, dou
   return 0;
 }
 
+// r2r_direct_kernel (fft_kernels.cuh): the O(n^2) evaluation every transform falls back to when neither the two-for-one
+// kernels nor the generic engine serve its length / kind (prime n, REDFT00 / 11, RODFT00 / 11 of awkward lengths); set up as
+// run_r2r (capi.cu) sets it up.  arr.bin (nz, ny, nx) -> out.bin
+template <class T> static int run_direct(int kind, int n, int axis, int nx, int ny, int nz, const std::string& dir) {
+  auto arr = rd<T>(dir, "arr", (size_t)nx * ny * nz);
+  const int Q = slow_Q(n, kind);
+  std::vector<C2<T>> cs(2 * (size_t)Q);
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (long long m = 0; m < 2LL * Q; ++m) cs[m] = {(T)cosl(pi * m / Q), (T)sinl(pi * m / Q)};
+  DirectArgs<T> D;
+  D.n = n; D.kind = kind; D.Q = Q; D.cs = cs.data(); D.in = arr.data(); D.out = arr.data();
+  if (axis == 0) { D.in_es = D.out_es = 1; D.in_ls = D.out_ls = nx; D.lines_per_group = ny; D.line_len = nx; }
+  else { D.in_es = D.out_es = nx; D.in_ls = D.out_ls = 1; D.lines_per_group = nx; D.line_len = ny; }
+  D.in_gs = D.out_gs = (long long)nx * ny; D.ngroups = nz;
+  launch((unsigned)((long long)D.lines_per_group * nz), 128, r2r_direct_kernel<T>, D);
+  wr(dir, "out", arr);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 10 && std::string(argv[1]) == "direct") {   // emu_cache direct <f64|f32> kind n axis nx ny nz dir
+    const bool f32 = std::string(argv[2]) == "f32";
+    const int v[6] = {atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8])};
+    return f32 ? run_direct<float>(v[0], v[1], v[2], v[3], v[4], v[5], argv[9]) : run_direct<double>(v[0], v[1], v[2], v[3], v[4], v[5], argv[9]);
+  }
   if (argc >= 9 && std::string(argv[1]) == "cache") return run_cache(argc, argv);
   if (argc >= 9 && std::string(argv[1]) == "chkdiv") {
     const bool f32 = std::string(argv[2]) == "f32";

@@ -104,3 +104,28 @@ def test_chkdiv_kernel(tmp_path, ng, dt):
     tot_o, max_o = O.chkdiv(ng, l, cs["dli"], cs["dzfi"], *uvw)
     assert mx == max_o                                   # same expression, same order: the maximum is bit-exact
     assert tot / (l[0] * l[1] * l[2]) == pytest.approx(tot_o, rel=1e-13 if dt == np.float64 else 1e-5)
+
+
+R2R_KINDS = {"R2HC": 0, "HC2R": 1, "REDFT00": 3, "REDFT01": 4, "REDFT10": 5, "REDFT11": 6,
+             "RODFT00": 7, "RODFT01": 8, "RODFT10": 9, "RODFT11": 10}
+
+
+@pytest.mark.parametrize("kname", sorted(R2R_KINDS))
+@pytest.mark.parametrize("n,axis", [(2, 0), (3, 1), (7, 0), (17, 1), (30, 0), (31, 1)])
+def test_direct_transform_kernel(tmp_path, kname, n, axis):
+    """r2r_direct_kernel: every FFTW kind the reference can plan (src/fft.f90:260-313), odd / prime lengths, both axes, and a
+    line longer than the transform (the face-centred Dirichlet case transforms n - 1 points and copies the last one)"""
+    kind = R2R_KINDS[kname]
+    if kname == "REDFT00" and n < 2:
+        pytest.skip("REDFT00 needs n >= 2")
+    ll = n + (1 if n % 2 else 0)                      # odd n: one untransformed tail point
+    shape = (2, 3, ll) if axis == 0 else (2, ll, 5)
+    x = np.random.default_rng(n * 31 + kind).uniform(-1, 1, shape)
+    x.tofile(os.path.join(tmp_path, "arr.bin"))
+    _run("direct", "f64", kind, n, axis, shape[2], shape[1], shape[0], tmp_path)
+    got = np.fromfile(os.path.join(tmp_path, "out.bin"), dtype=np.float64).reshape(shape)
+    ref = x.copy()
+    sl = [slice(None)] * 3
+    sl[2 - axis] = slice(0, n)
+    ref[tuple(sl)] = O.r2r_1d(np.ascontiguousarray(x[tuple(sl)]), kind, axis=2 - axis)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-14 * max(1.0, np.log2(n))
